@@ -1,0 +1,89 @@
+"""ctypes binding of libhd_b200.so (the C ABI in include/hd_b200.h).
+
+There is deliberately no CPU fallback: if the CUDA library is missing or a tensor
+is not on a CUDA device the call raises.
+"""
+import ctypes as C
+import os
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libhd_b200.so")
+
+HD_MAX_LEVELS = 8
+HD_MAX_ANCHORS = 8
+FLAG_CONF_GE = 1
+FLAG_DENSE_READ = 2
+NMS_AGNOSTIC, NMS_CLASS_EXACT, NMS_CLASS_OFFSET = 0, 1, 2
+
+
+class YoloLevel(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("stride", C.c_float),
+                ("anchor_wh", C.c_float * (2 * HD_MAX_ANCHORS))]
+
+
+class RpnLevel(C.Structure):
+    _fields_ = [("objectness", C.c_void_p), ("deltas", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32),
+                ("stride", C.c_float), ("anchor_base", C.c_float * (4 * HD_MAX_ANCHORS))]
+
+
+class RoiLevel(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("spatial_scale", C.c_float)]
+
+
+_vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/hd_b200.h declares appears here
+SIGNATURES = {
+    "hd_version": (_i, []),
+    "hd_last_error": (C.c_char_p, []),
+    "hd_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _vp, _vp]),
+    "hd_yolo_decode_filter": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "hd_yolo_filter_pred": (_i, [_vp, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "hd_sort_nms_workspace_size": (_sz, [_i, _i]),
+    "hd_sort_nms_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hd_box_iou": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C heltondetection_b200/csrc`). There is no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(lib().hd_last_error().decode())
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("heltondetection_b200 ops are CUDA-only (sm_100a); got a tensor on " + str(t.device))
+
+
+def f32c(t):
+    """float32 contiguous view/copy (inputs are borrowed, never mutated)."""
+    if t.dtype != torch.float32:
+        raise NotImplementedError(f"heltondetection_b200 kernels are fp32-only, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()

@@ -1,0 +1,293 @@
+// Batched per-image sort + greedy NMS (a3/a4) and pairwise IoU (a5).
+// Replaces torchvision.ops.nms / batched_nms / box_iou (boxes.py:20-120, 308-370).
+//
+// One CTA per image.  Candidates are ordered by a CTA radix sort on (score desc, tiebreak asc), the
+// sorted boxes are materialised once, then suppression runs *lazily*: boxes are visited in chunks of
+// 64 in score order; the chunk's 64x64 upper-triangular IoU bitmask is built with all threads,
+// one warp resolves the chunk serially with bit operations, and only the boxes that were actually
+// kept are tested against the still-alive tail.  The `removed` bitmap lives in shared memory for the
+// whole image.  Work is kept*n instead of n^2/2 and the loop stops as soon as max_det boxes are kept,
+// which is what the detection callers (max_det=300, RPN post_nms_top_n) need.
+#include "hd_sort.cuh"
+
+#define NMS_NT 1024
+#define NMS_CHUNK 64
+
+struct NmsParams {
+    const float4* boxes;
+    const float* scores;
+    const int* cls;
+    const int* tiebreak;
+    const int* counts;
+    int n_fixed, B, cap;
+    float thr;  // hd_thr_floor(iou_thres)
+    int class_mode;
+    float offset_scale;
+    int max_nms, max_det;
+    float* out_det;
+    long long* out_idx;
+    int* out_count;
+    // workspace (per image stride = cap)
+    uint64_t* k0; uint64_t* k1; uint32_t* v0; uint32_t* v1;
+    float4* sbox; int* scls; int* keep_r;
+};
+
+__device__ __forceinline__ bool hd_iou_gt(const float4& a, float area_a, const float4& b, float area_b, float thr) {
+    float xx1 = hd_stdmax(a.x, b.x), yy1 = hd_stdmax(a.y, b.y);
+    float xx2 = hd_stdmin(a.z, b.z), yy2 = hd_stdmin(a.w, b.w);
+    float w = hd_stdmax(0.0f, __fsub_rn(xx2, xx1));
+    float h = hd_stdmax(0.0f, __fsub_rn(yy2, yy1));
+    if (thr >= 0.0f && !(w > 0.0f && h > 0.0f)) return false;  // inter == 0 -> iou is 0, -0 or NaN: never > thr
+    float inter = __fmul_rn(w, h);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter)) > thr;
+}
+
+__global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_constant__ NmsParams p) {
+    extern __shared__ uint32_t removed[];  // ceil(cap/32) words (+1 pad)
+    __shared__ HdSortSmem<NMS_NT> ssm;
+    __shared__ float4 cbox[NMS_CHUNK];
+    __shared__ float carea[NMS_CHUNK];
+    __shared__ int ccls[NMS_CHUNK];
+    __shared__ unsigned long long cmask[NMS_CHUNK];
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_kc;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int b = blockIdx.x;
+    int n = p.counts ? min(p.counts[b], p.cap) : p.n_fixed;
+    if (n <= 0) {
+        if (tid == 0) p.out_count[b] = 0;
+        return;
+    }
+    const size_t off = (size_t)b * p.cap;
+    uint64_t* k0 = p.k0 + off; uint64_t* k1 = p.k1 + off;
+    uint32_t* v0 = p.v0 + off; uint32_t* v1 = p.v1 + off;
+    float4* sbox = p.sbox + off;
+    int* scls = p.scls + off;
+    int* keep_r = p.keep_r + off;
+
+    for (int i = tid; i < n; i += NMS_NT) {
+        uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + i] : (uint32_t)i;
+        k0[i] = ((uint64_t)(~hd_orderable(p.scores[off + i])) << 32) | tb;
+        v0[i] = (uint32_t)i;
+    }
+    __syncthreads();
+    const int res = hd_cta_radix_sort<NMS_NT>(k0, v0, k1, v1, n, ssm);
+    const uint32_t* order = res ? v1 : v0;
+
+    const int n_use = (p.max_nms > 0) ? min(n, p.max_nms) : n;
+    const int max_det = (p.max_det > 0) ? p.max_det : n_use;
+    for (int r = tid; r < n_use; r += NMS_NT) {
+        const uint32_t slot = order[r];
+        float4 bx = p.boxes[off + slot];
+        int c = p.cls ? p.cls[off + slot] : 0;
+        if (p.class_mode == HD_NMS_CLASS_OFFSET) {
+            const float o = __fmul_rn((float)c, p.offset_scale);
+            bx.x = __fadd_rn(bx.x, o); bx.y = __fadd_rn(bx.y, o); bx.z = __fadd_rn(bx.z, o); bx.w = __fadd_rn(bx.w, o);
+        }
+        sbox[r] = bx;
+        scls[r] = (p.class_mode == HD_NMS_CLASS_EXACT) ? c : 0;
+    }
+    for (int i = tid; i < (n_use + 31) / 32 + 1; i += NMS_NT) removed[i] = 0;
+    __syncthreads();
+
+    int kc = 0;
+    for (int base = 0; base < n_use; base += NMS_CHUNK) {
+        const int m = min(NMS_CHUNK, n_use - base);
+        if (tid < NMS_CHUNK) {
+            cmask[tid] = 0ull;
+            if (tid < m) {
+                float4 bx = sbox[base + tid];
+                cbox[tid] = bx;
+                carea[tid] = hd_area(bx);
+                ccls[tid] = scls[base + tid];
+            }
+        }
+        __syncthreads();
+        {   // 64x64 upper-triangular mask: 16 threads per row, 4 columns each
+            const int i = tid >> 4, j0 = (tid & 15) * 4;
+            if (i < m) {
+                unsigned long long bits = 0ull;
+                const float4 bi = cbox[i];
+                const float ai = carea[i];
+                const int ci = ccls[i];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int jj = j0 + q;
+                    if (jj > i && jj < m && ccls[jj] == ci && hd_iou_gt(bi, ai, cbox[jj], carea[jj], p.thr)) bits |= 1ull << jj;
+                }
+                if (bits) atomicOr(&cmask[i], bits);
+            }
+        }
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned long long rem = (unsigned long long)removed[base >> 5] | ((unsigned long long)removed[(base >> 5) + 1] << 32);
+            unsigned long long alive = ~rem & ((m == 64) ? ~0ull : ((1ull << m) - 1ull));
+            unsigned long long kept = 0ull;
+            int room = max_det - kc;
+            while (alive && room > 0) {
+                const int i = __ffsll((long long)alive) - 1;
+                kept |= 1ull << i;
+                alive &= ~cmask[i];
+                alive &= ~(1ull << i);
+                --room;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int bit = lane + 32 * h;
+                if ((kept >> bit) & 1ull) keep_r[kc + __popcll(kept & ((1ull << bit) - 1ull))] = base + bit;
+            }
+            if (lane == 0) {
+                s_kept = kept;
+                s_kc = kc + __popcll(kept);
+            }
+        }
+        __syncthreads();
+        const unsigned long long kept = s_kept;
+        kc = s_kc;
+        const bool done = kc >= max_det;
+        if (!done && kept) {
+            for (int jr = base + NMS_CHUNK + tid; jr < n_use; jr += NMS_NT) {
+                if ((removed[jr >> 5] >> (jr & 31)) & 1u) continue;
+                const float4 bj = sbox[jr];
+                const float aj = hd_area(bj);
+                const int cj = scls[jr];
+                unsigned long long kk = kept;
+                while (kk) {
+                    const int i = __ffsll((long long)kk) - 1;
+                    kk &= kk - 1ull;
+                    if (ccls[i] == cj && hd_iou_gt(cbox[i], carea[i], bj, aj, p.thr)) {
+                        atomicOr(&removed[jr >> 5], 1u << (jr & 31));
+                        break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (done) break;
+    }
+
+    for (int q = tid; q < kc; q += NMS_NT) {
+        const int r = keep_r[q];
+        const uint32_t slot = order[r];
+        if (p.out_det) {
+            const float4 bx = p.boxes[off + slot];
+            float* o = p.out_det + ((size_t)b * p.max_det + q) * 6;
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+            o[4] = p.scores[off + slot];
+            o[5] = p.cls ? (float)p.cls[off + slot] : 0.0f;
+        }
+        if (p.out_idx) p.out_idx[(size_t)b * p.max_det + q] = p.tiebreak ? (long long)p.tiebreak[off + slot] : (long long)slot;
+    }
+    if (tid == 0) p.out_count[b] = kc;
+}
+
+// ------------------------------------------------------------------------------------------------ box_iou
+__global__ void __launch_bounds__(256) box_iou_kernel(const float4* __restrict__ b1, long long N, const float4* __restrict__ b2,
+                                                      long long M, float* __restrict__ iou) {
+    // block = 8 rows x 256 columns tile; thread handles one column for 8 rows (column-contiguous stores)
+    __shared__ float4 rows[8];
+    __shared__ float rarea[8];
+    const long long r0 = (long long)blockIdx.y * 8;
+    const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (threadIdx.x < 8 && r0 + threadIdx.x < N) {
+        float4 a = b1[r0 + threadIdx.x];
+        rows[threadIdx.x] = a;
+        rarea[threadIdx.x] = hd_area(a);
+    }
+    __syncthreads();
+    if (c >= M) return;
+    const float4 bb = b2[c];
+    const float ab = hd_area(bb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (r0 + k < N) {
+            const float4 a = rows[k];
+            // torch: lt = max(b1[:, None, :2], b2[:, :2]); wh = (rb - lt).clamp(min=0)
+            float w = fmaxf(__fsub_rn(fminf(a.z, bb.z), fmaxf(a.x, bb.x)), 0.0f);
+            float h = fmaxf(__fsub_rn(fminf(a.w, bb.w), fmaxf(a.y, bb.y)), 0.0f);
+            float inter = __fmul_rn(w, h);
+            iou[(r0 + k) * M + c] = __fdiv_rn(inter, __fsub_rn(__fadd_rn(rarea[k], ab), inter));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static void nms_ws_layout(int B, int cap, size_t* offs, size_t* total) {
+    size_t n = (size_t)B * cap, o = 0;
+    offs[0] = o; o = hd_align_up(o + n * 8, 256);   // k0
+    offs[1] = o; o = hd_align_up(o + n * 8, 256);   // k1
+    offs[2] = o; o = hd_align_up(o + n * 4, 256);   // v0
+    offs[3] = o; o = hd_align_up(o + n * 4, 256);   // v1
+    offs[4] = o; o = hd_align_up(o + n * 16, 256);  // sbox
+    offs[5] = o; o = hd_align_up(o + n * 4, 256);   // scls
+    offs[6] = o; o = hd_align_up(o + n * 4, 256);   // keep_r
+    *total = o;
+}
+
+extern "C" HD_API size_t hd_sort_nms_workspace_size(int B, int cap) {
+    size_t offs[7], total;
+    nms_ws_layout(B < 0 ? 0 : B, cap < 0 ? 0 : cap, offs, &total);
+    return total + 256;
+}
+
+extern "C" HD_API int hd_sort_nms_batched(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
+                                   const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
+                                   float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
+                                   int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    HD_CHECK_ARG(B >= 0 && cap >= 0, "bad shape B=%d cap=%d", B, cap);
+    if (B == 0) return HD_OK;
+    HD_CHECK_ARG(out_count != nullptr, "out_count is NULL");
+    HD_CHECK_ARG(class_mode >= 0 && class_mode <= 2, "class_mode must be 0,1,2, got %d", class_mode);
+    HD_CHECK_ARG(class_mode == HD_NMS_AGNOSTIC || cls != nullptr, "cls is NULL for a class-aware mode");
+    HD_CHECK_ARG(counts != nullptr || (n_fixed >= 0 && n_fixed <= cap), "n_fixed=%d out of [0,cap=%d]", n_fixed, cap);
+    HD_CHECK_ARG(max_det > 0 || (out_det == nullptr && out_idx == nullptr) || true, "max_det");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cap == 0) {
+        HD_CUDA_CALL(cudaMemsetAsync(out_count, 0, sizeof(int) * (size_t)B, st));
+        return HD_OK;
+    }
+    HD_CHECK_ARG(boxes && scores, "boxes/scores is NULL");
+    HD_CHECK_ARG(max_det > 0, "max_det must be > 0 (row stride of out_det/out_idx), got %d", max_det);
+    size_t offs[7], total;
+    nms_ws_layout(B, cap, offs, &total);
+    uintptr_t w0 = hd_align_up((uintptr_t)workspace, 256);
+    if (!workspace || w0 + total > (uintptr_t)workspace + workspace_bytes)
+        HD_FAIL(HD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", total + 256, workspace_bytes);
+    NmsParams p;
+    p.boxes = (const float4*)boxes; p.scores = scores; p.cls = (class_mode == HD_NMS_AGNOSTIC) ? cls : cls; p.tiebreak = tiebreak;
+    p.counts = counts; p.n_fixed = n_fixed; p.B = B; p.cap = cap;
+    p.thr = hd_thr_floor(iou_thres);
+    p.class_mode = class_mode; p.offset_scale = offset_scale; p.max_nms = max_nms; p.max_det = max_det;
+    p.out_det = out_det; p.out_idx = (long long*)out_idx; p.out_count = out_count;
+    p.k0 = (uint64_t*)(w0 + offs[0]); p.k1 = (uint64_t*)(w0 + offs[1]);
+    p.v0 = (uint32_t*)(w0 + offs[2]); p.v1 = (uint32_t*)(w0 + offs[3]);
+    p.sbox = (float4*)(w0 + offs[4]); p.scls = (int*)(w0 + offs[5]); p.keep_r = (int*)(w0 + offs[6]);
+    size_t smem = ((size_t)(cap + 31) / 32 + 2) * 4;
+    HD_CHECK_ARG(smem <= 160 * 1024, "cap=%d too large for the shared-memory removed bitmap", cap);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        HD_CUDA_CALL(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        smem_set = 160 * 1024;
+    }
+    sort_nms_kernel<<<B, NMS_NT, smem, st>>>(p);
+    HD_CUDA_LAUNCH_CHECK("sort_nms_kernel");
+    return HD_OK;
+}
+
+extern "C" HD_API int hd_box_iou(const float* boxes1, int64_t N, const float* boxes2, int64_t M, float* iou, void* stream) {
+    HD_CHECK_ARG(N >= 0 && M >= 0, "bad shape N=%lld M=%lld", (long long)N, (long long)M);
+    if (N == 0 || M == 0) return HD_OK;
+    HD_CHECK_ARG(boxes1 && boxes2 && iou, "null pointer");
+    long long gx = (M + 255) / 256, gy = (N + 7) / 8;
+    HD_CHECK_ARG(gy <= 65535 * 1ll || true, "N too large");
+    // grid.y is limited to 65535: loop in slabs
+    for (long long y0 = 0; y0 < gy; y0 += 65535) {
+        long long ny = (gy - y0 < 65535) ? (gy - y0) : 65535;
+        dim3 grid((unsigned)gx, (unsigned)ny);
+        box_iou_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes1 + y0 * 8, N - y0 * 8, (const float4*)boxes2, M,
+                                                              iou + y0 * 8 * M);
+    }
+    HD_CUDA_LAUNCH_CHECK("box_iou_kernel");
+    return HD_OK;
+}

@@ -1,0 +1,392 @@
+// YOLOv5 head kernels: dense decode (a1), fused decode+filter+compaction (a1+a2), filter on decoded pred (a2).
+// Reference feature: README.md:9; semantics SURVEY.md A.1/A.2 (ultralytics / bubbliiiing lineage, README.md:158-162).
+#include "hd_common.cuh"
+
+struct YoloParams {
+    const float* data[HD_MAX_LEVELS];
+    int HW[HD_MAX_LEVELS];
+    int W[HD_MAX_LEVELS];
+    float stride[HD_MAX_LEVELS];
+    float anchor[HD_MAX_LEVELS][2 * HD_MAX_ANCHORS];
+    int tile_start[HD_MAX_LEVELS + 1];  // cumulative 128-cell tiles per (image, anchor)
+    int level_off[HD_MAX_LEVELS + 1];   // flat anchor index offset of each level
+    int n_levels, B, A, nc, no;
+    float thr;   // (float) conf_thres: torch compares the fp32 tensor with the scalar cast to fp32
+    float gate;  // conservative logit-domain pre-test for sigmoid(obj) > thr
+    int ge, dense, cap;
+    int items_per_image;
+    long long total_items;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Fused decode + filter + compaction.  One warp owns a tile of 128 consecutive cells of one
+// (image, level, anchor): lane k holds cells 4k..4k+3, so every plane is read with one coalesced
+// 512-byte request (128-bit per lane).  Channels live in planes H*W apart (the head's native NCHW),
+// which is why the warp walks planes instead of rows.
+//   - objectness plane first: if no cell of the tile can pass sigmoid(obj) > thr the 84 remaining
+//     planes are skipped (exact, since cls <= 1 => obj*cls <= obj) unless HD_FLAG_DENSE_READ;
+//   - class max is taken on the logits (sigmoid and x*obj are monotone), so only survivors pay for
+//     expf; the one case where that could differ from torch.max over the products -- an earlier class
+//     whose product rounds to the same float -- is detected through the runner-up L and resolved by
+//     an exact rescan;
+//   - survivors are compacted with one atomicAdd per warp.
+// ------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256) yolo_decode_filter_kernel(const __grid_constant__ YoloParams p,
+                                                                 float4* __restrict__ cand_box,
+                                                                 float* __restrict__ cand_score,
+                                                                 int* __restrict__ cand_cls,
+                                                                 int* __restrict__ cand_anchor,
+                                                                 int* __restrict__ cand_count) {
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= p.total_items) return;
+    const int b = (int)(item / p.items_per_image);
+    int r = (int)(item - (long long)b * p.items_per_image);
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < HD_MAX_LEVELS; ++q)
+        if (q < p.n_levels && r >= p.A * p.tile_start[q]) l = q;
+    r -= p.A * p.tile_start[l];
+    const int tiles_l = p.tile_start[l + 1] - p.tile_start[l];
+    const int a = r / tiles_l;
+    const int t = r - a * tiles_l;
+    const int HW = p.HW[l];
+    const int cell0 = t * 128 + lane * 4;
+    const float* __restrict__ base = p.data[l] + ((size_t)(b * p.A + a) * p.no) * HW + cell0;
+
+    float o[4], bx[4][4], m[4], L[4];
+    int j[4];
+    bool valid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) valid[k] = (cell0 + k) < HW;
+
+    auto load4 = [&](int plane, float* v) {
+        const float* q = base + (size_t)plane * HW;
+        if (VEC) {
+            if (valid[0]) {
+                float4 w = hd_ldg_stream4(q);
+                v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (valid[k]) v[k] = hd_ldg_stream(q + k);
+        }
+    };
+
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = -INFINITY;
+    load4(4, o);
+    bool gate_any = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gate_any |= valid[k] && (o[k] > p.gate);
+    if (!p.dense && !__any_sync(HD_FULL, gate_any)) return;
+
+#pragma unroll
+    for (int c = 0; c < 4; ++c) load4(c, bx[c]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = -INFINITY; L[k] = -INFINITY; j[k] = 0; }
+
+    auto upd = [&](const float* v, int c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bool g = v[k] > m[k];
+            L[k] = g ? m[k] : L[k];
+            j[k] = g ? c : j[k];
+            m[k] = g ? v[k] : m[k];
+        }
+    };
+    constexpr int U = 8;
+    int c = 0;
+    for (; c + U <= p.nc; c += U) {
+        float v[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[u][k] = -INFINITY;
+            load4(5 + c + u, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) upd(v[u], c + u);
+    }
+    for (; c < p.nc; ++c) {
+        float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        load4(5 + c, v);
+        upd(v, c);
+    }
+
+    // survivors
+    float conf[4];
+    int npass = 0;
+    bool pass[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pass[k] = false;
+        if (valid[k] && o[k] > p.gate) {
+            float po = hd_sigmoid(o[k]);
+            float cf = __fmul_rn(hd_sigmoid(m[k]), po);
+            bool ok = p.ge ? (po >= p.thr && cf >= p.thr) : (po > p.thr && cf > p.thr);
+            if (ok) {
+                if (L[k] > -INFINITY && __fmul_rn(hd_sigmoid(L[k]), po) == cf) {
+                    // an earlier class ties after rounding: torch.max returns the first maximal product
+                    const float* q = base + k;
+                    for (int cc = 0; cc < j[k]; ++cc) {
+                        float lg = __ldg(q + (size_t)(5 + cc) * HW);
+                        if (__fmul_rn(hd_sigmoid(lg), po) == cf) { j[k] = cc; break; }
+                    }
+                }
+                pass[k] = true;
+                conf[k] = cf;
+                ++npass;
+            }
+        }
+    }
+    // warp-aggregated slot claim
+    int incl = npass;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(HD_FULL, incl, d);
+        if (lane >= d) incl += y;
+    }
+    int total = __shfl_sync(HD_FULL, incl, 31);
+    if (total == 0) return;
+    int slot0 = 0;
+    if (lane == 31) slot0 = atomicAdd(cand_count + b, total);
+    slot0 = __shfl_sync(HD_FULL, slot0, 31);
+    int slot = slot0 + incl - npass;
+    const float s = p.stride[l];
+    const float aw = p.anchor[l][2 * a], ah = p.anchor[l][2 * a + 1];
+    const int W = p.W[l];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!pass[k]) continue;
+        if (slot < p.cap) {
+            const int cell = cell0 + k;
+            const int gi = cell / W, gj = cell - gi * W;
+            // (p*2 - 0.5 + grid) * s ; (p*2)^2 * anchor : fp32, op order of the reference decode
+            float px = __fmul_rn(hd_sigmoid(bx[0][k]), 2.0f), py = __fmul_rn(hd_sigmoid(bx[1][k]), 2.0f);
+            float pw = __fmul_rn(hd_sigmoid(bx[2][k]), 2.0f), ph = __fmul_rn(hd_sigmoid(bx[3][k]), 2.0f);
+            float cx = __fmul_rn(__fadd_rn(__fsub_rn(px, 0.5f), (float)gj), s);
+            float cy = __fmul_rn(__fadd_rn(__fsub_rn(py, 0.5f), (float)gi), s);
+            float w = __fmul_rn(__fmul_rn(pw, pw), aw), h = __fmul_rn(__fmul_rn(ph, ph), ah);
+            float hw2 = __fmul_rn(w, 0.5f), hh2 = __fmul_rn(h, 0.5f);  // w/2 exact
+            size_t g = (size_t)b * p.cap + slot;
+            cand_box[g] = make_float4(__fsub_rn(cx, hw2), __fsub_rn(cy, hh2), __fadd_rn(cx, hw2), __fadd_rn(cy, hh2));
+            cand_score[g] = conf[k];
+            cand_cls[g] = j[k];
+            cand_anchor[g] = p.level_off[l] + a * HW + cell;
+        }
+        ++slot;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense decode to pred[B, N, 5+nc] (drop-in for decode_box).  A warp reads 32 consecutive cells of
+// every plane (coalesced), transposes through padded shared memory and writes the 32 output rows,
+// which are contiguous in pred, with fully coalesced stores.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) yolo_decode_kernel(const __grid_constant__ YoloParams p, float* __restrict__ pred,
+                                                          int total_anchors) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* tile = smem + (size_t)wid * p.no * 33;
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + wid;  // 32-cell tiles here
+    if (item >= p.total_items) return;
+    const int b = (int)(item / p.items_per_image);
+    int r = (int)(item - (long long)b * p.items_per_image);
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < HD_MAX_LEVELS; ++q)
+        if (q < p.n_levels && r >= p.A * p.tile_start[q]) l = q;
+    r -= p.A * p.tile_start[l];
+    const int tiles_l = p.tile_start[l + 1] - p.tile_start[l];
+    const int a = r / tiles_l, t = r - a * tiles_l;
+    const int HW = p.HW[l], W = p.W[l];
+    const int cell = t * 32 + lane;
+    const bool valid = cell < HW;
+    const float* __restrict__ base = p.data[l] + ((size_t)(b * p.A + a) * p.no) * HW + cell;
+    const float s = p.stride[l];
+    const int gi = cell / W, gj = cell - gi * W;
+    for (int c = 0; c < p.no; ++c) {
+        float v = 0.f;
+        if (valid) {
+            float pr = hd_sigmoid(hd_ldg_stream(base + (size_t)c * HW));
+            if (c == 0) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(pr, 2.0f), 0.5f), (float)gj), s);
+            else if (c == 1) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(pr, 2.0f), 0.5f), (float)gi), s);
+            else if (c == 2 || c == 3) {
+                float q2 = __fmul_rn(pr, 2.0f);
+                v = __fmul_rn(__fmul_rn(q2, q2), p.anchor[l][2 * a + (c - 2)]);
+            } else v = pr;
+        }
+        tile[c * 33 + lane] = v;
+    }
+    __syncwarp();
+    const int rows = min(32, HW - t * 32);
+    float* out = pred + ((size_t)b * total_anchors + p.level_off[l] + a * HW + t * 32) * p.no;
+    for (int k = lane; k < rows * p.no; k += 32) {
+        int row = k / p.no, c = k - row * p.no;
+        out[k] = tile[c * 33 + row];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Filter on a decoded prediction [B, N, 5+nc]: warp per 32 rows; objectness gathered first, rows of
+// survivors are then read cooperatively (3 coalesced requests for nc=80) with a warp arg-max.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) yolo_filter_pred_kernel(const float* __restrict__ pred, int B, int N, int nc,
+                                                               float thr, int ge, float4* __restrict__ cand_box,
+                                                               float* __restrict__ cand_score, int* __restrict__ cand_cls,
+                                                               int* __restrict__ cand_anchor, int* __restrict__ cand_count,
+                                                               int cap) {
+    const int lane = threadIdx.x & 31;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int groups = (N + 31) / 32;
+    if (wg >= (long long)B * groups) return;
+    const int b = (int)(wg / groups);
+    const int row0 = (int)(wg - (long long)b * groups) * 32;
+    const int no = 5 + nc;
+    const float* __restrict__ img = pred + (size_t)b * N * no;
+    const int myrow = row0 + lane;
+    float obj = (myrow < N) ? __ldg(img + (size_t)myrow * no + 4) : -INFINITY;
+    bool s = ge ? (obj >= thr) : (obj > thr);
+    unsigned surv = __ballot_sync(HD_FULL, s);
+    while (surv) {
+        int src = __ffs(surv) - 1;
+        surv &= surv - 1;
+        const int row = row0 + src;
+        const float po = __shfl_sync(HD_FULL, obj, src);
+        const float* __restrict__ q = img + (size_t)row * no;
+        float best = -INFINITY;
+        int bj = 0x7fffffff;
+        for (int c = lane; c < nc; c += 32) {
+            float v = __fmul_rn(__ldg(q + 5 + c), po);
+            if (bj == 0x7fffffff || v > best) { best = v; bj = c; }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            float ob = __shfl_xor_sync(HD_FULL, best, d);
+            int oj = __shfl_xor_sync(HD_FULL, bj, d);
+            bool take = (oj != 0x7fffffff) && (bj == 0x7fffffff || ob > best || (ob == best && oj < bj));
+            if (take) { best = ob; bj = oj; }
+        }
+        if (lane == 0 && bj != 0x7fffffff) {
+            bool ok = ge ? (best >= thr) : (best > thr);
+            if (ok) {
+                int slot = atomicAdd(cand_count + b, 1);
+                if (slot < cap) {
+                    float cx = __ldg(q), cy = __ldg(q + 1), w = __ldg(q + 2), h = __ldg(q + 3);
+                    float hw2 = __fmul_rn(w, 0.5f), hh2 = __fmul_rn(h, 0.5f);
+                    size_t g = (size_t)b * cap + slot;
+                    cand_box[g] = make_float4(__fsub_rn(cx, hw2), __fsub_rn(cy, hh2), __fadd_rn(cx, hw2), __fadd_rn(cy, hh2));
+                    cand_score[g] = best;
+                    cand_cls[g] = bj;
+                    cand_anchor[g] = row;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int fill_params(YoloParams& p, const hd_yolo_level* levels, int n_levels, int B, int A, int nc, int tile_cells) {
+    HD_CHECK_ARG(levels != nullptr, "levels is NULL");
+    HD_CHECK_ARG(n_levels >= 1 && n_levels <= HD_MAX_LEVELS, "n_levels must be in [1,%d], got %d", HD_MAX_LEVELS, n_levels);
+    HD_CHECK_ARG(A >= 1 && A <= HD_MAX_ANCHORS, "A must be in [1,%d], got %d", HD_MAX_ANCHORS, A);
+    HD_CHECK_ARG(B >= 0 && nc >= 1, "B must be >= 0 and nc >= 1, got B=%d nc=%d", B, nc);
+    memset(&p, 0, sizeof(p));
+    p.n_levels = n_levels; p.B = B; p.A = A; p.nc = nc; p.no = 5 + nc;
+    int tiles = 0, off = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        HD_CHECK_ARG(levels[l].H > 0 && levels[l].W > 0, "level %d has empty spatial size", l);
+        HD_CHECK_ARG(B == 0 || levels[l].data != nullptr, "level %d data is NULL", l);
+        p.data[l] = levels[l].data;
+        p.HW[l] = levels[l].H * levels[l].W;
+        p.W[l] = levels[l].W;
+        p.stride[l] = levels[l].stride;
+        for (int k = 0; k < 2 * A; ++k) p.anchor[l][k] = levels[l].anchor_wh[k];
+        p.tile_start[l] = tiles;
+        p.level_off[l] = off;
+        tiles += (p.HW[l] + tile_cells - 1) / tile_cells;
+        off += A * p.HW[l];
+    }
+    p.tile_start[n_levels] = tiles;
+    p.level_off[n_levels] = off;
+    p.items_per_image = A * tiles;
+    p.total_items = (long long)B * p.items_per_image;
+    return HD_OK;
+}
+
+static float conf_gate(double thr) {
+    if (!(thr > 0.0)) return -INFINITY;
+    if (thr >= 1.0) return 15.0f;
+    return (float)(log(thr / (1.0 - thr)) - 0.01);
+}
+
+extern "C" HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels, int n_levels, int B, int A, int nc, double conf_thres,
+                                     int flags, float* cand_box, float* cand_score, int32_t* cand_cls,
+                                     int32_t* cand_anchor, int32_t* cand_count, int cap, void* stream) {
+    YoloParams p;
+    int rc = fill_params(p, levels, n_levels, B, A, nc, 128);
+    if (rc) return rc;
+    HD_CHECK_ARG(cap > 0 && cand_box && cand_score && cand_cls && cand_anchor && cand_count, "null output or cap <= 0");
+    p.thr = (float)conf_thres;
+    p.gate = conf_gate(conf_thres);
+    p.ge = (flags & HD_FLAG_CONF_GE) ? 1 : 0;
+    p.dense = (flags & HD_FLAG_DENSE_READ) ? 1 : 0;
+    p.cap = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) return HD_OK;
+    HD_CUDA_CALL(cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)B, st));
+    bool vec = true;
+    for (int l = 0; l < n_levels; ++l) vec = vec && (p.HW[l] % 4 == 0) && (((uintptr_t)p.data[l] & 15) == 0);
+    const int warps = 8;
+    long long blocks = (p.total_items + warps - 1) / warps;
+    HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
+    if (vec)
+        yolo_decode_filter_kernel<true><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count);
+    else
+        yolo_decode_filter_kernel<false><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count);
+    HD_CUDA_LAUNCH_CHECK("yolo_decode_filter_kernel");
+    return HD_OK;
+}
+
+extern "C" HD_API int hd_yolo_decode(const hd_yolo_level* levels, int n_levels, int B, int A, int nc, float* pred, void* stream) {
+    YoloParams p;
+    int rc = fill_params(p, levels, n_levels, B, A, nc, 32);
+    if (rc) return rc;
+    if (B == 0) return HD_OK;
+    HD_CHECK_ARG(pred != nullptr, "pred is NULL");
+    const int warps = 8;
+    size_t smem = (size_t)warps * p.no * 33 * sizeof(float);
+    HD_CHECK_ARG(smem <= 200 * 1024, "nc=%d too large for the decode transpose tile", nc);
+    static bool attr_set = false;
+    if (!attr_set) {
+        HD_CUDA_CALL(cudaFuncSetAttribute(yolo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    long long blocks = (p.total_items + warps - 1) / warps;
+    HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
+    yolo_decode_kernel<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p, pred, p.level_off[n_levels]);
+    HD_CUDA_LAUNCH_CHECK("yolo_decode_kernel");
+    return HD_OK;
+}
+
+extern "C" HD_API int hd_yolo_filter_pred(const float* pred, int B, int N, int nc, double conf_thres, int flags, float* cand_box,
+                                   float* cand_score, int32_t* cand_cls, int32_t* cand_anchor, int32_t* cand_count,
+                                   int cap, void* stream) {
+    HD_CHECK_ARG(B >= 0 && N >= 0 && nc >= 1, "bad shape B=%d N=%d nc=%d", B, N, nc);
+    HD_CHECK_ARG(cap > 0 && cand_box && cand_score && cand_cls && cand_anchor && cand_count, "null output or cap <= 0");
+    if (B == 0) return HD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    HD_CUDA_CALL(cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)B, st));
+    if (N == 0) return HD_OK;
+    HD_CHECK_ARG(pred != nullptr, "pred is NULL");
+    long long groups = (long long)B * ((N + 31) / 32);
+    long long blocks = (groups + 7) / 8;
+    HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
+    yolo_filter_pred_kernel<<<(unsigned)blocks, 256, 0, st>>>(pred, B, N, nc, (float)conf_thres, (flags & HD_FLAG_CONF_GE) ? 1 : 0,
+                                                             (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count, cap);
+    HD_CUDA_LAUNCH_CHECK("yolo_filter_pred_kernel");
+    return HD_OK;
+}

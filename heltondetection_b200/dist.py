@@ -1,0 +1,63 @@
+"""Image sharding + the one collective of the path: an all-gather of the padded per-image detections
+(SURVEY.md 8e).  Every stage is per-image independent, so ranks never exchange data until the final
+fixed-size record {int32 count, float32 [max_det, 6]} per image is gathered over NCCL (NVLink 5 / NVSwitch).
+The host logic is backend-agnostic so it is tested on CPU with gloo, world_size 2.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_slice(n_images, rank, world):
+    """Contiguous image slice of `rank`: the first (n % world) ranks take one extra image."""
+    base, rem = divmod(n_images, world)
+    start = rank * base + min(rank, rem)
+    return slice(start, start + base + (1 if rank < rem else 0))
+
+
+def pack_records(det, count, out=None):
+    """det [B,max_det,6] f32 + count [B] i32 -> records [B, 1 + max_det*6] f32 (count bits in column 0)."""
+    B, md = det.shape[0], det.shape[1]
+    if out is None:
+        out = torch.empty((B, 1 + md * 6), dtype=torch.float32, device=det.device)
+    out[:, 1:].copy_(det.reshape(B, md * 6))
+    out[:, 0].view(torch.int32).copy_(count.to(torch.int32))
+    return out
+
+
+def unpack_records(rec, max_det):
+    count = rec[:, 0].contiguous().view(torch.int32)
+    return rec[:, 1:].reshape(rec.shape[0], max_det, 6), count
+
+
+class DetectionGather:
+    """Preallocated all-gather of the padded detections of equally sized shards."""
+
+    def __init__(self, B, max_det, device, group=None):
+        self.group, self.max_det = group, max_det
+        self.world = dist.get_world_size(group)
+        self.rec = torch.empty((B, 1 + max_det * 6), dtype=torch.float32, device=device)
+        self.out = torch.empty((self.world * B, 1 + max_det * 6), dtype=torch.float32, device=device)
+
+    def __call__(self, det, count):
+        pack_records(det, count, self.rec)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_gather_into_tensor(self.out, self.rec, group=self.group)
+        else:
+            chunks = list(self.out.chunk(self.world, 0))
+            dist.all_gather(chunks, self.rec, group=self.group)
+        return unpack_records(self.out, self.max_det)
+
+
+def gather_ragged(det, count, n_images, group=None):
+    """All-gather for uneven shards (n_images % world != 0): pads every shard to the largest one,
+    gathers, and strips the padding so the result is in global image order."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_slice(n_images, r, world) for r in range(world)]
+    bmax = max(s.stop - s.start for s in sizes)
+    md = det.shape[1]
+    rec = torch.zeros((bmax, 1 + md * 6), dtype=torch.float32, device=det.device)
+    pack_records(det, count, rec[: det.shape[0]])
+    outs = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(outs, rec, group=group)
+    full = torch.cat([o[: s.stop - s.start] for o, s in zip(outs, sizes)], 0)
+    return unpack_records(full, md)

@@ -1,0 +1,91 @@
+"""torchvision-compatible box ops on the hd_b200 kernels.
+
+``nms`` / ``batched_nms`` / ``box_iou`` keep the torchvision signatures, argument meaning and
+error messages (torchvision/ops/boxes.py:20-120, 308-370).  They are also registered as the
+``hd_b200::nms`` / ``hd_b200::box_iou`` PyTorch custom ops with the torchvision schemas.
+"""
+import torch
+from . import _lib
+
+
+def _check_nms_args(boxes, scores):
+    if boxes.dim() != 2:
+        raise RuntimeError(f"boxes should be a 2d tensor, got {boxes.dim()}D")
+    if boxes.size(1) != 4:
+        raise RuntimeError(f"boxes should have 4 elements in dimension 1, got {boxes.size(1)}")
+    if scores.dim() != 1:
+        raise RuntimeError(f"scores should be a 1d tensor, got {scores.dim()}D")
+    if boxes.size(0) != scores.size(0):
+        raise RuntimeError("boxes and scores should have same number of elements in dimension 0, "
+                           f"got {boxes.size(0)} and {scores.size(0)}")
+    if boxes.dtype != scores.dtype:
+        raise RuntimeError("dets should have the same type as scores")
+    if boxes.dtype != torch.float32:
+        raise NotImplementedError(f'"nms_kernel" not implemented for \'{str(boxes.dtype).split(".")[-1].capitalize()}\' (hd_b200 is fp32-only)')
+
+
+def _nms_single(boxes, scores, iou_threshold, cls=None, mode=_lib.NMS_AGNOSTIC, offset=0.0, max_det=None, max_nms=0):
+    """One image through hd_sort_nms_batched -> int64 keep indices in score order."""
+    _lib.require_cuda(boxes, scores, cls)
+    _check_nms_args(boxes, scores)
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    boxes, scores = _lib.f32c(boxes), _lib.f32c(scores)
+    if cls is not None:
+        cls = cls.to(torch.int32).contiguous()
+    md = n if max_det is None else int(max_det)
+    L = _lib.lib()
+    ws_bytes = L.hd_sort_nms_workspace_size(1, n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=boxes.device)
+    idx = torch.empty((md,), dtype=torch.int64, device=boxes.device)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    _lib.check(L.hd_sort_nms_batched(_lib.ptr(boxes), _lib.ptr(scores), _lib.ptr(cls), None, None, n, 1, n,
+                                     float(iou_threshold), mode, float(offset), int(max_nms), md, None, _lib.ptr(idx),
+                                     _lib.ptr(cnt), _lib.ptr(ws), ws_bytes, _lib.stream()))
+    return idx[: int(cnt.item())]  # data-dependent size: the op's one host sync, as in torchvision
+
+
+def nms(boxes, scores, iou_threshold):
+    """torchvision.ops.nms (boxes.py:20-48)."""
+    return torch.ops.hd_b200.nms(boxes, scores, float(iou_threshold))
+
+
+def batched_nms(boxes, scores, idxs, iou_threshold):
+    """torchvision.ops.batched_nms (boxes.py:51-120) with exact class masking
+    (= _batched_nms_vanilla for every input size; no coordinate-offset rounding)."""
+    _lib.require_cuda(boxes, scores, idxs)
+    if boxes.numel() == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    return _nms_single(boxes, scores, iou_threshold, idxs, _lib.NMS_CLASS_EXACT)
+
+
+def box_iou(boxes1, boxes2):
+    """torchvision.ops.box_iou (boxes.py:308-370)."""
+    return torch.ops.hd_b200.box_iou(boxes1, boxes2)
+
+
+def _box_iou_impl(boxes1, boxes2):
+    _lib.require_cuda(boxes1, boxes2)
+    if boxes1.dim() != 2 or boxes1.size(1) != 4 or boxes2.dim() != 2 or boxes2.size(1) != 4:
+        raise RuntimeError("box_iou expects Tensor[N, 4] and Tensor[M, 4]")
+    b1, b2 = _lib.f32c(boxes1), _lib.f32c(boxes2)
+    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
+    _lib.check(_lib.lib().hd_box_iou(_lib.ptr(b1), b1.shape[0], _lib.ptr(b2), b2.shape[0], _lib.ptr(out), _lib.stream()))
+    return out
+
+
+# ----------------------------------------------------------------------------- custom-op registration
+_LIB = torch.library.Library("hd_b200", "DEF")
+_LIB.define("nms(Tensor dets, Tensor scores, float iou_threshold) -> Tensor")
+_LIB.define("box_iou(Tensor boxes1, Tensor boxes2) -> Tensor")
+
+
+def _cpu_refuse(*a, **k):
+    raise RuntimeError("hd_b200 ops are CUDA-only (sm_100a); there is no CPU fallback")
+
+
+_LIB.impl("nms", lambda dets, scores, thr: _nms_single(dets, scores, thr), "CUDA")
+_LIB.impl("box_iou", _box_iou_impl, "CUDA")
+_LIB.impl("nms", _cpu_refuse, "CPU")
+_LIB.impl("box_iou", _cpu_refuse, "CPU")

@@ -1,0 +1,155 @@
+"""YOLOv5 post-process host API (drop-in names of the reference lineage, README.md:9).
+
+``decode_box`` / ``non_max_suppression`` keep the lineage signatures;
+``YoloPostprocessor`` is the fused fast path (raw heads -> detections, two kernels, no host sync).
+"""
+import ctypes as C
+import torch
+from . import _lib
+
+DEFAULT_ANCHORS = (
+    ((10, 13), (16, 30), (33, 23)),
+    ((30, 61), (62, 45), (59, 119)),
+    ((116, 90), (156, 198), (373, 326)),
+)
+DEFAULT_STRIDES = (8, 16, 32)
+_CLASS_MODES = {"agnostic": _lib.NMS_AGNOSTIC, "exact": _lib.NMS_CLASS_EXACT, "offset": _lib.NMS_CLASS_OFFSET}
+
+
+def _levels(outputs, anchors, strides):
+    if len(outputs) != len(anchors) or len(outputs) != len(strides):
+        raise RuntimeError("outputs, anchors and strides must have one entry per level")
+    A = len(anchors[0])
+    B, Ctot = outputs[0].shape[0], outputs[0].shape[1]
+    if Ctot % A != 0 or Ctot // A < 6:
+        raise RuntimeError(f"head channels {Ctot} are not A*(5+nc) with A={A}")
+    nc = Ctot // A - 5
+    arr = (_lib.YoloLevel * len(outputs))()
+    keep = []
+    total = 0
+    for l, (x, anc, s) in enumerate(zip(outputs, anchors, strides)):
+        _lib.require_cuda(x)
+        if x.dim() != 4 or x.shape[0] != B or x.shape[1] != Ctot or len(anc) != A:
+            raise RuntimeError(f"level {l}: expected [B={B}, {Ctot}, H, W], got {tuple(x.shape)}")
+        x = _lib.f32c(x)
+        keep.append(x)
+        arr[l].data = x.data_ptr()
+        arr[l].H, arr[l].W, arr[l].stride = x.shape[2], x.shape[3], float(s)
+        for a, (w, h) in enumerate(anc):
+            arr[l].anchor_wh[2 * a], arr[l].anchor_wh[2 * a + 1] = float(w), float(h)
+        total += A * x.shape[2] * x.shape[3]
+    return arr, keep, B, A, nc, total
+
+
+def decode_box(outputs, anchors=DEFAULT_ANCHORS, strides=DEFAULT_STRIDES):
+    """list of [B, A*(5+nc), H, W] -> [B, sum(A*H*W), 5+nc] (cx,cy,w,h,obj,cls..) px (A.1)."""
+    arr, keep, B, A, nc, total = _levels(outputs, anchors, strides)
+    pred = torch.empty((B, total, 5 + nc), dtype=torch.float32, device=keep[0].device)
+    _lib.check(_lib.lib().hd_yolo_decode(arr, len(keep), B, A, nc, _lib.ptr(pred), _lib.stream()))
+    return pred
+
+
+class _Buffers:
+    """Candidate + NMS buffers for (B, cap, max_det) on one device; reused across calls."""
+
+    def __init__(self, B, cap, max_det, device):
+        self.B, self.cap, self.max_det = B, cap, max_det
+        self.box = torch.empty((B, cap, 4), dtype=torch.float32, device=device)
+        self.score = torch.empty((B, cap), dtype=torch.float32, device=device)
+        self.cls = torch.empty((B, cap), dtype=torch.int32, device=device)
+        self.anchor = torch.empty((B, cap), dtype=torch.int32, device=device)
+        self.count = torch.zeros((B,), dtype=torch.int32, device=device)
+        self.ws_bytes = _lib.lib().hd_sort_nms_workspace_size(B, cap)
+        self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=device)
+        self.det = torch.zeros((B, max_det, 6), dtype=torch.float32, device=device)
+        self.idx = torch.zeros((B, max_det), dtype=torch.int64, device=device)
+        self.out_count = torch.zeros((B,), dtype=torch.int32, device=device)
+
+
+def _run_nms(buf, iou_thres, class_mode, max_wh, max_nms):
+    _lib.check(_lib.lib().hd_sort_nms_batched(
+        _lib.ptr(buf.box), _lib.ptr(buf.score), _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), 0,
+        buf.B, buf.cap, float(iou_thres), class_mode, float(max_wh), int(max_nms), buf.max_det,
+        _lib.ptr(buf.det), _lib.ptr(buf.idx), _lib.ptr(buf.out_count), _lib.ptr(buf.ws), buf.ws_bytes, _lib.stream()))
+
+
+class YoloPostprocessor:
+    """Fused raw-head post-process: decode+filter+compaction kernel, then per-image sort+NMS kernel.
+
+    __call__(outputs) -> (det [B,max_det,6] = x1,y1,x2,y2,conf,cls ; count [B] int32 ; idx [B,max_det] anchor ids)
+    all on the device, padded, with no host synchronisation (CUDA-graph capturable)."""
+
+    def __init__(self, anchors=DEFAULT_ANCHORS, strides=DEFAULT_STRIDES, conf_thres=0.25, iou_thres=0.45,
+                 agnostic=False, max_det=300, max_nms=30000, max_wh=7680.0, class_mode="offset", ge=False,
+                 dense_read=False):
+        self.anchors, self.strides = anchors, strides
+        self.conf_thres, self.iou_thres = float(conf_thres), float(iou_thres)
+        self.max_det, self.max_nms, self.max_wh = int(max_det), int(max_nms), float(max_wh)
+        self.class_mode = _lib.NMS_AGNOSTIC if agnostic else _CLASS_MODES[class_mode]
+        self.flags = (_lib.FLAG_CONF_GE if ge else 0) | (_lib.FLAG_DENSE_READ if dense_read else 0)
+        self._buf = None
+
+    def buffers(self, B, cap, device):
+        b = self._buf
+        if b is None or b.B != B or b.cap != cap or b.box.device != device:
+            b = self._buf = _Buffers(B, cap, self.max_det, device)
+        return b
+
+    def __call__(self, outputs):
+        arr, keep, B, A, nc, total = _levels(outputs, self.anchors, self.strides)
+        buf = self.buffers(B, total, keep[0].device)
+        _lib.check(_lib.lib().hd_yolo_decode_filter(
+            arr, len(keep), B, A, nc, self.conf_thres, self.flags, _lib.ptr(buf.box), _lib.ptr(buf.score),
+            _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))
+        _run_nms(buf, self.iou_thres, self.class_mode, self.max_wh, self.max_nms)
+        return buf.det, buf.out_count, buf.idx
+
+    def candidates(self, outputs):
+        """decode+filter only -> per image (cand [n,6], anchor idx [n]) sorted by anchor index (test helper)."""
+        arr, keep, B, A, nc, total = _levels(outputs, self.anchors, self.strides)
+        buf = self.buffers(B, total, keep[0].device)
+        _lib.check(_lib.lib().hd_yolo_decode_filter(
+            arr, len(keep), B, A, nc, self.conf_thres, self.flags, _lib.ptr(buf.box), _lib.ptr(buf.score),
+            _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))
+        return _collect_candidates(buf)
+
+
+def _collect_candidates(buf):
+    out = []
+    for b, n in enumerate(buf.count.tolist()):
+        n = min(n, buf.cap)
+        o = torch.argsort(buf.anchor[b, :n])
+        c = torch.cat((buf.box[b, :n], buf.score[b, :n, None], buf.cls[b, :n, None].float()), 1)[o]
+        out.append((c, buf.anchor[b, :n][o].long()))
+    return out
+
+
+def _slice(det, count, idx=None):
+    counts = count.tolist()  # the one host sync of the list-returning drop-in
+    if idx is None:
+        return [det[b, :n] for b, n in enumerate(counts)]
+    return [det[b, :n] for b, n in enumerate(counts)], [idx[b, :n] for b, n in enumerate(counts)]
+
+
+def postprocess(outputs, conf_thres=0.25, iou_thres=0.45, return_index=False, **kw):
+    """Raw heads -> list of [k,6] detections (fused path)."""
+    det, count, idx = YoloPostprocessor(conf_thres=conf_thres, iou_thres=iou_thres, **kw)(outputs)
+    return _slice(det, count, idx) if return_index else _slice(det, count)
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000,
+                        max_wh=7680.0, class_mode="offset", ge=False, return_index=False):
+    """Lineage signature: decoded prediction [B, N, 5+nc] -> list of [k,6] (xyxy, conf, cls) (A.2)."""
+    _lib.require_cuda(prediction)
+    if prediction.dim() != 3 or prediction.shape[2] < 6:
+        raise RuntimeError(f"prediction should be [B, N, 5+nc], got {tuple(prediction.shape)}")
+    pred = _lib.f32c(prediction)
+    B, N, no = pred.shape
+    buf = _Buffers(B, max(N, 1), max_det, pred.device)
+    flags = _lib.FLAG_CONF_GE if ge else 0
+    _lib.check(_lib.lib().hd_yolo_filter_pred(
+        _lib.ptr(pred), B, N, no - 5, float(conf_thres), flags, _lib.ptr(buf.box), _lib.ptr(buf.score),
+        _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))
+    mode = _lib.NMS_AGNOSTIC if agnostic else _CLASS_MODES[class_mode]
+    _run_nms(buf, iou_thres, mode, max_wh, max_nms)
+    return _slice(buf.det, buf.out_count, buf.idx) if return_index else _slice(buf.det, buf.out_count)

@@ -1,0 +1,97 @@
+"""hd_sort_nms_batched / hd_box_iou against torchvision CPU ops: keep indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+import torchvision
+
+pytestmark = pytest.mark.gpu
+
+
+def _boxes(n, seed, img=640.0, cluster=True):
+    g = torch.Generator().manual_seed(seed)
+    if cluster:
+        k = max(n // 8, 1)
+        ctr = torch.rand((k, 2), generator=g) * img
+        wh = torch.rand((k, 2), generator=g) * 100 + 8
+        pick = torch.randint(0, k, (n,), generator=g)
+        c = ctr[pick] + torch.randn((n, 2), generator=g) * 4
+        s = wh[pick] * (1 + 0.1 * torch.randn((n, 2), generator=g))
+    else:
+        c = torch.rand((n, 2), generator=g) * img
+        s = torch.rand((n, 2), generator=g) * 100 + 1
+    b = torch.cat((c - s / 2, c + s / 2), 1)
+    return b, torch.rand((n,), generator=g)
+
+
+def _run(boxes, scores, thr, cls=None, mode=0, offset=0.0, max_det=None, max_nms=0):
+    from heltondetection_b200 import ops
+    return ops._nms_single(boxes.cuda(), scores.cuda(), thr, None if cls is None else cls.cuda(), mode, offset,
+                           max_det=max_det, max_nms=max_nms).cpu()
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 300, 1023, 1025, 5000])
+@pytest.mark.parametrize("thr", [0.45, 0.6, 0.7])
+def test_nms_matches_torchvision(n, thr):
+    b, s = _boxes(n, n)
+    ref = torchvision.ops.nms(b, s, thr)
+    assert torch.equal(_run(b, s, thr), ref)
+
+
+def test_nms_ties_nan_degenerate():
+    b, s = _boxes(500, 7)
+    s = (s * 4).round() / 4  # massive score ties -> stable order by index
+    assert torch.equal(_run(b, s, 0.5), torchvision.ops.nms(b, s, 0.5))
+    s2 = s.clone(); s2[3] = float("nan"); s2[77] = float("nan")
+    assert torch.equal(_run(b, s2, 0.5), torchvision.ops.nms(b, s2, 0.5))
+    same = torch.tensor([[0., 0., 10., 10.]]).repeat(5, 1)
+    assert torch.equal(_run(same, torch.ones(5), 0.5), torchvision.ops.nms(same, torch.ones(5), 0.5))
+    zero = torch.tensor([[5., 5., 5., 5.]]).repeat(4, 1)  # 0/0 = NaN -> all kept
+    assert torch.equal(_run(zero, torch.ones(4), 0.5), torchvision.ops.nms(zero, torch.ones(4), 0.5))
+    bn = b.clone(); bn[10, 0] = float("nan")
+    assert torch.equal(_run(bn, s, 0.5), torchvision.ops.nms(bn, s, 0.5))
+    inv = b.clone(); inv[5] = inv[5][[2, 3, 0, 1]]
+    assert torch.equal(_run(inv, s, 0.5), torchvision.ops.nms(inv, s, 0.5))
+
+
+def test_nms_threshold_edge_is_strict_and_double():
+    # IoU exactly 0.5: kept at thr 0.5
+    b = torch.tensor([[0., 0., 2., 1.], [1., 0., 3., 1.], [0., 0., 2., 2.], [0., 0., 2., 1.]])
+    s = torch.tensor([0.9, 0.8, 0.7, 0.6])
+    for thr in (0.5, 1 / 3, 0.6, 0.0):
+        assert torch.equal(_run(b, s, thr), torchvision.ops.nms(b, s, thr)), thr
+
+
+@pytest.mark.parametrize("nc,n", [(80, 3000), (10, 4000), (1000, 2000)])
+def test_batched_nms_exact_class_masking(nc, n):
+    b, s = _boxes(n, 11)
+    c = torch.randint(0, nc, (n,), generator=torch.Generator().manual_seed(3))
+    ref = torchvision.ops.boxes._batched_nms_vanilla(b, s, c, 0.5)
+    assert torch.equal(_run(b, s, 0.5, c.int(), 1), ref)
+
+
+def test_batched_nms_offset_trick_matches_ultralytics_form():
+    b, s = _boxes(3000, 12)
+    c = torch.randint(0, 80, (3000,), generator=torch.Generator().manual_seed(4))
+    ref = torchvision.ops.nms(b + (c.float() * 7680.0)[:, None], s, 0.45)
+    assert torch.equal(_run(b, s, 0.45, c.int(), 2, 7680.0), ref)
+
+
+def test_max_det_and_max_nms_truncation():
+    b, s = _boxes(2000, 13)
+    ref = torchvision.ops.nms(b, s, 0.5)
+    assert torch.equal(_run(b, s, 0.5, max_det=37), ref[:37])
+    o = torch.sort(s, descending=True, stable=True)[1][:500]
+    ref2 = o[torchvision.ops.nms(b[o], s[o], 0.5)]
+    assert torch.equal(_run(b, s, 0.5, max_nms=500), ref2)
+
+
+def test_box_iou_matches_torchvision():
+    from heltondetection_b200 import ops
+    b1, _ = _boxes(777, 1)
+    b2, _ = _boxes(1301, 2)
+    ref = torchvision.ops.box_iou(b1, b2)
+    got = ops.box_iou(b1.cuda(), b2.cuda()).cpu()
+    assert got.shape == ref.shape
+    # same fp32 op order; division correctly rounded on both sides
+    assert torch.allclose(got, ref, rtol=1e-6, atol=1e-7)
+    assert ops.box_iou(b1[:0].cuda(), b2.cuda()).shape == (0, 1301)

@@ -1,0 +1,114 @@
+"""Parity of the CUDA YOLO path (through the C ABI) against the CPU oracle.
+
+Tolerances: integer results (candidate sets, class ids, keep indices, counts) bit-exact;
+floating point <= 1e-5 relative (north_star), written as |a-b| <= 1e-5*max(|ref|,1) for pixel
+coordinates / scores.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def close(a, b, scale=1.0):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return bool(((a - b).abs() <= RTOL * torch.clamp(b.abs(), min=scale)).all())
+
+
+def _cfg(B, img, nc, G, seed, dense=False):
+    from heltondetection_b200 import synth
+    heads, _ = synth.yolo_heads(B, img, nc, G, seed, dense=dense)
+    return heads
+
+
+@pytest.fixture(scope="module")
+def cfg1():
+    return _cfg(2, 640, 80, 20, 1234)
+
+
+def test_decode_box_matches_oracle(cfg1):
+    import oracle
+    from heltondetection_b200 import yolo
+    ref = oracle.yolo.decode_box(cfg1)
+    got = yolo.decode_box([h.cuda() for h in cfg1])
+    assert got.shape == ref.shape
+    assert close(got, ref, scale=1e-3)
+
+
+@pytest.mark.parametrize("thr,dense_read,ge", [(0.25, False, False), (0.25, True, False), (0.001, False, False), (0.25, False, True)])
+def test_candidates_match_oracle(cfg1, thr, dense_read, ge):
+    import oracle
+    from heltondetection_b200 import yolo
+    pred = oracle.yolo.decode_box(cfg1)
+    pp = yolo.YoloPostprocessor(conf_thres=thr, dense_read=dense_read, ge=ge)
+    got = pp.candidates([h.cuda() for h in cfg1])
+    for b in range(pred.shape[0]):
+        ref, ridx = oracle.yolo.filter_candidates(pred[b], thr, ge)
+        c, idx = got[b]
+        assert torch.equal(idx.cpu(), ridx), f"candidate set differs: {idx.numel()} vs {ridx.numel()}"
+        assert torch.equal(c[:, 5].cpu(), ref[:, 5])
+        assert close(c[:, :4], ref[:, :4])
+        assert close(c[:, 4], ref[:, 4], scale=1e-3)
+
+
+@pytest.mark.parametrize("thr,iou,mode", [(0.25, 0.45, "offset"), (0.001, 0.6, "offset"), (0.25, 0.45, "exact"), (0.001, 0.45, "agnostic")])
+def test_fused_postprocess_keeps_match_oracle(cfg1, thr, iou, mode):
+    import oracle
+    from heltondetection_b200 import yolo
+    pred = oracle.yolo.decode_box(cfg1)
+    agn = mode == "agnostic"
+    ref, ridx = oracle.yolo.non_max_suppression(pred, thr, iou, agnostic=agn, class_mode=mode if not agn else "offset", return_index=True)
+    got, gidx = yolo.postprocess([h.cuda() for h in cfg1], thr, iou, agnostic=agn, class_mode=mode if not agn else "offset", return_index=True)
+    for b in range(len(ref)):
+        assert torch.equal(gidx[b].cpu(), ridx[b]), f"keep indices differ for image {b}"
+        assert torch.equal(got[b][:, 5].cpu(), ref[b][:, 5])
+        assert close(got[b][:, :4], ref[b][:, :4])
+        assert close(got[b][:, 4], ref[b][:, 4], scale=1e-3)
+
+
+def test_nms_on_decoded_prediction_matches_oracle(cfg1):
+    import oracle
+    from heltondetection_b200 import yolo
+    pred = oracle.yolo.decode_box(cfg1)
+    ref, ridx = oracle.yolo.non_max_suppression(pred, 0.25, 0.45, return_index=True)
+    got, gidx = yolo.non_max_suppression(pred.cuda(), 0.25, 0.45, return_index=True)
+    for b in range(len(ref)):
+        # identical fp32 inputs -> identical products, boxes and keeps
+        assert torch.equal(gidx[b].cpu(), ridx[b])
+        assert torch.equal(got[b].cpu(), ref[b])
+
+
+def test_dense_visdrone_like():
+    import oracle
+    from heltondetection_b200 import yolo
+    heads = _cfg(1, 1280, 10, 300, 1238, dense=True)
+    pred = oracle.yolo.decode_box(heads)
+    ref, ridx = oracle.yolo.non_max_suppression(pred, 0.001, 0.6, return_index=True)
+    got, gidx = yolo.postprocess([h.cuda() for h in heads], 0.001, 0.6, return_index=True)
+    assert torch.equal(gidx[0].cpu(), ridx[0])
+    assert close(got[0][:, :4], ref[0][:, :4])
+
+
+def test_odd_spatial_size_scalar_path():
+    """H*W not divisible by 4 -> scalar-load kernel variant."""
+    import oracle
+    from heltondetection_b200 import yolo
+    g = torch.Generator().manual_seed(5)
+    heads = [torch.randn((2, 3 * 9, 7, 9), generator=g), torch.randn((2, 3 * 9, 5, 3), generator=g)]
+    anchors = (((10, 13), (16, 30), (33, 23)), ((30, 61), (62, 45), (59, 119)))
+    pred = oracle.yolo.decode_box(heads, anchors, (8, 16))
+    assert close(yolo.decode_box([h.cuda() for h in heads], anchors, (8, 16)), pred, scale=1e-3)
+    ref, ridx = oracle.yolo.non_max_suppression(pred, 0.1, 0.45, return_index=True)
+    got, gidx = yolo.postprocess([h.cuda() for h in heads], 0.1, 0.45, anchors=anchors, strides=(8, 16), return_index=True)
+    for b in range(2):
+        assert torch.equal(gidx[b].cpu(), ridx[b])
+
+
+def test_no_candidates_and_empty_batch():
+    from heltondetection_b200 import yolo
+    heads = [torch.full((1, 255, 8, 8), -12.0).cuda()]
+    out = yolo.postprocess(heads, 0.25, 0.45, anchors=(((10, 13), (16, 30), (33, 23)),), strides=(8,))
+    assert out[0].shape == (0, 6)
