@@ -15,6 +15,9 @@ HD_MAX_ANCHORS = 8
 FLAG_CONF_GE = 1
 FLAG_DENSE_READ = 2
 NMS_AGNOSTIC, NMS_CLASS_EXACT, NMS_CLASS_OFFSET = 0, 1, 2
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+RPN_SOFTMAX, RPN_CLAMP_DWH = 1, 2
+WBF_AVG, WBF_MAX = 0, 1
 
 
 class YoloLevel(C.Structure):
@@ -43,6 +46,19 @@ SIGNATURES = {
     "hd_sort_nms_workspace_size": (_sz, [_i, _i]),
     "hd_sort_nms_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hd_box_iou": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "hd_rpn_num_anchors": (_i, [C.POINTER(RpnLevel), _i, _i]),
+    "hd_rpn_decode": (_i, [C.POINTER(RpnLevel), _i, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "hd_rpn_select_nms_workspace_size": (_sz, [_i, _i, _i]),
+    "hd_rpn_select_nms": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hd_rpn_proposals_workspace_size": (_sz, [_i, _i, _i]),
+    "hd_rpn_proposals": (_i, [C.POINTER(RpnLevel), _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hd_wbf_workspace_size": (_sz, [_i, _i, _i, _i]),
+    "hd_wbf": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_double), _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hd_tta_map_back": (_i, [_vp, _vp, _i, _i, _f, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "hd_roi_align": (_i, [C.POINTER(RoiLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "hd_roi_pool": (_i, [C.POINTER(RoiLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "hd_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "hd_roi_level_map": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp]),
 }
 
 _lib = None

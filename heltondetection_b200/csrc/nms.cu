@@ -9,9 +9,9 @@
 // whole image.  Work is kept*n instead of n^2/2 and the loop stops as soon as max_det boxes are kept,
 // which is what the detection callers (max_det=300, RPN post_nms_top_n) need.
 #include "hd_sort.cuh"
+#include "hd_nms_core.cuh"
 
 #define NMS_NT 1024
-#define NMS_CHUNK 64
 
 struct NmsParams {
     const float4* boxes;
@@ -32,27 +32,12 @@ struct NmsParams {
     float4* sbox; int* scls; int* keep_r;
 };
 
-__device__ __forceinline__ bool hd_iou_gt(const float4& a, float area_a, const float4& b, float area_b, float thr) {
-    float xx1 = hd_stdmax(a.x, b.x), yy1 = hd_stdmax(a.y, b.y);
-    float xx2 = hd_stdmin(a.z, b.z), yy2 = hd_stdmin(a.w, b.w);
-    float w = hd_stdmax(0.0f, __fsub_rn(xx2, xx1));
-    float h = hd_stdmax(0.0f, __fsub_rn(yy2, yy1));
-    if (thr >= 0.0f && !(w > 0.0f && h > 0.0f)) return false;  // inter == 0 -> iou is 0, -0 or NaN: never > thr
-    float inter = __fmul_rn(w, h);
-    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter)) > thr;
-}
-
 __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_constant__ NmsParams p) {
     extern __shared__ uint32_t removed[];  // ceil(cap/32) words (+1 pad)
     __shared__ HdSortSmem<NMS_NT> ssm;
-    __shared__ float4 cbox[NMS_CHUNK];
-    __shared__ float carea[NMS_CHUNK];
-    __shared__ int ccls[NMS_CHUNK];
-    __shared__ unsigned long long cmask[NMS_CHUNK];
-    __shared__ unsigned long long s_kept;
-    __shared__ int s_kc;
+    __shared__ HdNmsSmem nsm;
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x;
     const int b = blockIdx.x;
     int n = p.counts ? min(p.counts[b], p.cap) : p.n_fixed;
     if (n <= 0) {
@@ -88,84 +73,8 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
         sbox[r] = bx;
         scls[r] = (p.class_mode == HD_NMS_CLASS_EXACT) ? c : 0;
     }
-    for (int i = tid; i < (n_use + 31) / 32 + 1; i += NMS_NT) removed[i] = 0;
     __syncthreads();
-
-    int kc = 0;
-    for (int base = 0; base < n_use; base += NMS_CHUNK) {
-        const int m = min(NMS_CHUNK, n_use - base);
-        if (tid < NMS_CHUNK) {
-            cmask[tid] = 0ull;
-            if (tid < m) {
-                float4 bx = sbox[base + tid];
-                cbox[tid] = bx;
-                carea[tid] = hd_area(bx);
-                ccls[tid] = scls[base + tid];
-            }
-        }
-        __syncthreads();
-        {   // 64x64 upper-triangular mask: 16 threads per row, 4 columns each
-            const int i = tid >> 4, j0 = (tid & 15) * 4;
-            if (i < m) {
-                unsigned long long bits = 0ull;
-                const float4 bi = cbox[i];
-                const float ai = carea[i];
-                const int ci = ccls[i];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int jj = j0 + q;
-                    if (jj > i && jj < m && ccls[jj] == ci && hd_iou_gt(bi, ai, cbox[jj], carea[jj], p.thr)) bits |= 1ull << jj;
-                }
-                if (bits) atomicOr(&cmask[i], bits);
-            }
-        }
-        __syncthreads();
-        if (wid == 0) {
-            const unsigned long long rem = (unsigned long long)removed[base >> 5] | ((unsigned long long)removed[(base >> 5) + 1] << 32);
-            unsigned long long alive = ~rem & ((m == 64) ? ~0ull : ((1ull << m) - 1ull));
-            unsigned long long kept = 0ull;
-            int room = max_det - kc;
-            while (alive && room > 0) {
-                const int i = __ffsll((long long)alive) - 1;
-                kept |= 1ull << i;
-                alive &= ~cmask[i];
-                alive &= ~(1ull << i);
-                --room;
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int bit = lane + 32 * h;
-                if ((kept >> bit) & 1ull) keep_r[kc + __popcll(kept & ((1ull << bit) - 1ull))] = base + bit;
-            }
-            if (lane == 0) {
-                s_kept = kept;
-                s_kc = kc + __popcll(kept);
-            }
-        }
-        __syncthreads();
-        const unsigned long long kept = s_kept;
-        kc = s_kc;
-        const bool done = kc >= max_det;
-        if (!done && kept) {
-            for (int jr = base + NMS_CHUNK + tid; jr < n_use; jr += NMS_NT) {
-                if ((removed[jr >> 5] >> (jr & 31)) & 1u) continue;
-                const float4 bj = sbox[jr];
-                const float aj = hd_area(bj);
-                const int cj = scls[jr];
-                unsigned long long kk = kept;
-                while (kk) {
-                    const int i = __ffsll((long long)kk) - 1;
-                    kk &= kk - 1ull;
-                    if (ccls[i] == cj && hd_iou_gt(cbox[i], carea[i], bj, aj, p.thr)) {
-                        atomicOr(&removed[jr >> 5], 1u << (jr & 31));
-                        break;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (done) break;
-    }
+    const int kc = hd_cta_greedy_nms<NMS_NT>(sbox, (p.class_mode == HD_NMS_CLASS_EXACT) ? scls : nullptr, n_use, max_det, p.thr, removed, keep_r, nsm);
 
     for (int q = tid; q < kc; q += NMS_NT) {
         const int r = keep_r[q];
@@ -263,7 +172,7 @@ extern "C" HD_API int hd_sort_nms_batched(const float* boxes, const float* score
     p.k0 = (uint64_t*)(w0 + offs[0]); p.k1 = (uint64_t*)(w0 + offs[1]);
     p.v0 = (uint32_t*)(w0 + offs[2]); p.v1 = (uint32_t*)(w0 + offs[3]);
     p.sbox = (float4*)(w0 + offs[4]); p.scls = (int*)(w0 + offs[5]); p.keep_r = (int*)(w0 + offs[6]);
-    size_t smem = ((size_t)(cap + 31) / 32 + 2) * 4;
+    size_t smem = ((size_t)(cap + 31) / 32 + 4) * 4;
     HD_CHECK_ARG(smem <= 160 * 1024, "cap=%d too large for the shared-memory removed bitmap", cap);
     static size_t smem_set = 0;
     if (smem > smem_set) {

@@ -1,0 +1,398 @@
+// RoIAlign / RoIPool / FPN level assignment (a7-a9).  Replaces torchvision::roi_align / roi_pool
+// (roi_align.py:204-260, roi_pool.py:15-53) and the LevelMapper / MultiScaleRoIAlign gather-scatter
+// (poolers.py:73-84, 147-227).  Reference feature: README.md:65,73-78.
+//
+// Fast layout is channel-contiguous (NHWC / torch channels_last): one CTA per RoI, one thread per
+// channel, so every corner fetch of a warp is one coalesced 128-byte line.  Bilinear sampling on the
+// regular per-bin sample grid is separable, so each RoI first builds per-axis tables of
+// (cell, merged weight) in shared memory; a bin then costs ny*nx (typically 4-9) loads instead of the
+// 16*grid^2/4 corner reads of the sample-by-sample form.  The [C,PH,PW] result tile is assembled in
+// shared memory in exactly the output layout and leaves with ONE TMA bulk store (cp.async.bulk).
+#include "hd_common.cuh"
+
+#define ROI_MAX_LEVELS HD_MAX_LEVELS
+#define ROI_TAB 1024  // table entries per axis
+
+struct RoiParams {
+    const float* data[ROI_MAX_LEVELS];
+    int H[ROI_MAX_LEVELS], W[ROI_MAX_LEVELS];
+    float scale[ROI_MAX_LEVELS];
+    int n_levels, C, PH, PW, sampling_ratio, aligned;
+    const float* rois;       // [K,5]
+    const int* level_ids;    // [K] or NULL (level 0)
+    long long K;
+    float* out;              // [K,C,PH,PW]
+    int* argmax;             // roi_pool only, nullable
+};
+
+struct AxisEntry { int off; float w; };  // off = cell index premultiplied by the element stride of the axis
+
+// Per-axis table of one RoI: bin b owns entries [b*stride, b*stride + cnt[b]).  Sample positions grow
+// monotonically inside a bin, so a cell that was already emitted is one of the last two entries.
+__device__ __forceinline__ void build_axis(AxisEntry* tab, int* cnt, int b, int stride, float start, float bin_size, int grid,
+                                           int extent, int elem_stride) {
+    int n = 0;
+    AxisEntry* t = tab + b * stride;
+    auto add = [&](int cell, float w) {
+        const int off = cell * elem_stride;
+        if (n >= 1 && t[n - 1].off == off) t[n - 1].w = __fadd_rn(t[n - 1].w, w);
+        else if (n >= 2 && t[n - 2].off == off) t[n - 2].w = __fadd_rn(t[n - 2].w, w);
+        else { t[n].off = off; t[n].w = w; ++n; }
+    };
+    for (int i = 0; i < grid; ++i) {
+        // y = roi_start + ph*bin_size + (iy + .5f) * bin_size / grid   (fp32, left to right)
+        float y = __fadd_rn(__fadd_rn(start, __fmul_rn((float)b, bin_size)),
+                            __fdiv_rn(__fmul_rn(__fadd_rn((float)i, 0.5f), bin_size), (float)grid));
+        if (y < -1.0f || y > (float)extent) continue;  // sample contributes 0 (C++/CUDA kernel rule)
+        if (y <= 0.0f) y = 0.0f;
+        int lo = (int)y, hi;
+        if (lo >= extent - 1) { hi = lo = extent - 1; y = (float)lo; } else hi = lo + 1;
+        const float l = __fsub_rn(y, (float)lo), h = __fsub_rn(1.0f, l);
+        add(lo, h);
+        add(hi, l);
+    }
+    cnt[b] = n;
+}
+
+__device__ __forceinline__ void tile_store(float* __restrict__ gdst, const float* tile, int n_floats, bool use_tma) {
+    if (use_tma) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned saddr = (unsigned)__cvta_generic_to_shared(tile);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(n_floats * 4) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_floats; i += blockDim.x) gdst[i] = tile[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ RoIAlign NHWC
+__global__ void __launch_bounds__(256) roi_align_nhwc_kernel(const __grid_constant__ RoiParams p, int use_tma) {
+    extern __shared__ __align__(128) float smem_f[];
+    float* tile = smem_f;                                  // [C][PH*PW]
+    AxisEntry* ytab = (AxisEntry*)(tile + (size_t)p.C * p.PH * p.PW);
+    AxisEntry* xtab = ytab + ROI_TAB;
+    __shared__ int ycnt[64], xcnt[64];
+
+    const long long k = blockIdx.x;
+    const float* roi = p.rois + k * 5;
+    const int lvl = p.level_ids ? p.level_ids[k] : 0;
+    const int H = p.H[lvl], W = p.W[lvl];
+    const float sc = p.scale[lvl];
+    const int bidx = (int)roi[0];
+    const float off = p.aligned ? 0.5f : 0.0f;
+    const float sw = __fsub_rn(__fmul_rn(roi[1], sc), off), sh = __fsub_rn(__fmul_rn(roi[2], sc), off);
+    const float ew = __fsub_rn(__fmul_rn(roi[3], sc), off), eh = __fsub_rn(__fmul_rn(roi[4], sc), off);
+    float rw = __fsub_rn(ew, sw), rh = __fsub_rn(eh, sh);
+    if (!p.aligned) { rw = fmaxf(rw, 1.0f); rh = fmaxf(rh, 1.0f); }
+    const float bh = __fdiv_rn(rh, (float)p.PH), bw = __fdiv_rn(rw, (float)p.PW);
+    const int gh = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)p.PH));
+    const int gw = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)p.PW));
+    const float count = (float)max(gh * gw, 1);
+    const int stride_y = max(2 * max(gh, 0), 1), stride_x = max(2 * max(gw, 0), 1);
+    const bool fits = (long long)stride_y * p.PH <= ROI_TAB && (long long)stride_x * p.PW <= ROI_TAB;
+    if (fits) {
+        if (threadIdx.x < p.PH) build_axis(ytab, ycnt, threadIdx.x, stride_y, sh, bh, gh, H, W * p.C);
+        else if (threadIdx.x >= 64 && threadIdx.x < 64 + p.PW) build_axis(xtab, xcnt, threadIdx.x - 64, stride_x, sw, bw, gw, W, p.C);
+    }
+    __syncthreads();
+    const float* __restrict__ f = p.data[lvl] + (size_t)bidx * H * W * p.C;
+    const int nb = p.PH * p.PW;
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+        const float* __restrict__ fc = f + c;
+        for (int ph = 0; ph < p.PH; ++ph) {
+            for (int pw = 0; pw < p.PW; ++pw) {
+                float acc = 0.0f;
+                if (fits) {
+                    const AxisEntry* yt = ytab + ph * stride_y;
+                    const AxisEntry* xt = xtab + pw * stride_x;
+                    const int ny = ycnt[ph], nx = xcnt[pw];
+                    for (int a = 0; a < ny; ++a) {
+                        const float wy = yt[a].w;
+                        const float* __restrict__ row = fc + yt[a].off;
+                        for (int b = 0; b < nx; ++b) acc = fmaf(wy * xt[b].w, __ldg(row + xt[b].off), acc);
+                    }
+                } else {
+                    // huge adaptive grids: sample by sample, no tables
+                    for (int iy = 0; iy < gh; ++iy) {
+                        float y = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)ph, bh)), __fdiv_rn(__fmul_rn(__fadd_rn((float)iy, 0.5f), bh), (float)gh));
+                        if (y < -1.0f || y > (float)H) continue;
+                        if (y <= 0.0f) y = 0.0f;
+                        int yl = (int)y, yh;
+                        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+                        const float ly = y - (float)yl, hy = 1.0f - ly;
+                        for (int ix = 0; ix < gw; ++ix) {
+                            float x = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)pw, bw)), __fdiv_rn(__fmul_rn(__fadd_rn((float)ix, 0.5f), bw), (float)gw));
+                            if (x < -1.0f || x > (float)W) continue;
+                            if (x <= 0.0f) x = 0.0f;
+                            int xl = (int)x, xh;
+                            if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+                            const float lx = x - (float)xl, hx = 1.0f - lx;
+                            acc += hy * hx * __ldg(fc + ((size_t)yl * W + xl) * p.C) + hy * lx * __ldg(fc + ((size_t)yl * W + xh) * p.C) +
+                                   ly * hx * __ldg(fc + ((size_t)yh * W + xl) * p.C) + ly * lx * __ldg(fc + ((size_t)yh * W + xh) * p.C);
+                        }
+                    }
+                }
+                tile[c * nb + ph * p.PW + pw] = __fdiv_rn(acc, count);
+            }
+        }
+    }
+    tile_store(p.out + (size_t)k * p.C * nb, tile, p.C * nb, use_tma != 0);
+}
+
+// ------------------------------------------------------------------------------------------------ RoIPool NHWC
+__global__ void __launch_bounds__(256) roi_pool_nhwc_kernel(const __grid_constant__ RoiParams p, int use_tma) {
+    extern __shared__ __align__(128) float smem_f[];
+    float* tile = smem_f;
+    const long long k = blockIdx.x;
+    const float* roi = p.rois + k * 5;
+    const int lvl = p.level_ids ? p.level_ids[k] : 0;
+    const int H = p.H[lvl], W = p.W[lvl];
+    const float sc = p.scale[lvl];
+    const int bidx = (int)roi[0];
+    const int x1 = (int)roundf(__fmul_rn(roi[1], sc)), y1 = (int)roundf(__fmul_rn(roi[2], sc));
+    const int x2 = (int)roundf(__fmul_rn(roi[3], sc)), y2 = (int)roundf(__fmul_rn(roi[4], sc));
+    const int rw = max(x2 - x1 + 1, 1), rh = max(y2 - y1 + 1, 1);
+    const float bh = __fdiv_rn((float)rh, (float)p.PH), bw = __fdiv_rn((float)rw, (float)p.PW);
+    const float* __restrict__ f = p.data[lvl] + (size_t)bidx * H * W * p.C;
+    const int nb = p.PH * p.PW;
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+        for (int ph = 0; ph < p.PH; ++ph) {
+            const int hs = min(max((int)floorf(__fmul_rn((float)ph, bh)) + y1, 0), H);
+            const int he = min(max((int)ceilf(__fmul_rn((float)(ph + 1), bh)) + y1, 0), H);
+            for (int pw = 0; pw < p.PW; ++pw) {
+                const int ws = min(max((int)floorf(__fmul_rn((float)pw, bw)) + x1, 0), W);
+                const int we = min(max((int)ceilf(__fmul_rn((float)(pw + 1), bw)) + x1, 0), W);
+                const bool empty = (he <= hs) || (we <= ws);
+                float mx = empty ? 0.0f : -INFINITY;
+                int mi = -1;
+                for (int h = hs; h < he; ++h)
+                    for (int w = ws; w < we; ++w) {
+                        float v = __ldg(f + ((size_t)h * W + w) * p.C + c);
+                        if (v > mx) { mx = v; mi = h * W + w; }
+                    }
+                tile[c * nb + ph * p.PW + pw] = mx;
+                if (p.argmax) p.argmax[((size_t)k * p.C + c) * nb + ph * p.PW + pw] = mi;
+            }
+        }
+    }
+    tile_store(p.out + (size_t)k * p.C * nb, tile, p.C * nb, use_tma != 0);
+}
+
+// ------------------------------------------------------------------------------------------------ direct NCHW
+// warp per (roi, channel), lane per bin: reference-order sample-by-sample arithmetic.  Used for few RoIs
+// (where a layout pass over the whole feature map would dominate) and as the in-library cross-check.
+template <bool POOL>
+__global__ void __launch_bounds__(256) roi_nchw_kernel(const __grid_constant__ RoiParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wg >= p.K * p.C) return;
+    const long long k = wg / p.C;
+    const int c = (int)(wg - k * p.C);
+    const float* roi = p.rois + k * 5;
+    const int lvl = p.level_ids ? p.level_ids[k] : 0;
+    const int H = p.H[lvl], W = p.W[lvl];
+    const float sc = p.scale[lvl];
+    const int bidx = (int)roi[0];
+    const float* __restrict__ f = p.data[lvl] + ((size_t)bidx * p.C + c) * H * W;
+    const int nb = p.PH * p.PW;
+    float* o = p.out + ((size_t)k * p.C + c) * nb;
+    if (POOL) {
+        const int x1 = (int)roundf(__fmul_rn(roi[1], sc)), y1 = (int)roundf(__fmul_rn(roi[2], sc));
+        const int x2 = (int)roundf(__fmul_rn(roi[3], sc)), y2 = (int)roundf(__fmul_rn(roi[4], sc));
+        const int rw = max(x2 - x1 + 1, 1), rh = max(y2 - y1 + 1, 1);
+        const float bh = __fdiv_rn((float)rh, (float)p.PH), bw = __fdiv_rn((float)rw, (float)p.PW);
+        for (int bin = lane; bin < nb; bin += 32) {
+            const int ph = bin / p.PW, pw = bin - ph * p.PW;
+            const int hs = min(max((int)floorf(__fmul_rn((float)ph, bh)) + y1, 0), H);
+            const int he = min(max((int)ceilf(__fmul_rn((float)(ph + 1), bh)) + y1, 0), H);
+            const int ws = min(max((int)floorf(__fmul_rn((float)pw, bw)) + x1, 0), W);
+            const int we = min(max((int)ceilf(__fmul_rn((float)(pw + 1), bw)) + x1, 0), W);
+            const bool empty = (he <= hs) || (we <= ws);
+            float mx = empty ? 0.0f : -INFINITY;
+            int mi = -1;
+            for (int h = hs; h < he; ++h)
+                for (int w = ws; w < we; ++w) {
+                    float v = __ldg(f + (size_t)h * W + w);
+                    if (v > mx) { mx = v; mi = h * W + w; }
+                }
+            o[bin] = mx;
+            if (p.argmax) p.argmax[((size_t)k * p.C + c) * nb + bin] = mi;
+        }
+    } else {
+        const float off = p.aligned ? 0.5f : 0.0f;
+        const float sw = __fsub_rn(__fmul_rn(roi[1], sc), off), sh = __fsub_rn(__fmul_rn(roi[2], sc), off);
+        const float ew = __fsub_rn(__fmul_rn(roi[3], sc), off), eh = __fsub_rn(__fmul_rn(roi[4], sc), off);
+        float rw = __fsub_rn(ew, sw), rh = __fsub_rn(eh, sh);
+        if (!p.aligned) { rw = fmaxf(rw, 1.0f); rh = fmaxf(rh, 1.0f); }
+        const float bh = __fdiv_rn(rh, (float)p.PH), bw = __fdiv_rn(rw, (float)p.PW);
+        const int gh = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)p.PH));
+        const int gw = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)p.PW));
+        const float count = (float)max(gh * gw, 1);
+        for (int bin = lane; bin < nb; bin += 32) {
+            const int ph = bin / p.PW, pw = bin - ph * p.PW;
+            float acc = 0.0f;
+            for (int iy = 0; iy < gh; ++iy) {
+                float y = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)ph, bh)), __fdiv_rn(__fmul_rn(__fadd_rn((float)iy, 0.5f), bh), (float)gh));
+                if (y < -1.0f || y > (float)H) continue;
+                if (y <= 0.0f) y = 0.0f;
+                int yl = (int)y, yh;
+                if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+                const float ly = __fsub_rn(y, (float)yl), hy = __fsub_rn(1.0f, ly);
+                for (int ix = 0; ix < gw; ++ix) {
+                    float x = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)pw, bw)), __fdiv_rn(__fmul_rn(__fadd_rn((float)ix, 0.5f), bw), (float)gw));
+                    if (x < -1.0f || x > (float)W) continue;
+                    if (x <= 0.0f) x = 0.0f;
+                    int xl = (int)x, xh;
+                    if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+                    const float lx = __fsub_rn(x, (float)xl), hx = __fsub_rn(1.0f, lx);
+                    // w1*v1 + w2*v2 + w3*v3 + w4*v4, left to right, then added to the running sum
+                    float s = __fmul_rn(__fmul_rn(hy, hx), __ldg(f + (size_t)yl * W + xl));
+                    s = __fadd_rn(s, __fmul_rn(__fmul_rn(hy, lx), __ldg(f + (size_t)yl * W + xh)));
+                    s = __fadd_rn(s, __fmul_rn(__fmul_rn(ly, hx), __ldg(f + (size_t)yh * W + xl)));
+                    s = __fadd_rn(s, __fmul_rn(__fmul_rn(ly, lx), __ldg(f + (size_t)yh * W + xh)));
+                    acc = __fadd_rn(acc, s);
+                }
+            }
+            o[bin] = __fdiv_rn(acc, count);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ layout pass
+// [B, C, HW] -> [B, HW, C] through a 32x33 shared tile (both sides coalesced).
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int HW) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.z;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const float* src = in + (size_t)b * C * HW;
+    float* dst = out + (size_t)b * C * HW;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (c0 + r < C && hw0 + tx < HW) t[r][tx] = hd_ldg_stream(src + (size_t)(c0 + r) * HW + hw0 + tx);
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (hw0 + r < HW && c0 + tx < C) dst[(size_t)(hw0 + r) * C + c0 + tx] = t[tx][r];
+}
+
+// ------------------------------------------------------------------------------------------------ level map
+__global__ void roi_level_map_kernel(const float* __restrict__ rois, int stride, int box_off, long long K, int style, int k_min,
+                                     int k_max, float s0, float lvl0, float eps, int* __restrict__ out32, long long* __restrict__ out64) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const float* r = rois + i * stride + box_off;
+    const float area = __fmul_rn(__fsub_rn(r[2], r[0]), __fsub_rn(r[3], r[1]));
+    const float s = __fsqrt_rn(area);
+    int lv;
+    if (style == 1) {  // mmdet: floor(log2(s / finest_scale + eps)), clamp [0, L-1]
+        float v = floorf(log2f(__fadd_rn(__fdiv_rn(s, s0), eps)));
+        v = fminf(fmaxf(v, 0.0f), (float)(k_max - k_min));
+        lv = (v != v) ? 0 : (int)v;
+    } else {           // torchvision: floor(lvl0 + log2(s / s0) + eps), clamp [k_min, k_max], - k_min
+        float v = floorf(__fadd_rn(__fadd_rn(lvl0, log2f(__fdiv_rn(s, s0))), eps));
+        v = fminf(fmaxf(v, (float)k_min), (float)k_max);
+        lv = ((v != v) ? k_min : (int)v) - k_min;
+    }
+    if (out32) out32[i] = lv;
+    if (out64) out64[i] = lv;
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int fill_roi(RoiParams& p, const hd_roi_level* levels, int n_levels, int C, const float* rois, const int32_t* level_ids,
+                    int64_t K, int PH, int PW, int sampling_ratio, int aligned, float* out, int32_t* argmax) {
+    HD_CHECK_ARG(levels != nullptr && n_levels >= 1 && n_levels <= ROI_MAX_LEVELS, "n_levels must be in [1,%d], got %d", ROI_MAX_LEVELS, n_levels);
+    HD_CHECK_ARG(C >= 1 && PH >= 1 && PW >= 1 && PH <= 64 && PW <= 64, "bad C=%d or output size %dx%d (max 64x64)", C, PH, PW);
+    HD_CHECK_ARG(K >= 0, "K must be >= 0");
+    HD_CHECK_ARG(n_levels == 1 || level_ids != nullptr || K == 0, "level_ids is NULL for a multi-level call");
+    memset(&p, 0, sizeof(p));
+    for (int l = 0; l < n_levels; ++l) {
+        HD_CHECK_ARG(levels[l].H > 0 && levels[l].W > 0, "level %d has an empty feature map", l);
+        HD_CHECK_ARG(K == 0 || levels[l].data != nullptr, "level %d data is NULL", l);
+        p.data[l] = levels[l].data; p.H[l] = levels[l].H; p.W[l] = levels[l].W; p.scale[l] = levels[l].spatial_scale;
+    }
+    p.n_levels = n_levels; p.C = C; p.PH = PH; p.PW = PW; p.sampling_ratio = sampling_ratio; p.aligned = aligned;
+    p.rois = rois; p.level_ids = level_ids; p.K = K; p.out = out; p.argmax = argmax;
+    return HD_OK;
+}
+
+static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st) {
+    if (p.K == 0) return HD_OK;
+    HD_CHECK_ARG(p.rois && p.out, "rois/out is NULL");
+    if (layout == HD_LAYOUT_NHWC) {
+        size_t tile = (size_t)p.C * p.PH * p.PW * 4;
+        size_t smem = tile + (pool ? 0 : 2 * ROI_TAB * sizeof(AxisEntry));
+        HD_CHECK_ARG(smem <= 220 * 1024, "C*PH*PW=%d floats exceed the shared-memory tile", p.C * p.PH * p.PW);
+        HD_CHECK_ARG(p.K < (1ll << 31), "too many RoIs");
+        int use_tma = (tile % 16 == 0) && (((uintptr_t)p.out & 15) == 0);
+        static bool attr_set = false;
+        if (!attr_set) {
+            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            HD_CUDA_CALL(cudaFuncSetAttribute(roi_pool_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            attr_set = true;
+        }
+        int threads = p.C >= 256 ? 256 : ((p.C + 31) / 32 * 32 < 128 ? 128 : (p.C + 31) / 32 * 32);
+        for (int l = 0; l < p.n_levels; ++l) HD_CHECK_ARG((long long)p.H[l] * p.W[l] * p.C < (1ll << 31), "level %d: H*W*C must be < 2^31", l);
+        if (pool) roi_pool_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
+        else roi_align_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
+        HD_CUDA_LAUNCH_CHECK("roi_nhwc_kernel");
+    } else if (layout == HD_LAYOUT_NCHW) {
+        long long warps = p.K * p.C;
+        long long blocks = (warps + 7) / 8;
+        HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
+        if (pool) roi_nchw_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(p);
+        else roi_nchw_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(p);
+        HD_CUDA_LAUNCH_CHECK("roi_nchw_kernel");
+    } else {
+        HD_FAIL(HD_ERR_INVALID, "layout must be HD_LAYOUT_NCHW or HD_LAYOUT_NHWC, got %d", layout);
+    }
+    return HD_OK;
+}
+
+extern "C" HD_API int hd_roi_align(const hd_roi_level* levels, int n_levels, int layout, int C, const float* rois, const int32_t* level_ids,
+                                   int64_t K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, float* out, void* stream) {
+    RoiParams p;
+    int rc = fill_roi(p, levels, n_levels, C, rois, level_ids, K, pooled_h, pooled_w, sampling_ratio, aligned, out, nullptr);
+    if (rc) return rc;
+    return launch_roi(p, layout, false, (cudaStream_t)stream);
+}
+
+extern "C" HD_API int hd_roi_pool(const hd_roi_level* levels, int n_levels, int layout, int C, const float* rois, const int32_t* level_ids,
+                                  int64_t K, int pooled_h, int pooled_w, float* out, int32_t* argmax, void* stream) {
+    RoiParams p;
+    int rc = fill_roi(p, levels, n_levels, C, rois, level_ids, K, pooled_h, pooled_w, 0, 0, out, argmax);
+    if (rc) return rc;
+    return launch_roi(p, layout, true, (cudaStream_t)stream);
+}
+
+extern "C" HD_API int hd_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, void* stream) {
+    HD_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1, "bad shape");
+    if (B == 0) return HD_OK;
+    HD_CHECK_ARG(in && out, "null pointer");
+    HD_CHECK_ARG(B <= 65535 && (C + 31) / 32 <= 65535, "B or C too large");
+    int HW = H * W;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+    nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, C, HW);
+    HD_CUDA_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+    return HD_OK;
+}
+
+extern "C" HD_API int hd_roi_level_map(const float* rois, int roi_stride, int box_offset, int64_t K, int style, int k_min, int k_max,
+                                       float canonical_scale, float canonical_level, float eps, int32_t* levels32, int64_t* levels64,
+                                       void* stream) {
+    HD_CHECK_ARG(K >= 0 && roi_stride >= 4 && box_offset >= 0 && box_offset + 4 <= roi_stride, "bad roi layout");
+    HD_CHECK_ARG(k_max >= k_min, "k_max < k_min");
+    if (K == 0) return HD_OK;
+    HD_CHECK_ARG(rois && (levels32 || levels64), "null pointer");
+    float s0 = canonical_scale;
+    if (style == 1) s0 = canonical_scale / exp2f(canonical_level - (float)k_min);  // mmdet finest_scale (56 for 224/4/2)
+    roi_level_map_kernel<<<(unsigned)((K + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rois, roi_stride, box_offset, K, style, k_min, k_max, s0,
+                                                                                      canonical_level, eps, levels32, (long long*)levels64);
+    HD_CUDA_LAUNCH_CHECK("roi_level_map_kernel");
+    return HD_OK;
+}

@@ -1,0 +1,355 @@
+// RPN proposal creation (a6): fused anchor generation + delta decode + clip + min-size + score, then per image
+// radix-select top-k -> sort -> greedy NMS -> first n_post.  Reference feature: README.md:8,63-65; semantics
+// SURVEY.md A.3 (bubbliiiing ProposalCreator / loc2bbox lineage, README.md:158; cross-checked with torchvision
+// models/detection/rpn.py:231-297, _utils.py:183-224).
+#include "hd_sort.cuh"
+#include "hd_nms_core.cuh"
+
+#define RPN_NT 1024
+
+struct RpnParams {
+    const float* obj[HD_MAX_LEVELS];
+    const float* dlt[HD_MAX_LEVELS];
+    int H[HD_MAX_LEVELS], W[HD_MAX_LEVELS];
+    float stride[HD_MAX_LEVELS];
+    float base[HD_MAX_LEVELS][4 * HD_MAX_ANCHORS];
+    int cell_start[HD_MAX_LEVELS + 1];  // cumulative cells
+    int level_off[HD_MAX_LEVELS + 1];   // cumulative anchors
+    int n_levels, B, A, softmax;
+    float img_h, img_w, min_size, clamp_dwh;
+    int use_clamp;
+    long long total_cells;  // B * sum(HW)
+    int N;                  // anchors per image
+};
+
+// ------------------------------------------------------------------------------------------------
+// decode: one thread per (image, level, cell); it walks the A anchors of its cell, so every head plane is
+// read coalesced along W and the A decoded boxes of a cell leave as one contiguous A*16-byte run
+// (flat proposal index = level_off + cell*A + a, the permute(0,2,3,1) order of the reference).
+//   key  = orderable(score) (0 is reserved for boxes dropped by the min-size test)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rpn_decode_kernel(const __grid_constant__ RpnParams p, float4* __restrict__ boxes,
+                                                         float* __restrict__ scores, uint32_t* __restrict__ keys) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.total_cells) return;
+    const int cells_per_img = p.cell_start[p.n_levels];
+    const int b = (int)(g / cells_per_img);
+    int r = (int)(g - (long long)b * cells_per_img);
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < HD_MAX_LEVELS; ++q)
+        if (q < p.n_levels && r >= p.cell_start[q]) l = q;
+    const int cell = r - p.cell_start[l];
+    const int HW = p.H[l] * p.W[l], W = p.W[l];
+    const int gi = cell / W, gj = cell - gi * W;
+    const float sx = __fmul_rn((float)gj, p.stride[l]), sy = __fmul_rn((float)gi, p.stride[l]);
+    const int oc = p.softmax ? 2 * p.A : p.A;
+    const float* __restrict__ ob = p.obj[l] + (size_t)b * oc * HW + cell;
+    const float* __restrict__ dl = p.dlt[l] + (size_t)b * 4 * p.A * HW + cell;
+    const size_t out0 = (size_t)b * p.N + p.level_off[l] + (size_t)cell * p.A;
+    for (int a = 0; a < p.A; ++a) {
+        float score;
+        if (p.softmax) {  // F.softmax over (bg, fg): exp(x - max) / sum
+            const float s0 = hd_ldg_stream(ob + (size_t)(2 * a) * HW), s1 = hd_ldg_stream(ob + (size_t)(2 * a + 1) * HW);
+            const float m = fmaxf(s0, s1);
+            const float e0 = expf(__fsub_rn(s0, m)), e1 = expf(__fsub_rn(s1, m));
+            score = __fdiv_rn(e1, __fadd_rn(e0, e1));
+        } else {
+            score = hd_sigmoid(hd_ldg_stream(ob + (size_t)a * HW));
+        }
+        const float dx = hd_ldg_stream(dl + (size_t)(4 * a) * HW), dy = hd_ldg_stream(dl + (size_t)(4 * a + 1) * HW);
+        float dw = hd_ldg_stream(dl + (size_t)(4 * a + 2) * HW), dh = hd_ldg_stream(dl + (size_t)(4 * a + 3) * HW);
+        if (p.use_clamp) { dw = fminf(dw, p.clamp_dwh); dh = fminf(dh, p.clamp_dwh); }
+        // anchor = base + shift (fp32 add, as enumerate_shifted_anchor)
+        const float ax1 = __fadd_rn(p.base[l][4 * a], sx), ay1 = __fadd_rn(p.base[l][4 * a + 1], sy);
+        const float ax2 = __fadd_rn(p.base[l][4 * a + 2], sx), ay2 = __fadd_rn(p.base[l][4 * a + 3], sy);
+        // loc2bbox
+        const float wa = __fsub_rn(ax2, ax1), ha = __fsub_rn(ay2, ay1);
+        const float cxa = __fadd_rn(ax1, __fmul_rn(0.5f, wa)), cya = __fadd_rn(ay1, __fmul_rn(0.5f, ha));
+        const float cx = __fadd_rn(__fmul_rn(dx, wa), cxa), cy = __fadd_rn(__fmul_rn(dy, ha), cya);
+        const float w = __fmul_rn(expf(dw), wa), h = __fmul_rn(expf(dh), ha);
+        float x1 = __fsub_rn(cx, __fmul_rn(0.5f, w)), y1 = __fsub_rn(cy, __fmul_rn(0.5f, h));
+        float x2 = __fadd_rn(cx, __fmul_rn(0.5f, w)), y2 = __fadd_rn(cy, __fmul_rn(0.5f, h));
+        // clip to the image (torch.clamp(min=0, max=size))
+        x1 = fminf(fmaxf(x1, 0.0f), p.img_w); x2 = fminf(fmaxf(x2, 0.0f), p.img_w);
+        y1 = fminf(fmaxf(y1, 0.0f), p.img_h); y2 = fminf(fmaxf(y2, 0.0f), p.img_h);
+        const bool ok = (__fsub_rn(x2, x1) >= p.min_size) && (__fsub_rn(y2, y1) >= p.min_size);
+        boxes[out0 + a] = make_float4(x1, y1, x2, y2);
+        scores[out0 + a] = score;
+        uint32_t k = hd_orderable(score);
+        keys[out0 + a] = ok ? (k == 0u ? 1u : k) : 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// select + sort + NMS: one CTA per image.
+//   1. radix select (MSB first, 8-bit digits, warp-aggregated shared histograms) of the k-th largest
+//      64-bit composite (key << 32 | ~index): composites are unique, so "composite >= T" selects exactly k
+//      elements with ties going to the lower index, like a stable descending sort.
+//   2. the k selected elements are compacted and radix-sorted on (score desc, index asc);
+//   3. lazy chunked greedy NMS (hd_nms_core.cuh) until n_post boxes are kept.
+// ------------------------------------------------------------------------------------------------
+struct RpnSelParams {
+    const float4* boxes; const float* scores; const uint32_t* keys;
+    int B, N, n_pre, n_post;
+    float thr;
+    float* out_rois;   // [B, n_post, 5]
+    float* out_scores; // [B, n_post] nullable
+    long long* out_idx;  // [B, n_post] nullable
+    int* out_count;
+    int cap;           // per-image workspace stride (>= min(n_pre, N))
+    uint64_t* k0; uint64_t* k1; uint32_t* v0; uint32_t* v1; float4* sbox; int* keep_r;
+};
+
+__device__ __forceinline__ uint64_t rpn_composite(uint32_t key, int idx) { return ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)idx); }
+
+__global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_constant__ RpnSelParams p) {
+    extern __shared__ uint32_t removed[];
+    __shared__ HdSortSmem<RPN_NT> ssm;
+    __shared__ HdNmsSmem nsm;
+    __shared__ int s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_need, s_valid, s_count;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.x;
+    const uint32_t* __restrict__ keys = p.keys + (size_t)b * p.N;
+    const size_t off = (size_t)b * p.cap;
+    uint64_t* k0 = p.k0 + off; uint64_t* k1 = p.k1 + off;
+    uint32_t* v0 = p.v0 + off; uint32_t* v1 = p.v1 + off;
+    float4* sbox = p.sbox + off;
+    int* keep_r = p.keep_r + off;
+
+    // number of valid (key != 0) proposals
+    if (tid == 0) { s_valid = 0; s_count = 0; }
+    __syncthreads();
+    {
+        int c = 0;
+        for (int i = tid; i < p.N; i += RPN_NT) c += keys[i] != 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(HD_FULL, c, d);
+        if (lane == 0 && c) atomicAdd(&s_valid, c);
+    }
+    __syncthreads();
+    const int k = (p.n_pre > 0) ? min(p.n_pre, s_valid) : s_valid;
+    if (k == 0) {
+        for (int q = tid; q < p.n_post; q += RPN_NT) {
+            float* o = p.out_rois + ((size_t)b * p.n_post + q) * 5;
+            o[0] = (float)b; o[1] = o[2] = o[3] = o[4] = 0.0f;
+            if (p.out_scores) p.out_scores[(size_t)b * p.n_post + q] = 0.0f;
+            if (p.out_idx) p.out_idx[(size_t)b * p.n_post + q] = -1;
+        }
+        if (tid == 0) p.out_count[b] = 0;
+        return;
+    }
+    // ---- radix select of the k-th largest composite
+    uint64_t T = 0;
+    if (k < s_valid) {
+        if (tid == 0) { s_prefix = 0ull; s_need = k; }
+        __syncthreads();
+        for (int byte = 7; byte >= 0; --byte) {
+            if (byte == 3) continue;  // index < 2^24: top byte of ~index is 0xff for every element
+            const int sh = byte * 8;
+            if (tid < 256) s_hist[tid] = 0;
+            __syncthreads();
+            const uint64_t prefix = s_prefix;
+            const uint64_t himask = (byte == 7) ? 0ull : (~0ull << (sh + 8));
+            for (int i0 = 0; i0 < p.N; i0 += RPN_NT) {
+                const int i = i0 + tid;
+                int dg = 256 + lane;
+                if (i < p.N) {
+                    const uint32_t key = keys[i];
+                    uint64_t comp = rpn_composite(key, i);
+                    if (byte <= 2) comp |= 0xff000000ull;  // skipped byte: treat as matching
+                    uint64_t pf = prefix;
+                    if (byte <= 2) pf |= 0xff000000ull;
+                    if (key != 0u && ((comp ^ pf) & himask) == 0ull) dg = (int)((comp >> sh) & 255);
+                }
+                const unsigned peers = __match_any_sync(HD_FULL, dg);
+                if (dg < 256 && (peers & hd_lanemask_lt()) == 0u) atomicAdd(&s_hist[dg], __popc(peers));
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int need = s_need, d = 255;
+                for (; d > 0; --d) {
+                    if (s_hist[d] >= need) break;
+                    need -= s_hist[d];
+                }
+                s_need = need;
+                s_prefix = prefix | ((uint64_t)d << sh);
+            }
+            __syncthreads();
+        }
+        T = s_prefix | 0xff000000ull;
+    }
+    // ---- compaction of the selected set (unordered; the sort key carries the index)
+    for (int i0 = 0; i0 < p.N; i0 += RPN_NT) {
+        const int i = i0 + tid;
+        bool sel = false;
+        uint32_t key = 0;
+        if (i < p.N) {
+            key = keys[i];
+            sel = key != 0u && rpn_composite(key, i) >= T;
+        }
+        const unsigned m = __ballot_sync(HD_FULL, sel);
+        if (m) {
+            int basep = 0;
+            if (lane == 0) basep = atomicAdd(&s_count, __popc(m));
+            basep = __shfl_sync(HD_FULL, basep, 0);
+            if (sel) {
+                const int slot = basep + __popc(m & hd_lanemask_lt());
+                if (slot < p.cap) {
+                    k0[slot] = ((uint64_t)(~key) << 32) | (uint32_t)i;
+                    v0[slot] = (uint32_t)i;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int n = min(s_count, p.cap);
+    const int res = hd_cta_radix_sort<RPN_NT>(k0, v0, k1, v1, n, ssm);
+    const uint32_t* order = res ? v1 : v0;
+    const float4* __restrict__ boxes = p.boxes + (size_t)b * p.N;
+    for (int r = tid; r < n; r += RPN_NT) sbox[r] = boxes[order[r]];
+    __syncthreads();
+    const int kc = hd_cta_greedy_nms<RPN_NT>(sbox, nullptr, n, p.n_post, p.thr, removed, keep_r, nsm);
+    for (int q = tid; q < p.n_post; q += RPN_NT) {
+        float* o = p.out_rois + ((size_t)b * p.n_post + q) * 5;
+        o[0] = (float)b;
+        if (q < kc) {
+            const int r = keep_r[q];
+            const float4 bx = sbox[r];
+            o[1] = bx.x; o[2] = bx.y; o[3] = bx.z; o[4] = bx.w;
+            if (p.out_scores) p.out_scores[(size_t)b * p.n_post + q] = p.scores[(size_t)b * p.N + order[r]];
+            if (p.out_idx) p.out_idx[(size_t)b * p.n_post + q] = (long long)order[r];
+        } else {
+            o[1] = o[2] = o[3] = o[4] = 0.0f;
+            if (p.out_scores) p.out_scores[(size_t)b * p.n_post + q] = 0.0f;
+            if (p.out_idx) p.out_idx[(size_t)b * p.n_post + q] = -1;
+        }
+    }
+    if (tid == 0) p.out_count[b] = kc;
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int rpn_fill(RpnParams& p, const hd_rpn_level* levels, int n_levels, int B, int A, int flags, float img_h, float img_w,
+                    float min_size, float clamp_dwh) {
+    HD_CHECK_ARG(levels && n_levels >= 1 && n_levels <= HD_MAX_LEVELS, "n_levels must be in [1,%d], got %d", HD_MAX_LEVELS, n_levels);
+    HD_CHECK_ARG(A >= 1 && A <= HD_MAX_ANCHORS, "A must be in [1,%d], got %d", HD_MAX_ANCHORS, A);
+    HD_CHECK_ARG(B >= 0, "B must be >= 0");
+    memset(&p, 0, sizeof(p));
+    int cells = 0, anchors = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        HD_CHECK_ARG(levels[l].H > 0 && levels[l].W > 0, "level %d has empty spatial size", l);
+        HD_CHECK_ARG(B == 0 || (levels[l].objectness && levels[l].deltas), "level %d has a NULL head", l);
+        p.obj[l] = levels[l].objectness; p.dlt[l] = levels[l].deltas;
+        p.H[l] = levels[l].H; p.W[l] = levels[l].W; p.stride[l] = levels[l].stride;
+        for (int q = 0; q < 4 * A; ++q) p.base[l][q] = levels[l].anchor_base[q];
+        p.cell_start[l] = cells; p.level_off[l] = anchors;
+        cells += levels[l].H * levels[l].W;
+        anchors += A * levels[l].H * levels[l].W;
+    }
+    HD_CHECK_ARG(anchors < (1 << 24), "more than 2^24 anchors per image");
+    p.cell_start[n_levels] = cells; p.level_off[n_levels] = anchors;
+    p.n_levels = n_levels; p.B = B; p.A = A; p.softmax = (flags & HD_RPN_SOFTMAX) ? 1 : 0;
+    p.img_h = img_h; p.img_w = img_w; p.min_size = min_size;
+    p.use_clamp = (flags & HD_RPN_CLAMP_DWH) ? 1 : 0; p.clamp_dwh = clamp_dwh;
+    p.total_cells = (long long)B * cells; p.N = anchors;
+    return HD_OK;
+}
+
+extern "C" HD_API int hd_rpn_num_anchors(const hd_rpn_level* levels, int n_levels, int A) {
+    if (!levels || n_levels < 1 || n_levels > HD_MAX_LEVELS) return HD_ERR_INVALID;
+    long long n = 0;
+    for (int l = 0; l < n_levels; ++l) n += (long long)A * levels[l].H * levels[l].W;
+    return (int)n;
+}
+
+extern "C" HD_API int hd_rpn_decode(const hd_rpn_level* levels, int n_levels, int B, int A, int flags, float img_h, float img_w,
+                                    float min_size, float clamp_dwh, float* boxes, float* scores, uint32_t* keys, void* stream) {
+    RpnParams p;
+    int rc = rpn_fill(p, levels, n_levels, B, A, flags, img_h, img_w, min_size, clamp_dwh);
+    if (rc) return rc;
+    if (B == 0) return HD_OK;
+    HD_CHECK_ARG(boxes && scores && keys, "null output");
+    long long blocks = (p.total_cells + 255) / 256;
+    HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
+    rpn_decode_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, (float4*)boxes, scores, keys);
+    HD_CUDA_LAUNCH_CHECK("rpn_decode_kernel");
+    return HD_OK;
+}
+
+static void rpn_ws_layout(int B, int cap, size_t* offs, size_t* total) {
+    size_t n = (size_t)B * cap, o = 0;
+    offs[0] = o; o = hd_align_up(o + n * 8, 256);
+    offs[1] = o; o = hd_align_up(o + n * 8, 256);
+    offs[2] = o; o = hd_align_up(o + n * 4, 256);
+    offs[3] = o; o = hd_align_up(o + n * 4, 256);
+    offs[4] = o; o = hd_align_up(o + n * 16, 256);
+    offs[5] = o; o = hd_align_up(o + n * 4, 256);
+    *total = o;
+}
+static int rpn_cap(int N, int n_pre) { return (n_pre > 0 && n_pre < N) ? n_pre : N; }
+
+extern "C" HD_API size_t hd_rpn_select_nms_workspace_size(int B, int N, int n_pre) {
+    size_t offs[6], total;
+    rpn_ws_layout(B < 0 ? 0 : B, rpn_cap(N < 0 ? 0 : N, n_pre), offs, &total);
+    return total + 256;
+}
+
+extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores, const uint32_t* keys, int B, int N, int n_pre, int n_post,
+                                        double nms_iou, float* out_rois, float* out_scores, int64_t* out_idx, int32_t* out_count,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    HD_CHECK_ARG(B >= 0 && N >= 0 && n_post > 0, "bad shape B=%d N=%d n_post=%d", B, N, n_post);
+    HD_CHECK_ARG(N < (1 << 24), "more than 2^24 proposals per image");
+    if (B == 0) return HD_OK;
+    HD_CHECK_ARG(out_rois && out_count, "null output");
+    HD_CHECK_ARG(N == 0 || (boxes && scores && keys), "null input");
+    const int cap = rpn_cap(N, n_pre) > 0 ? rpn_cap(N, n_pre) : 1;
+    size_t offs[6], total;
+    rpn_ws_layout(B, cap, offs, &total);
+    uintptr_t w0 = hd_align_up((uintptr_t)workspace, 256);
+    if (!workspace || w0 + total > (uintptr_t)workspace + workspace_bytes)
+        HD_FAIL(HD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", total + 256, workspace_bytes);
+    RpnSelParams p;
+    p.boxes = (const float4*)boxes; p.scores = scores; p.keys = keys; p.B = B; p.N = N; p.n_pre = n_pre; p.n_post = n_post;
+    p.thr = hd_thr_floor(nms_iou);
+    p.out_rois = out_rois; p.out_scores = out_scores; p.out_idx = (long long*)out_idx; p.out_count = out_count; p.cap = cap;
+    p.k0 = (uint64_t*)(w0 + offs[0]); p.k1 = (uint64_t*)(w0 + offs[1]); p.v0 = (uint32_t*)(w0 + offs[2]); p.v1 = (uint32_t*)(w0 + offs[3]);
+    p.sbox = (float4*)(w0 + offs[4]); p.keep_r = (int*)(w0 + offs[5]);
+    size_t smem = ((size_t)(cap + 31) / 32 + 4) * 4;
+    HD_CHECK_ARG(smem <= 150 * 1024, "n_pre too large for the shared-memory bitmap");
+    static bool attr_set = false;
+    if (!attr_set) {
+        HD_CUDA_CALL(cudaFuncSetAttribute(rpn_select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+        attr_set = true;
+    }
+    rpn_select_nms_kernel<<<B, RPN_NT, smem, (cudaStream_t)stream>>>(p);
+    HD_CUDA_LAUNCH_CHECK("rpn_select_nms_kernel");
+    return HD_OK;
+}
+
+extern "C" HD_API size_t hd_rpn_proposals_workspace_size(int B, int N, int n_pre) {
+    size_t n = (size_t)(B < 0 ? 0 : B) * (N < 0 ? 0 : N);
+    return hd_align_up(n * 16, 256) + hd_align_up(n * 4, 256) * 2 + hd_rpn_select_nms_workspace_size(B, N, n_pre) + 256;
+}
+
+extern "C" HD_API int hd_rpn_proposals(const hd_rpn_level* levels, int n_levels, int B, int A, int flags, float img_h, float img_w,
+                                       float min_size, float clamp_dwh, int n_pre, int n_post, double nms_iou, float* out_rois,
+                                       float* out_scores, int64_t* out_idx, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+    int N = hd_rpn_num_anchors(levels, n_levels, A);
+    HD_CHECK_ARG(N >= 0, "bad levels");
+    if (B <= 0) return B == 0 ? HD_OK : HD_ERR_INVALID;
+    size_t need = hd_rpn_proposals_workspace_size(B, N, n_pre);
+    if (!workspace || workspace_bytes < need) HD_FAIL(HD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+    size_t n = (size_t)B * N;
+    uintptr_t w = hd_align_up((uintptr_t)workspace, 256);
+    float* boxes = (float*)w; w += hd_align_up(n * 16, 256);
+    float* scores = (float*)w; w += hd_align_up(n * 4, 256);
+    uint32_t* keys = (uint32_t*)w; w += hd_align_up(n * 4, 256);
+    int rc = hd_rpn_decode(levels, n_levels, B, A, flags, img_h, img_w, min_size, clamp_dwh, boxes, scores, keys, stream);
+    if (rc) return rc;
+    return hd_rpn_select_nms(boxes, scores, keys, B, N, n_pre, n_post, nms_iou, out_rois, out_scores, out_idx, out_count, (void*)w,
+                             (size_t)((uintptr_t)workspace + workspace_bytes - w), stream);
+}

@@ -89,3 +89,15 @@ _LIB.impl("nms", lambda dets, scores, thr: _nms_single(dets, scores, thr), "CUDA
 _LIB.impl("box_iou", _box_iou_impl, "CUDA")
 _LIB.impl("nms", _cpu_refuse, "CPU")
 _LIB.impl("box_iou", _cpu_refuse, "CPU")
+
+# RoI ops re-exported beside the box ops, as in torchvision.ops
+from .roi import (roi_align, roi_pool, roi_pool_with_argmax, RoIAlign, RoIPool, level_map,  # noqa: E402,F401
+                  multilevel_roi_align, convert_boxes_to_roi_format)
+
+_LIB.define("roi_align(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width, "
+            "int sampling_ratio, bool aligned) -> Tensor")
+_LIB.define("roi_pool(Tensor input, Tensor rois, float spatial_scale, SymInt pooled_height, SymInt pooled_width) -> (Tensor, Tensor)")
+_LIB.impl("roi_align", lambda input, rois, s, ph, pw, sr, al: roi_align(input, rois, (ph, pw), s, sr, al), "CUDA")
+_LIB.impl("roi_pool", lambda input, rois, s, ph, pw: roi_pool_with_argmax(input, rois, (ph, pw), s), "CUDA")
+_LIB.impl("roi_align", _cpu_refuse, "CPU")
+_LIB.impl("roi_pool", _cpu_refuse, "CPU")

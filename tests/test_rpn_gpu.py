@@ -1,0 +1,112 @@
+"""RPN proposal path parity.
+
+Stage 1 (decode, fp): boxes/scores within 1e-5 relative of the oracle restatement.
+Stage 2 (top-k + sort + NMS, integer): bit-exact proposal indices against the oracle's
+stable-sort + torchvision CPU nms run on the SAME fp32 stage-1 arrays.
+End to end the two stages are chained; because the sigmoid of torch-CPU and CUDA differ by an ulp,
+near-tied scores may swap, so the e2e test asserts agreement statistics, not identity."""
+import numpy as np
+import pytest
+import torch
+import torchvision
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, scale=1.0):
+    a, b = a.cpu().double(), b.cpu().double()
+    return bool(((a - b).abs() <= 1e-5 * torch.clamp(b.abs(), min=scale)).all())
+
+
+@pytest.fixture(scope="module", params=["sigmoid", "softmax"])
+def cfg(request):
+    from heltondetection_b200 import synth
+    obj, dlt, bases, _ = synth.rpn_heads(2, 416, G=12, seed=1237, softmax=(request.param == "softmax"))
+    return obj, dlt, bases, request.param
+
+
+def _oracle_flat(obj, dlt, bases, mode, img):
+    import oracle
+    locs, fgs, ancs = [], [], []
+    for o, d, ab, s in zip(obj, dlt, bases, (4, 8, 16, 32)):
+        l, f = oracle.rpn.flatten_head(o, d, mode)
+        locs.append(l); fgs.append(f)
+        ancs.append(torch.from_numpy(oracle.rpn.enumerate_shifted_anchor(ab, s, d.shape[2], d.shape[3])))
+    return torch.cat(locs, 1), torch.cat(fgs, 1), torch.cat(ancs, 0)
+
+
+def test_decode_stage_matches_oracle(cfg):
+    import oracle
+    from heltondetection_b200 import rpn
+    obj, dlt, bases, mode = cfg
+    loc, fg, anc = _oracle_flat(obj, dlt, bases, mode, 416)
+    pr = rpn.RpnProposals(bases, (4, 8, 16, 32), (416, 416), score_mode=mode, min_size=16)
+    boxes, scores, keys = pr.decode([o.cuda() for o in obj], [d.cuda() for d in dlt])
+    for b in range(2):
+        roi = oracle.rpn.loc2bbox(anc, loc[b])
+        roi[:, [0, 2]] = roi[:, [0, 2]].clamp(0, 416.0)
+        roi[:, [1, 3]] = roi[:, [1, 3]].clamp(0, 416.0)
+        assert close(boxes[b], roi)
+        assert close(scores[b], fg[b], scale=1e-3)
+        valid = ((roi[:, 2] - roi[:, 0]) >= 16) & ((roi[:, 3] - roi[:, 1]) >= 16)
+        gv = keys[b].cpu() != 0
+        border = ((roi[:, 2] - roi[:, 0]) - 16).abs().lt(1e-3) | ((roi[:, 3] - roi[:, 1]) - 16).abs().lt(1e-3)
+        assert torch.equal(gv[~border], valid[~border])
+
+
+@pytest.mark.parametrize("n_pre,n_post", [(3000, 300), (12000, 2000), (0, 1000), (50, 50)])
+def test_select_sort_nms_stage_bit_exact(cfg, n_pre, n_post):
+    from heltondetection_b200 import rpn
+    obj, dlt, bases, mode = cfg
+    pr = rpn.RpnProposals(bases, (4, 8, 16, 32), (416, 416), score_mode=mode, n_pre_nms=n_pre, n_post_nms=n_post)
+    boxes, scores, keys = pr.decode([o.cuda() for o in obj], [d.cuda() for d in dlt])
+    rois, cnt, osc, idx = pr([o.cuda() for o in obj], [d.cuda() for d in dlt])
+    rois = rois.view(2, n_post, 5)
+    for b in range(2):
+        bx, sc, valid = boxes[b].cpu(), scores[b].cpu(), keys[b].cpu() != 0
+        keep = torch.where(valid)[0]
+        order = torch.sort(sc[keep], descending=True, stable=True)[1]
+        if n_pre > 0:
+            order = order[:n_pre]
+        sel = keep[order]
+        k = torchvision.ops.nms(bx[sel], sc[sel], 0.7)[:n_post]
+        ref_idx = sel[k]
+        n = int(cnt[b].item())
+        assert n == ref_idx.numel()
+        assert torch.equal(idx[b, :n].cpu(), ref_idx)
+        assert torch.equal(rois[b, :n, 1:].cpu(), bx[ref_idx])
+        assert torch.equal(osc[b, :n].cpu(), sc[ref_idx])
+        assert bool((rois[b, :, 0] == b).all()) and bool((rois[b, n:, 1:] == 0).all()) and bool((idx[b, n:] == -1).all())
+
+
+def test_end_to_end_agreement_with_oracle(cfg):
+    import oracle
+    from heltondetection_b200 import rpn
+    obj, dlt, bases, mode = cfg
+    ref = oracle.rpn.rpn_proposals(obj, dlt, bases, (4, 8, 16, 32), (416, 416), score_mode=mode, n_pre_nms=6000, n_post_nms=1000)
+    pr = rpn.RpnProposals(bases, (4, 8, 16, 32), (416, 416), score_mode=mode, n_pre_nms=6000, n_post_nms=1000)
+    rois, cnt, osc, idx = pr([o.cuda() for o in obj], [d.cuda() for d in dlt])
+    rois = rois.view(2, 1000, 5)
+    for b in range(2):
+        r_roi, r_sc, r_idx = ref[b]
+        n = int(cnt[b].item())
+        got = set(idx[b, :n].cpu().tolist())
+        want = set(r_idx.tolist())
+        agree = len(got & want) / max(len(want), 1)
+        assert abs(n - len(want)) <= max(2, len(want) // 200), (n, len(want))
+        assert agree >= 0.99, agree
+        if torch.equal(idx[b, :n].cpu(), r_idx):
+            assert close(rois[b, :n, 1:], r_roi)
+
+
+def test_proposal_creator_lineage_signature(cfg):
+    import oracle
+    from heltondetection_b200 import rpn
+    obj, dlt, bases, mode = cfg
+    loc, fg, anc = _oracle_flat(obj, dlt, bases, mode, 416)
+    ref_roi, ref_sc, ref_idx = oracle.rpn.ProposalCreator(0.7, 3000, 300, 16)(loc[0], fg[0], anc, (416, 416), return_index=True)
+    pc = rpn.ProposalCreator("test", 0.7, n_test_pre_nms=3000, n_test_post_nms=300, min_size=16)
+    roi, sc, idx = pc(loc[0].cuda(), fg[0].cuda(), anc.cuda(), (416, 416), return_index=True)
+    # same fp32 scores in, decode by elementwise torch ops on the GPU (exp differs by ulps): compare sets
+    want, got = set(ref_idx.tolist()), set(idx.cpu().tolist())
+    assert len(want & got) / len(want) >= 0.99
