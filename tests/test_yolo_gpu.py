@@ -10,12 +10,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-RTOL = 1e-5
-
-
-def close(a, b, scale=1.0):
-    a, b = a.detach().cpu().double(), b.detach().cpu().double()
-    return bool(((a - b).abs() <= RTOL * torch.clamp(b.abs(), min=scale)).all())
+from _tol import close, boxes_close
 
 
 def _cfg(B, img, nc, G, seed, dense=False):
@@ -51,7 +46,7 @@ def test_candidates_match_oracle(cfg1, thr, dense_read, ge):
         c, idx = got[b]
         assert torch.equal(idx.cpu(), ridx), f"candidate set differs: {idx.numel()} vs {ridx.numel()}"
         assert torch.equal(c[:, 5].cpu(), ref[:, 5])
-        assert close(c[:, :4], ref[:, :4])
+        assert boxes_close(c[:, :4], ref[:, :4])
         assert close(c[:, 4], ref[:, 4], scale=1e-3)
 
 
@@ -66,7 +61,7 @@ def test_fused_postprocess_keeps_match_oracle(cfg1, thr, iou, mode):
     for b in range(len(ref)):
         assert torch.equal(gidx[b].cpu(), ridx[b]), f"keep indices differ for image {b}"
         assert torch.equal(got[b][:, 5].cpu(), ref[b][:, 5])
-        assert close(got[b][:, :4], ref[b][:, :4])
+        assert boxes_close(got[b][:, :4], ref[b][:, :4])
         assert close(got[b][:, 4], ref[b][:, 4], scale=1e-3)
 
 
@@ -90,7 +85,7 @@ def test_dense_visdrone_like():
     ref, ridx = oracle.yolo.non_max_suppression(pred, 0.001, 0.6, return_index=True)
     got, gidx = yolo.postprocess([h.cuda() for h in heads], 0.001, 0.6, return_index=True)
     assert torch.equal(gidx[0].cpu(), ridx[0])
-    assert close(got[0][:, :4], ref[0][:, :4])
+    assert boxes_close(got[0][:, :4], ref[0][:, :4])
 
 
 def test_odd_spatial_size_scalar_path():
