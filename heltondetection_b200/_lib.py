@@ -42,6 +42,8 @@ SIGNATURES = {
     "hd_last_error": (C.c_char_p, []),
     "hd_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _vp, _vp]),
     "hd_yolo_decode_filter": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "hd_yolo_postprocess_workspace_size": (_sz, [_i, _i]),
+    "hd_yolo_postprocess": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _d, _d, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hd_yolo_filter_pred": (_i, [_vp, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "hd_sort_nms_workspace_size": (_sz, [_i, _i]),
     "hd_sort_nms_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -28,11 +28,13 @@ __device__ __forceinline__ bool hd_iou_gt(const float4& a, float area_a, const f
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter)) > thr;
 }
 
-// all threads of the CTA must call; blockDim.x == NT >= 1024 is assumed by the 16-threads-per-row mask build
+// all threads of the CTA must call; blockDim.x == NT (a multiple of 64, <= 1024)
 template <int NT>
 __device__ int hd_cta_greedy_nms(const float4* sbox, const int* scls, int n_use, int max_det, float thr, uint32_t* removed,
                                  int* keep_r, HdNmsSmem& sm) {
-    static_assert(NT == 1024, "mask build maps 16 threads to each of 64 rows");
+    static_assert(NT % 64 == 0 && NT <= 1024 && 64 % (NT / 64) == 0, "mask build maps NT/64 threads to each of 64 rows");
+    constexpr int ROWT = NT / 64;       // threads per mask row
+    constexpr int COLS = 64 / ROWT;     // columns per thread
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < (n_use + 31) / 32 + 2; i += NT) removed[i] = 0;
     __syncthreads();
@@ -49,15 +51,15 @@ __device__ int hd_cta_greedy_nms(const float4* sbox, const int* scls, int n_use,
             }
         }
         __syncthreads();
-        {   // 64x64 upper-triangular mask: 16 threads per row, 4 columns each
-            const int i = tid >> 4, j0 = (tid & 15) * 4;
+        {   // 64x64 upper-triangular mask: ROWT threads per row, COLS columns each
+            const int i = tid / ROWT, j0 = (tid % ROWT) * COLS;
             if (i < m) {
                 unsigned long long bits = 0ull;
                 const float4 bi = sm.cbox[i];
                 const float ai = sm.carea[i];
                 const int ci = sm.ccls[i];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
+#pragma unroll 4
+                for (int q = 0; q < COLS; ++q) {
                     const int jj = j0 + q;
                     if (jj > i && jj < m && sm.ccls[jj] == ci && hd_iou_gt(bi, ai, sm.cbox[jj], sm.carea[jj], thr)) bits |= 1ull << jj;
                 }

@@ -19,7 +19,7 @@ struct NmsParams {
     const int* cls;
     const int* tiebreak;
     const int* counts;
-    int n_fixed, B, cap;
+    int n_fixed, B, cap, min_n;  // images with n <= min_n are skipped (already handled by the fused small-n path)
     float thr;  // hd_thr_floor(iou_thres)
     int class_mode;
     float offset_scale;
@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     const int tid = threadIdx.x;
     const int b = blockIdx.x;
     int n = p.counts ? min(p.counts[b], p.cap) : p.n_fixed;
+    if (p.min_n >= 0 && n <= p.min_n) return;
     if (n <= 0) {
         if (tid == 0) p.out_count[b] = 0;
         return;
@@ -140,10 +141,23 @@ extern "C" HD_API size_t hd_sort_nms_workspace_size(int B, int cap) {
     return total + 256;
 }
 
+int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
+                            const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
+                            float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
+                            int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream, int min_n);
+
 extern "C" HD_API int hd_sort_nms_batched(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
-                                   const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
-                                   float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
-                                   int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+                                          const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
+                                          float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
+                                          int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    return hd_sort_nms_batched_min(boxes, scores, cls, tiebreak, counts, n_fixed, B, cap, iou_thres, class_mode, offset_scale, max_nms,
+                                   max_det, out_det, out_idx, out_count, workspace, workspace_bytes, stream, -1);
+}
+
+int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
+                            const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
+                            float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
+                            int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream, int min_n) {
     HD_CHECK_ARG(B >= 0 && cap >= 0, "bad shape B=%d cap=%d", B, cap);
     if (B == 0) return HD_OK;
     HD_CHECK_ARG(out_count != nullptr, "out_count is NULL");
@@ -165,7 +179,7 @@ extern "C" HD_API int hd_sort_nms_batched(const float* boxes, const float* score
         HD_FAIL(HD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", total + 256, workspace_bytes);
     NmsParams p;
     p.boxes = (const float4*)boxes; p.scores = scores; p.cls = (class_mode == HD_NMS_AGNOSTIC) ? cls : cls; p.tiebreak = tiebreak;
-    p.counts = counts; p.n_fixed = n_fixed; p.B = B; p.cap = cap;
+    p.counts = counts; p.n_fixed = n_fixed; p.B = B; p.cap = cap; p.min_n = min_n;
     p.thr = hd_thr_floor(iou_thres);
     p.class_mode = class_mode; p.offset_scale = offset_scale; p.max_nms = max_nms; p.max_det = max_det;
     p.out_det = out_det; p.out_idx = (long long*)out_idx; p.out_count = out_count;

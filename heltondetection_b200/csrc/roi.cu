@@ -30,7 +30,7 @@ struct AxisEntry { int off; float w; };  // off = cell index premultiplied by th
 // Per-axis table of one RoI: bin b owns entries [b*stride, b*stride + cnt[b]).  Sample positions grow
 // monotonically inside a bin, so a cell that was already emitted is one of the last two entries.
 __device__ __forceinline__ void build_axis(AxisEntry* tab, int* cnt, int b, int stride, float start, float bin_size, int grid,
-                                           int extent, int elem_stride) {
+                                           int extent, int elem_stride, int pad_to) {
     int n = 0;
     AxisEntry* t = tab + b * stride;
     auto add = [&](int cell, float w) {
@@ -52,6 +52,39 @@ __device__ __forceinline__ void build_axis(AxisEntry* tab, int* cnt, int b, int 
         add(hi, l);
     }
     cnt[b] = n;
+    // pad with zero-weight duplicates of a real cell so the consumer can run fixed-trip-count loops
+    const int dup = n > 0 ? t[n - 1].off : 0;
+    for (int i = n; i < pad_to; ++i) { t[i].off = dup; t[i].w = 0.0f; }
+}
+
+// one bin row with compile-time entry counts: all E*E loads of a bin are independent and issued together
+template <int E>
+__device__ __forceinline__ void roi_align_rows_fixed(const float* __restrict__ fc, const AxisEntry* ytab, const AxisEntry* xtab, int PH,
+                                                     int PW, float count, float* tile_c) {
+    for (int ph = 0; ph < PH; ++ph) {
+        int yo[E]; float wy[E];
+#pragma unroll
+        for (int a = 0; a < E; ++a) { yo[a] = ytab[ph * E + a].off; wy[a] = ytab[ph * E + a].w; }
+        for (int pw = 0; pw < PW; ++pw) {
+            int xo[E]; float wx[E];
+#pragma unroll
+            for (int b = 0; b < E; ++b) { xo[b] = xtab[pw * E + b].off; wx[b] = xtab[pw * E + b].w; }
+            float v[E][E];
+#pragma unroll
+            for (int a = 0; a < E; ++a)
+#pragma unroll
+                for (int b = 0; b < E; ++b) v[a][b] = __ldg(fc + yo[a] + xo[b]);
+            float acc = 0.0f;
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                float r = 0.0f;
+#pragma unroll
+                for (int b = 0; b < E; ++b) r = fmaf(wx[b], v[a][b], r);
+                acc = fmaf(wy[a], r, acc);
+            }
+            tile_c[ph * PW + pw] = __fdiv_rn(acc, count);
+        }
+    }
 }
 
 __device__ __forceinline__ void tile_store(float* __restrict__ gdst, const float* tile, int n_floats, bool use_tma) {
@@ -93,17 +126,22 @@ __global__ void __launch_bounds__(256) roi_align_nhwc_kernel(const __grid_consta
     const int gh = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)p.PH));
     const int gw = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)p.PW));
     const float count = (float)max(gh * gw, 1);
-    const int stride_y = max(2 * max(gh, 0), 1), stride_x = max(2 * max(gw, 0), 1);
+    // entries per bin and axis are <= 2*grid; the common cases get fixed widths (4: grid<=2, 8: grid<=4)
+    const int need = 2 * max(max(gh, gw), 0);
+    const int E = need <= 4 ? 4 : (need <= 8 ? 8 : 0);
+    const int stride_y = E ? E : max(2 * max(gh, 0), 1), stride_x = E ? E : max(2 * max(gw, 0), 1);
     const bool fits = (long long)stride_y * p.PH <= ROI_TAB && (long long)stride_x * p.PW <= ROI_TAB;
     if (fits) {
-        if (threadIdx.x < p.PH) build_axis(ytab, ycnt, threadIdx.x, stride_y, sh, bh, gh, H, W * p.C);
-        else if (threadIdx.x >= 64 && threadIdx.x < 64 + p.PW) build_axis(xtab, xcnt, threadIdx.x - 64, stride_x, sw, bw, gw, W, p.C);
+        if (threadIdx.x < p.PH) build_axis(ytab, ycnt, threadIdx.x, stride_y, sh, bh, gh, H, W * p.C, E);
+        else if (threadIdx.x >= 64 && threadIdx.x < 64 + p.PW) build_axis(xtab, xcnt, threadIdx.x - 64, stride_x, sw, bw, gw, W, p.C, E);
     }
     __syncthreads();
     const float* __restrict__ f = p.data[lvl] + (size_t)bidx * H * W * p.C;
     const int nb = p.PH * p.PW;
     for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
         const float* __restrict__ fc = f + c;
+        if (fits && E == 4) { roi_align_rows_fixed<4>(fc, ytab, xtab, p.PH, p.PW, count, tile + c * nb); continue; }
+        if (fits && E == 8) { roi_align_rows_fixed<8>(fc, ytab, xtab, p.PH, p.PW, count, tile + c * nb); continue; }
         for (int ph = 0; ph < p.PH; ++ph) {
             for (int pw = 0; pw < p.PW; ++pw) {
                 float acc = 0.0f;
@@ -114,7 +152,15 @@ __global__ void __launch_bounds__(256) roi_align_nhwc_kernel(const __grid_consta
                     for (int a = 0; a < ny; ++a) {
                         const float wy = yt[a].w;
                         const float* __restrict__ row = fc + yt[a].off;
-                        for (int b = 0; b < nx; ++b) acc = fmaf(wy * xt[b].w, __ldg(row + xt[b].off), acc);
+                        float r = 0.0f;
+                        int b = 0;
+                        for (; b + 4 <= nx; b += 4) {
+                            const float v0 = __ldg(row + xt[b].off), v1 = __ldg(row + xt[b + 1].off);
+                            const float v2 = __ldg(row + xt[b + 2].off), v3 = __ldg(row + xt[b + 3].off);
+                            r = fmaf(xt[b].w, v0, r); r = fmaf(xt[b + 1].w, v1, r); r = fmaf(xt[b + 2].w, v2, r); r = fmaf(xt[b + 3].w, v3, r);
+                        }
+                        for (; b < nx; ++b) r = fmaf(xt[b].w, __ldg(row + xt[b].off), r);
+                        acc = fmaf(wy, r, acc);
                     }
                 } else {
                     // huge adaptive grids: sample by sample, no tables
@@ -170,11 +216,22 @@ __global__ void __launch_bounds__(256) roi_pool_nhwc_kernel(const __grid_constan
                 const bool empty = (he <= hs) || (we <= ws);
                 float mx = empty ? 0.0f : -INFINITY;
                 int mi = -1;
-                for (int h = hs; h < he; ++h)
-                    for (int w = ws; w < we; ++w) {
-                        float v = __ldg(f + ((size_t)h * W + w) * p.C + c);
+                for (int h = hs; h < he; ++h) {
+                    const float* __restrict__ row = f + (size_t)h * W * p.C + c;
+                    int w = ws;
+                    for (; w + 4 <= we; w += 4) {  // four independent loads in flight
+                        const float v0 = __ldg(row + (size_t)w * p.C), v1 = __ldg(row + (size_t)(w + 1) * p.C);
+                        const float v2 = __ldg(row + (size_t)(w + 2) * p.C), v3 = __ldg(row + (size_t)(w + 3) * p.C);
+                        if (v0 > mx) { mx = v0; mi = h * W + w; }
+                        if (v1 > mx) { mx = v1; mi = h * W + w + 1; }
+                        if (v2 > mx) { mx = v2; mi = h * W + w + 2; }
+                        if (v3 > mx) { mx = v3; mi = h * W + w + 3; }
+                    }
+                    for (; w < we; ++w) {
+                        const float v = __ldg(row + (size_t)w * p.C);
                         if (v > mx) { mx = v; mi = h * W + w; }
                     }
+                }
                 tile[c * nb + ph * p.PW + pw] = mx;
                 if (p.argmax) p.argmax[((size_t)k * p.C + c) * nb + ph * p.PW + pw] = mi;
             }

@@ -16,7 +16,11 @@ DEFAULT_STRIDES = (8, 16, 32)
 _CLASS_MODES = {"agnostic": _lib.NMS_AGNOSTIC, "exact": _lib.NMS_CLASS_EXACT, "offset": _lib.NMS_CLASS_OFFSET}
 
 
-def _levels(outputs, anchors, strides):
+def _is_pinned_host(x):
+    return (not x.is_cuda) and x.is_pinned()
+
+
+def _levels(outputs, anchors, strides, host_ok=False):
     if len(outputs) != len(anchors) or len(outputs) != len(strides):
         raise RuntimeError("outputs, anchors and strides must have one entry per level")
     A = len(anchors[0])
@@ -28,7 +32,8 @@ def _levels(outputs, anchors, strides):
     keep = []
     total = 0
     for l, (x, anc, s) in enumerate(zip(outputs, anchors, strides)):
-        _lib.require_cuda(x)
+        if not (host_ok and _is_pinned_host(x)):
+            _lib.require_cuda(x)
         if x.dim() != 4 or x.shape[0] != B or x.shape[1] != Ctot or len(anc) != A:
             raise RuntimeError(f"level {l}: expected [B={B}, {Ctot}, H, W], got {tuple(x.shape)}")
         x = _lib.f32c(x)
@@ -81,7 +86,12 @@ class YoloPostprocessor:
 
     def __init__(self, anchors=DEFAULT_ANCHORS, strides=DEFAULT_STRIDES, conf_thres=0.25, iou_thres=0.45,
                  agnostic=False, max_det=300, max_nms=30000, max_wh=7680.0, class_mode="offset", ge=False,
-                 dense_read=False):
+                 dense_read=False, fused=True, device=None):
+        """fused: one kernel decodes and runs each image's NMS as soon as its last tile is done (default);
+        False keeps the two-kernel path.  device: where the outputs live; needed when `outputs` are pinned HOST
+        tensors, which the kernel then reads directly over PCIe (zero-copy; only surviving tiles are fetched)."""
+        self.fused, self.device = bool(fused), (torch.device(device) if device is not None else None)
+        self._fkey = None
         self.anchors, self.strides = anchors, strides
         self.conf_thres, self.iou_thres = float(conf_thres), float(iou_thres)
         self.max_det, self.max_nms, self.max_wh = int(max_det), int(max_nms), float(max_wh)
@@ -95,9 +105,36 @@ class YoloPostprocessor:
             b = self._buf = _Buffers(B, cap, self.max_det, device)
         return b
 
+    def _out_device(self, keep):
+        if self.device is not None:
+            return self.device
+        if keep[0].is_cuda:
+            return keep[0].device
+        return torch.device("cuda", torch.cuda.current_device())
+
+    def _fused_call(self, arr, keep, B, A, nc, total):
+        dev = self._out_device(keep)
+        key = (B, total, dev)
+        if self._fkey != key:
+            L = _lib.lib()
+            self.f_ws_bytes = L.hd_yolo_postprocess_workspace_size(B, total)
+            self.f_ws = torch.empty((self.f_ws_bytes,), dtype=torch.uint8, device=dev)
+            self.f_det = torch.zeros((B, self.max_det, 6), dtype=torch.float32, device=dev)
+            self.f_idx = torch.zeros((B, self.max_det), dtype=torch.int64, device=dev)
+            self.f_count = torch.zeros((B,), dtype=torch.int32, device=dev)
+            self._fkey = key
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().hd_yolo_postprocess(
+                arr, len(keep), B, A, nc, self.conf_thres, self.iou_thres, self.flags, self.class_mode, self.max_wh, self.max_nms,
+                self.max_det, _lib.ptr(self.f_det), _lib.ptr(self.f_idx), _lib.ptr(self.f_count), _lib.ptr(self.f_ws), self.f_ws_bytes,
+                _lib.stream()))
+        return self.f_det, self.f_count, self.f_idx
+
     def __call__(self, outputs):
-        arr, keep, B, A, nc, total = _levels(outputs, self.anchors, self.strides)
-        buf = self.buffers(B, total, keep[0].device)
+        arr, keep, B, A, nc, total = _levels(outputs, self.anchors, self.strides, host_ok=True)
+        if self.fused:
+            return self._fused_call(arr, keep, B, A, nc, total)
+        buf = self.buffers(B, total, self._out_device(keep))
         _lib.check(_lib.lib().hd_yolo_decode_filter(
             arr, len(keep), B, A, nc, self.conf_thres, self.flags, _lib.ptr(buf.box), _lib.ptr(buf.score),
             _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))

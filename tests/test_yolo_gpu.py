@@ -109,3 +109,29 @@ def test_no_candidates_and_empty_batch():
     heads = [torch.full((1, 255, 8, 8), -12.0).cuda()]
     out = yolo.postprocess(heads, 0.25, 0.45, anchors=(((10, 13), (16, 30), (33, 23)),), strides=(8,))
     assert out[0].shape == (0, 6)
+
+
+@pytest.mark.parametrize("thr", [0.25, 0.02, 0.001])
+def test_fused_kernel_equals_two_kernel_path(cfg1, thr):
+    """thr 0.25: every image takes the in-kernel small-n tail; 0.001: all go to the radix path; 0.02: mixed."""
+    from heltondetection_b200 import yolo
+    heads = [h.cuda() for h in cfg1]
+    a = yolo.YoloPostprocessor(conf_thres=thr, fused=True)(heads)
+    a = [t.clone() for t in a]
+    b = yolo.YoloPostprocessor(conf_thres=thr, fused=False)(heads)
+    assert torch.equal(a[1], b[1])
+    for i, n in enumerate(a[1].tolist()):
+        assert torch.equal(a[0][i, :n], b[0][i, :n]) and torch.equal(a[2][i, :n], b[2][i, :n])
+
+
+def test_zero_copy_pinned_host_inputs(cfg1):
+    from heltondetection_b200 import yolo
+    ref = yolo.YoloPostprocessor(conf_thres=0.25)([h.cuda() for h in cfg1])
+    ref = [t.clone() for t in ref]
+    got = yolo.YoloPostprocessor(conf_thres=0.25, device="cuda:0")([h.pin_memory() for h in cfg1])
+    torch.cuda.synchronize()
+    assert torch.equal(ref[1], got[1])
+    for i, n in enumerate(ref[1].tolist()):
+        assert torch.equal(ref[0][i, :n], got[0][i, :n])
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        yolo.YoloPostprocessor()(cfg1)          # pageable host memory is refused

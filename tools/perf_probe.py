@@ -1,0 +1,173 @@
+#!/usr/bin/env python
+"""Stage-by-stage device timings of the five BASELINE.json configs (developer tool, not the bench contract).
+usage: python tools/perf_probe.py [cfg2 cfg3 cfg4 cfg5 zerocopy]"""
+import os
+import sys
+import json
+import time
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from heltondetection_b200 import synth, yolo, rpn, roi, wbf, _lib  # noqa: E402
+
+PEAK = 6536.7
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def report(name, ms, nbytes=None, imgs=None):
+    s = f"{name:44s} {ms * 1e3:10.1f} us"
+    if nbytes:
+        s += f"  {nbytes / ms / 1e6:8.1f} GB/s ({nbytes / ms / 1e6 / PEAK * 100:5.1f}% of measured peak)"
+    if imgs:
+        s += f"  {imgs / ms * 1e3:10.0f} img/s"
+    print(s, flush=True)
+
+
+def yolo_cfg(tag, B, img, nc, G, seed, conf, iou, dense_scene):
+    heads_cpu, _ = synth.yolo_heads(B, img, nc, G, seed, dense=dense_scene)
+    heads = [h.cuda() for h in heads_cpu]
+    nbytes = sum(h.numel() * 4 for h in heads)
+    for mode in (True, False):
+        pp = yolo.YoloPostprocessor(conf_thres=conf, iou_thres=iou, dense_read=mode)
+        arr, keep, Bn, A, ncc, total = yolo._levels(heads, pp.anchors, pp.strides)
+        buf = pp.buffers(Bn, total, heads[0].device)
+        L = _lib.lib()
+
+        def dec():
+            _lib.check(L.hd_yolo_decode_filter(arr, len(keep), Bn, A, ncc, pp.conf_thres, pp.flags, _lib.ptr(buf.box), _lib.ptr(buf.score),
+                                               _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))
+        t = timeit(dec)
+        report(f"{tag} decode_filter {'dense' if mode else 'sparse'}", t, nbytes, B)
+        t2 = timeit(lambda: yolo._run_nms(buf, pp.iou_thres, pp.class_mode, pp.max_wh, pp.max_nms))
+        report(f"{tag} sort_nms", t2, None, B)
+        cnt = buf.count.float()
+        print(f"    candidates/img mean {cnt.mean().item():.0f} max {cnt.max().item():.0f}; kept mean {buf.out_count.float().mean().item():.0f}")
+        t3 = timeit(lambda: pp(heads))
+        report(f"{tag} full postprocess ({'dense' if mode else 'sparse'})", t3, nbytes, B)
+    t = timeit(lambda: yolo.decode_box(heads), iters=5)
+    report(f"{tag} decode_box (dense pred out)", t, 2 * nbytes, B)
+    return heads_cpu, heads
+
+
+def cfg2():
+    yolo_cfg("cfg2", 256, 640, 80, 20, 1235, 0.25, 0.45, False)
+
+
+def cfg4():
+    yolo_cfg("cfg4", 64, 1280, 10, 300, 1238, 0.001, 0.6, True)
+
+
+def cfg3():
+    B, img = 16, 832
+    obj, dlt, bases, _ = synth.rpn_heads(B, img, G=20, seed=1237)
+    feats = [f.cuda() for f in synth.fpn_features(B, img, 256, 1237)]
+    obj, dlt = [o.cuda() for o in obj], [d.cuda() for d in dlt]
+    pr = rpn.RpnProposals(bases, (4, 8, 16, 32), (img, img), n_pre_nms=12000, n_post_nms=2000, min_size=16)
+    rpn_bytes = sum(o.numel() * 4 for o in obj) + sum(d.numel() * 4 for d in dlt)
+    t = timeit(lambda: pr.decode(obj, dlt), iters=10)
+    report("cfg3 rpn decode (incl. torch.empty)", t, rpn_bytes, B)
+    t = timeit(lambda: pr(obj, dlt), iters=5)
+    report("cfg3 rpn decode+select+nms", t, rpn_bytes, B)
+    rois, cnt, sc, idx = pr(obj, dlt)
+    print("    proposals kept/img:", cnt.tolist())
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    fbytes = sum(f.numel() * 4 for f in feats)
+    obytes = rois.shape[0] * 256 * 49 * 4
+    nhwc = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    for sr in (2, 0):
+        t = timeit(lambda: roi.multilevel_roi_align(nhwc, rois, 7, scales, sr, False), iters=5)
+        report(f"cfg3 multilevel roi_align NHWC-in sr={sr}", t, fbytes + obytes, B)
+    t = timeit(lambda: roi.multilevel_roi_align(feats, rois, 7, scales, 2, False), iters=5)
+    report("cfg3 multilevel roi_align NCHW-in (+layout pass)", t, fbytes + obytes, B)
+    t = timeit(lambda: roi.multilevel_roi_align(nhwc, rois, 7, scales, 2, False, op="pool"), iters=5)
+    report("cfg3 multilevel roi_pool NHWC-in", t, fbytes + obytes, B)
+    t = timeit(lambda: roi.multilevel_roi_align(nhwc[:1], rois, 7, scales[:1], 2, False), iters=3)
+    report("cfg3 single-level P2 roi_align NHWC sr=2", t, feats[0].numel() * 4 + obytes, B)
+    t = timeit(lambda: roi.multilevel_roi_align(nhwc[:1], rois, 7, scales[:1], 0, False), iters=2)
+    report("cfg3 single-level P2 roi_align NHWC sr=0", t, feats[0].numel() * 4 + obytes, B)
+    out = torch.empty((B, 208, 208, 256), device="cuda")
+    t = timeit(lambda: _lib.check(_lib.lib().hd_nchw_to_nhwc(_lib.ptr(feats[0]), _lib.ptr(out), B, 256, 208, 208, _lib.stream())), iters=5)
+    report("cfg3 nchw->nhwc level0", t, 2 * feats[0].numel() * 4)
+    try:
+        import torchvision
+        small = rois[:4000]
+        t = timeit(lambda: torchvision.ops.roi_align(feats[1], small, 7, 1 / 8, 2, False), iters=3)
+        report("   (torchvision CUDA roi_align, 4000 rois, lvl1)", t, None)
+        t = timeit(lambda: roi.roi_align(nhwc[1], small, 7, 1 / 8, 2, False), iters=3)
+        report("   (hd_b200 NHWC roi_align, 4000 rois, lvl1)", t, None)
+        bx = rois[:12000, 1:].contiguous(); ss = torch.rand(12000, device="cuda")
+        t = timeit(lambda: torchvision.ops.nms(bx, ss, 0.7), iters=3)
+        report("   (torchvision CUDA nms n=12000)", t, None)
+    except Exception as e:
+        print("   torchvision cuda comparison skipped:", e)
+
+
+def cfg5():
+    B, img, nc = 64, 640, 80
+    views, _ = synth.tta_heads(B, img, nc, G=20, seed=1239)
+    vspec = [(r, flip, size) for (_, r, flip, size) in views]
+    dev = [[h.cuda() for h in heads] for (heads, _, _, _) in views]
+    fusion = wbf.TTAFusion(vspec, (img, img), nc, max_det=300, iou_thr=0.55, skip_box_thr=0.001)
+    pps = [yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45) for _ in views]
+
+    def full():
+        for v in range(len(views)):
+            det, cnt, _ = pps[v](dev[v])
+            fusion.map_back(v, det, cnt)
+        return fusion.fuse()
+    nbytes = sum(h.numel() * 4 for d in dev for h in d)
+    t = timeit(full, iters=10)
+    report("cfg5 6x(decode+nms+mapback) + wbf (sparse)", t, nbytes, B)
+    full()
+    t = timeit(lambda: fusion.fuse(), iters=10)
+    report("cfg5 wbf alone", t, None, B)
+    print("    fused/img mean", fusion.wbf.oc.float().mean().item(), "inputs/img", fusion.cnt.sum(1).float().mean().item())
+
+
+def zerocopy():
+    """sparse decode reading pinned HOST memory directly over PCIe (UVA zero-copy)."""
+    B = 256
+    heads_cpu, _ = synth.yolo_heads(B, 640, 80, 20, 1235)
+    pinned = [h.pin_memory() for h in heads_cpu]
+    nbytes = sum(h.numel() * 4 for h in heads_cpu)
+    pp = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=False)
+    dev = [h.cuda() for h in heads_cpu]
+    det_ref, cnt_ref, idx_ref = pp(dev)
+    det_ref, cnt_ref, idx_ref = det_ref.clone(), cnt_ref.clone(), idx_ref.clone()
+    ppz = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=False, device="cuda:0")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    det, cnt, idx = ppz(pinned)
+    torch.cuda.synchronize()
+    print("zero-copy first call", (time.perf_counter() - t0) * 1e3, "ms")
+    print("zero-copy parity: counts equal", bool(torch.equal(cnt, cnt_ref)), "idx equal", bool(torch.equal(idx, idx_ref)))
+    t = timeit(lambda: ppz(pinned), iters=5)
+    report("zero-copy sparse postprocess from pinned host", t, nbytes, B)
+    stage = [torch.empty_like(h, device="cuda") for h in heads_cpu]
+
+    def copy_then():
+        for s, p in zip(stage, pinned):
+            s.copy_(p, non_blocking=True)
+        pp(stage)
+    t = timeit(copy_then, iters=5)
+    report("H2D copy + sparse postprocess", t, nbytes, B)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg4", "cfg5", "zerocopy"]
+    torch.cuda.set_device(0)
+    for w in which:
+        print(f"==== {w}", flush=True)
+        globals()[w]()
