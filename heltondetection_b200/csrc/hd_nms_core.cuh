@@ -8,6 +8,7 @@
 #include "hd_common.cuh"
 
 #define HD_NMS_CHUNK 64
+#define HD_GRID_MIN_N 768  // segments larger than this take the grid-pruned pass
 
 struct HdNmsSmem {
     float4 cbox[HD_NMS_CHUNK];
@@ -29,9 +30,9 @@ __device__ __forceinline__ bool hd_iou_gt(const float4& a, float area_a, const f
 }
 
 // all threads of the CTA must call; blockDim.x == NT (a multiple of 64, <= 1024)
-template <int NT>
+template <int NT, typename KeepT>
 __device__ int hd_cta_greedy_nms(const float4* sbox, const int* scls, int n_use, int max_det, float thr, uint32_t* removed,
-                                 int* keep_r, HdNmsSmem& sm) {
+                                 KeepT* keep_r, HdNmsSmem& sm) {
     static_assert(NT % 64 == 0 && NT <= 1024 && 64 % (NT / 64) == 0, "mask build maps NT/64 threads to each of 64 rows");
     constexpr int ROWT = NT / 64;       // threads per mask row
     constexpr int COLS = 64 / ROWT;     // columns per thread
@@ -54,35 +55,37 @@ __device__ int hd_cta_greedy_nms(const float4* sbox, const int* scls, int n_use,
         {   // 64x64 upper-triangular mask: ROWT threads per row, COLS columns each
             const int i = tid / ROWT, j0 = (tid % ROWT) * COLS;
             if (i < m) {
-                unsigned long long bits = 0ull;
                 const float4 bi = sm.cbox[i];
                 const float ai = sm.carea[i];
                 const int ci = sm.ccls[i];
 #pragma unroll 4
                 for (int q = 0; q < COLS; ++q) {
                     const int jj = j0 + q;
-                    if (jj > i && jj < m && sm.ccls[jj] == ci && hd_iou_gt(bi, ai, sm.cbox[jj], sm.carea[jj], thr)) bits |= 1ull << jj;
+                    // column mask: bit i of cmask[j] <=> box i (i<j) suppresses box j
+                    if (jj > i && jj < m && sm.ccls[jj] == ci && hd_iou_gt(bi, ai, sm.cbox[jj], sm.carea[jj], thr)) atomicOr(&sm.cmask[jj], 1ull << i);
                 }
-                if (bits) atomicOr(&sm.cmask[i], bits);
             }
         }
         __syncthreads();
         if (wid == 0) {
             const unsigned long long rem = (unsigned long long)removed[base >> 5] | ((unsigned long long)removed[(base >> 5) + 1] << 32);
-            unsigned long long alive = ~rem & ((m == 64) ? ~0ull : ((1ull << m) - 1ull));
-            unsigned long long kept = 0ull;
-            int room = max_det - kc;
-            while (alive && room > 0) {
-                const int i = __ffsll((long long)alive) - 1;
-                kept |= 1ull << i;
-                alive &= ~sm.cmask[i];
-                alive &= ~(1ull << i);
-                --room;
+            const unsigned long long alive = ~rem & ((m == 64) ? ~0ull : ((1ull << m) - 1ull));
+            // parallel resolve: kept[j] = alive[j] && !(col[j] & kept), iterated to its unique (= greedy) fixed point
+            const unsigned long long c0 = sm.cmask[lane], c1 = sm.cmask[lane + 32];
+            unsigned long long kept = alive;
+            for (int it = 0; it < 64; ++it) {
+                const bool b0 = ((alive >> lane) & 1ull) && !(c0 & kept);
+                const bool b1 = ((alive >> (lane + 32)) & 1ull) && !(c1 & kept);
+                const unsigned long long nk = (unsigned long long)__ballot_sync(HD_FULL, b0) | ((unsigned long long)__ballot_sync(HD_FULL, b1) << 32);
+                if (nk == kept) break;
+                kept = nk;
             }
+            const int room = max_det - kc;
+            while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll((long long)kept)));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int bit = lane + 32 * h;
-                if ((kept >> bit) & 1ull) keep_r[kc + __popcll(kept & ((1ull << bit) - 1ull))] = base + bit;
+                if ((kept >> bit) & 1ull) keep_r[kc + __popcll(kept & ((1ull << bit) - 1ull))] = (KeepT)(base + bit);
             }
             if (lane == 0) {
                 sm.s_kept = kept;
@@ -107,6 +110,209 @@ __device__ int hd_cta_greedy_nms(const float4* sbox, const int* scls, int n_use,
                         atomicOr(&removed[jr >> 5], 1u << (jr & 31));
                         break;
                     }
+                }
+            }
+        }
+        __syncthreads();
+        if (done) break;
+    }
+    return kc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Grid-pruned variant for large segments.  Same greedy result, but a kept box is only tested against the
+// boxes whose centre can lie inside it:
+//   iou(i,j) > t  =>  inter >= t*area_j  =>  the intersection spans >= t of j's width and height
+//   =>  centre_j is inside box_i grown by max(0, 0.5 - t) * (w_j, h_j)      (t = thr - 1e-3: fp32 rounding slack)
+// Proper boxes (finite, x2>x1, y2>y1) are hashed by centre cell into T buckets (counting sort in shared memory,
+// item list in global scratch); improper boxes can neither suppress nor be suppressed (their IoU is 0 or NaN) and
+// are left out.  Per chunk, the (kept box, covered cell) pairs are flattened over all threads.  The chunk itself
+// is resolved in parallel: kept[j] = alive[j] && !(col[j] & kept) iterated to its (unique = greedy) fixed point.
+// ------------------------------------------------------------------------------------------------------------
+struct HdGridSmem {
+    int qx1[HD_NMS_CHUNK], qy1[HD_NMS_CHUNK], qnx[HD_NMS_CHUNK], qpref[HD_NMS_CHUNK + 1];
+    float red[32][6];
+    float invS, dx, dy;
+    int log2T;
+};
+
+__device__ __forceinline__ bool hd_box_proper(const float4& b) {
+    return (b.z > b.x) && (b.w > b.y) && (fabsf(b.x) < 3.0e38f) && (fabsf(b.y) < 3.0e38f) && (fabsf(b.z) < 3.0e38f) && (fabsf(b.w) < 3.0e38f);
+}
+__device__ __forceinline__ int hd_cell(float v, float invS) { return __float2int_rd(v * invS); }  // saturating, monotone
+__device__ __forceinline__ uint32_t hd_cell_hash(int gx, int gy, int log2T) {
+    return (((uint32_t)gx * 0x9E3779B1u) ^ ((uint32_t)gy * 0x85EBCA77u)) * 0xC2B2AE3Du >> (32 - log2T);
+}
+
+template <int NT, typename KeepT>
+__device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n_use, int max_det, float thr, uint32_t* removed,
+                                      KeepT* keep_r, HdNmsSmem& sm, HdGridSmem& gs, int* bucket, int log2T, uint32_t* items) {
+    constexpr int ROWT = NT / 64, COLS = 64 / ROWT;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int T = 1 << log2T;
+    // ---- grid parameters: block reductions over the proper boxes
+    float cnt = 0.f, sarea = 0.f, wmax = 0.f, hmax = 0.f, cmax = 0.f;
+    for (int r = tid; r < n_use; r += NT) {
+        const float4 b = sbox[r];
+        if (hd_box_proper(b)) {
+            const float w = b.z - b.x, h = b.w - b.y;
+            cnt += 1.f; sarea += sqrtf(w * h);
+            wmax = fmaxf(wmax, w); hmax = fmaxf(hmax, h);
+            cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        cnt += __shfl_xor_sync(HD_FULL, cnt, d); sarea += __shfl_xor_sync(HD_FULL, sarea, d);
+        wmax = fmaxf(wmax, __shfl_xor_sync(HD_FULL, wmax, d)); hmax = fmaxf(hmax, __shfl_xor_sync(HD_FULL, hmax, d));
+        cmax = fmaxf(cmax, __shfl_xor_sync(HD_FULL, cmax, d));
+    }
+    if (lane == 0) { gs.red[wid][0] = cnt; gs.red[wid][1] = sarea; gs.red[wid][2] = wmax; gs.red[wid][3] = hmax; gs.red[wid][4] = cmax; }
+    for (int i = tid; i < T + 1; i += NT) bucket[i] = 0;
+    for (int i = tid; i < (n_use + 31) / 32 + 2; i += NT) removed[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        float c = 0.f, sa = 0.f, wm = 0.f, hm = 0.f, cm = 0.f;
+        for (int w = 0; w < NT / 32; ++w) { c += gs.red[w][0]; sa += gs.red[w][1]; wm = fmaxf(wm, gs.red[w][2]); hm = fmaxf(hm, gs.red[w][3]); cm = fmaxf(cm, gs.red[w][4]); }
+        float S = (c > 0.f) ? 0.5f * sa / c : 1.0f;       // half the mean box side
+        if (!(S > 0.f) || !(S < 3.0e38f)) S = 1.0f;
+        const float f = fmaxf(0.0f, 0.5f - (thr - 1.0e-3f));
+        gs.invS = 1.0f / S;
+        gs.dx = f * wm + 5.0e-7f * cm;
+        gs.dy = f * hm + 5.0e-7f * cm;
+        gs.log2T = log2T;
+    }
+    __syncthreads();
+    const float invS = gs.invS, qdx = gs.dx, qdy = gs.dy;
+    // ---- counting sort of the proper boxes by centre cell
+    for (int r = tid; r < n_use; r += NT) {
+        const float4 b = sbox[r];
+        if (hd_box_proper(b)) atomicAdd(&bucket[hd_cell_hash(hd_cell(0.5f * (b.x + b.z), invS), hd_cell(0.5f * (b.y + b.w), invS), log2T)], 1);
+    }
+    __syncthreads();
+    {   // exclusive scan of T counts (T/NT consecutive buckets per thread)
+        const int per = (T + NT - 1) / NT;
+        int loc = 0;
+        for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < T) loc += bucket[i]; }
+        int incl = loc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
+        __shared__ int wsum[NT / 32];
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        int pre = incl - loc;
+        for (int w = 0; w < wid; ++w) pre += wsum[w];
+        for (int k = 0; k < per; ++k) { const int i = tid * per + k; if (i < T) { const int c = bucket[i]; bucket[i] = pre; pre += c; } }
+    }
+    __syncthreads();
+    for (int r = tid; r < n_use; r += NT) {
+        const float4 b = sbox[r];
+        if (hd_box_proper(b)) {
+            const uint32_t h = hd_cell_hash(hd_cell(0.5f * (b.x + b.z), invS), hd_cell(0.5f * (b.y + b.w), invS), log2T);
+            items[atomicAdd(&bucket[h], 1)] = (uint32_t)r;   // afterwards bucket[h] = end of h = start of h+1
+        }
+    }
+    __syncthreads();
+
+    int kc = 0;
+    for (int base = 0; base < n_use; base += HD_NMS_CHUNK) {
+        const int m = min(HD_NMS_CHUNK, n_use - base);
+        if (tid < HD_NMS_CHUNK) {
+            sm.cmask[tid] = 0ull;   // used as the column mask: bit i of cmask[j] <=> box i (i<j) suppresses box j
+            if (tid < m) {
+                const float4 bx = sbox[base + tid];
+                sm.cbox[tid] = bx; sm.carea[tid] = hd_area(bx); sm.ccls[tid] = scls ? scls[base + tid] : 0;
+            }
+        }
+        __syncthreads();
+        {
+            const int i = tid / ROWT, j0 = (tid % ROWT) * COLS;
+            if (i < m) {
+                const float4 bi = sm.cbox[i];
+                const float ai = sm.carea[i];
+                const int ci = sm.ccls[i];
+#pragma unroll 4
+                for (int q = 0; q < COLS; ++q) {
+                    const int jj = j0 + q;
+                    if (jj > i && jj < m && sm.ccls[jj] == ci && hd_iou_gt(bi, ai, sm.cbox[jj], sm.carea[jj], thr)) atomicOr(&sm.cmask[jj], 1ull << i);
+                }
+            }
+        }
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned long long rem = (unsigned long long)removed[base >> 5] | ((unsigned long long)removed[(base >> 5) + 1] << 32);
+            const unsigned long long alive = ~rem & ((m == 64) ? ~0ull : ((1ull << m) - 1ull));
+            const unsigned long long c0 = sm.cmask[lane], c1 = sm.cmask[lane + 32];
+            unsigned long long kept = alive;
+            for (int it = 0; it < 64; ++it) {
+                const bool b0 = ((alive >> lane) & 1ull) && !(c0 & kept);
+                const bool b1 = ((alive >> (lane + 32)) & 1ull) && !(c1 & kept);
+                const unsigned long long nk = (unsigned long long)__ballot_sync(HD_FULL, b0) | ((unsigned long long)__ballot_sync(HD_FULL, b1) << 32);
+                if (nk == kept) break;
+                kept = nk;
+            }
+            const int room = max_det - kc;
+            while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll((long long)kept)));
+            // query ranges of the kept boxes
+            int ncell[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int bit = lane + 32 * h;
+                ncell[h] = 0;
+                if ((kept >> bit) & 1ull) {
+                    keep_r[kc + __popcll(kept & ((1ull << bit) - 1ull))] = (KeepT)(base + bit);
+                    const float4 b = sm.cbox[bit];
+                    if (hd_box_proper(b)) {
+                        const int x1 = hd_cell(b.x - qdx, invS), x2 = hd_cell(b.z + qdx, invS);
+                        const int y1 = hd_cell(b.y - qdy, invS), y2 = hd_cell(b.w + qdy, invS);
+                        const long long nx = (long long)x2 - x1 + 1, ny = (long long)y2 - y1 + 1;
+                        if (nx * ny >= (long long)T) { gs.qnx[bit] = 0; ncell[h] = T; }      // huge box: walk every bucket
+                        else { gs.qx1[bit] = x1; gs.qy1[bit] = y1; gs.qnx[bit] = (int)nx; ncell[h] = (int)(nx * ny); }
+                    }
+                }
+            }
+            // exclusive prefix over the 64 slots (slot = chunk position)
+            int i0 = ncell[0], i1 = ncell[1];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y0 = __shfl_up_sync(HD_FULL, i0, d), y1 = __shfl_up_sync(HD_FULL, i1, d);
+                if (lane >= d) { i0 += y0; i1 += y1; }
+            }
+            const int tot0 = __shfl_sync(HD_FULL, i0, 31);
+            gs.qpref[lane] = i0 - ncell[0];
+            gs.qpref[lane + 32] = tot0 + i1 - ncell[1];
+            if (lane == 31) gs.qpref[64] = tot0 + i1;
+            if (lane == 0) { sm.s_kept = kept; sm.s_kc = kc + __popcll(kept); }
+        }
+        __syncthreads();
+        const unsigned long long kept = sm.s_kept;
+        kc = sm.s_kc;
+        const bool done = kc >= max_det;
+        const int total = gs.qpref[64];
+        if (!done && kept && base + HD_NMS_CHUNK < n_use) {
+            for (int t = tid; t < total; t += NT) {
+                // slot i with qpref[i] <= t < qpref[i+1]
+                int lo = 0, hi = 64;
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (gs.qpref[mid] <= t) lo = mid; else hi = mid; }
+                const int i = lo, local = t - gs.qpref[i];
+                uint32_t hb;
+                if (gs.qnx[i] == 0) hb = (uint32_t)local;
+                else { const int nx = gs.qnx[i]; const int gy = local / nx; hb = hd_cell_hash(gs.qx1[i] + (local - gy * nx), gs.qy1[i] + gy, log2T); }
+                const int s0 = hb ? bucket[hb - 1] : 0, s1 = bucket[hb];
+                if (s1 <= s0) continue;
+                const float4 bi = sm.cbox[i];
+                const float ai = sm.carea[i];
+                const int ci = sm.ccls[i];
+                const float lx = bi.x - qdx, hx = bi.z + qdx, ly = bi.y - qdy, hy = bi.w + qdy;
+                for (int k = s0; k < s1; ++k) {
+                    const int jr = (int)items[k];
+                    if (jr < base + HD_NMS_CHUNK) continue;
+                    if ((removed[jr >> 5] >> (jr & 31)) & 1u) continue;
+                    const float4 bj = sbox[jr];
+                    const float cx = 0.5f * (bj.x + bj.z), cy = 0.5f * (bj.y + bj.w);
+                    if (cx < lx || cx > hx || cy < ly || cy > hy) continue;
+                    if ((scls ? scls[jr] : 0) != ci) continue;
+                    if (hd_iou_gt(bi, ai, bj, hd_area(bj), thr)) atomicOr(&removed[jr >> 5], 1u << (jr & 31));
                 }
             }
         }

@@ -9,7 +9,7 @@
 // whole image.  Work is kept*n instead of n^2/2 and the loop stops as soon as max_det boxes are kept,
 // which is what the detection callers (max_det=300, RPN post_nms_top_n) need.
 #include "hd_sort.cuh"
-#include "hd_nms_core.cuh"
+#include "hd_small_nms.cuh"
 
 #define NMS_NT 1024
 
@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     extern __shared__ uint32_t removed[];  // ceil(cap/32) words (+1 pad)
     __shared__ HdSortSmem<NMS_NT> ssm;
     __shared__ HdNmsSmem nsm;
+    __shared__ HdGridSmem gsm;
 
     const int tid = threadIdx.x;
     const int b = blockIdx.x;
@@ -75,7 +76,15 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
         scls[r] = (p.class_mode == HD_NMS_CLASS_EXACT) ? c : 0;
     }
     __syncthreads();
-    const int kc = hd_cta_greedy_nms<NMS_NT>(sbox, (p.class_mode == HD_NMS_CLASS_EXACT) ? scls : nullptr, n_use, max_det, p.thr, removed, keep_r, nsm);
+    const int* clsp = (p.class_mode == HD_NMS_CLASS_EXACT) ? scls : nullptr;
+    int kc;
+    if (n_use > HD_GRID_MIN_N && p.thr > 0.05f) {
+        // big segment: spatially pruned pass; buckets alias the (finished) sort scratch, items use the free key buffer
+        kc = hd_cta_greedy_nms_grid<NMS_NT, int>(sbox, clsp, n_use, max_det, p.thr, removed, keep_r, nsm, gsm, &ssm.warp_cnt[0][0], 12,
+                                                 (uint32_t*)(res ? k0 : k1));
+    } else {
+        kc = hd_cta_greedy_nms<NMS_NT, int>(sbox, clsp, n_use, max_det, p.thr, removed, keep_r, nsm);
+    }
 
     for (int q = tid; q < kc; q += NMS_NT) {
         const int r = keep_r[q];
@@ -90,6 +99,14 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
         if (p.out_idx) p.out_idx[(size_t)b * p.max_det + q] = p.tiebreak ? (long long)p.tiebreak[off + slot] : (long long)slot;
     }
     if (tid == 0) p.out_count[b] = kc;
+}
+
+// small-image variant: 256 threads, everything in shared memory, several images per SM at once
+__global__ void __launch_bounds__(HD_SMALL_NT) small_nms_kernel(const __grid_constant__ NmsParams p, const __grid_constant__ HdNmsTail q) {
+    __shared__ HdSmallSmem ssm;
+    const int b = blockIdx.x;
+    const int n = p.counts ? min(__ldcg(p.counts + b), p.cap) : p.n_fixed;
+    hd_small_nms_image(ssm, q, b, p.cap, n, p.boxes, p.scores, p.cls, p.tiebreak);
 }
 
 // ------------------------------------------------------------------------------------------------ box_iou
@@ -192,6 +209,17 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
     if (smem > smem_set) {
         HD_CUDA_CALL(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         smem_set = 160 * 1024;
+    }
+    if (min_n < 0 && (counts != nullptr || n_fixed <= HD_SMALL_N)) {
+        // images with <= HD_SMALL_N candidates: shared-memory kernel; the radix-sort kernel below then only
+        // works on the larger ones (it returns at once for the rest)
+        HdNmsTail q;
+        q.thr = p.thr; q.class_mode = class_mode; q.offset_scale = offset_scale; q.max_nms = max_nms; q.max_det = max_det;
+        q.out_det = out_det; q.out_idx = (long long*)out_idx; q.out_count = out_count;
+        small_nms_kernel<<<B, HD_SMALL_NT, 0, st>>>(p, q);
+        HD_CUDA_LAUNCH_CHECK("small_nms_kernel");
+        p.min_n = HD_SMALL_N;
+        if (counts == nullptr) return HD_OK;
     }
     sort_nms_kernel<<<B, NMS_NT, smem, st>>>(p);
     HD_CUDA_LAUNCH_CHECK("sort_nms_kernel");

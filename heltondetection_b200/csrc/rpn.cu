@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     extern __shared__ uint32_t removed[];
     __shared__ HdSortSmem<RPN_NT> ssm;
     __shared__ HdNmsSmem nsm;
+    __shared__ HdGridSmem gsm;
     __shared__ int s_hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_need, s_valid, s_count;
@@ -212,7 +213,12 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     const float4* __restrict__ boxes = p.boxes + (size_t)b * p.N;
     for (int r = tid; r < n; r += RPN_NT) sbox[r] = boxes[order[r]];
     __syncthreads();
-    const int kc = hd_cta_greedy_nms<RPN_NT>(sbox, nullptr, n, p.n_post, p.thr, removed, keep_r, nsm);
+    int kc;
+    if (n > HD_GRID_MIN_N && p.thr > 0.05f)
+        kc = hd_cta_greedy_nms_grid<RPN_NT, int>(sbox, nullptr, n, p.n_post, p.thr, removed, keep_r, nsm, gsm, &ssm.warp_cnt[0][0], 12,
+                                                 (uint32_t*)(res ? k0 : k1));
+    else
+        kc = hd_cta_greedy_nms<RPN_NT, int>(sbox, nullptr, n, p.n_post, p.thr, removed, keep_r, nsm);
     for (int q = tid; q < p.n_post; q += RPN_NT) {
         float* o = p.out_rois + ((size_t)b * p.n_post + q) * 5;
         o[0] = (float)b;

@@ -1,7 +1,6 @@
 // YOLOv5 head kernels: dense decode (a1), fused decode+filter+compaction (a1+a2), filter on decoded pred (a2).
 // Reference feature: README.md:9; semantics SURVEY.md A.1/A.2 (ultralytics / bubbliiiing lineage, README.md:158-162).
 #include "hd_common.cuh"
-#include "hd_nms_core.cuh"
 
 struct YoloParams {
     const float* data[HD_MAX_LEVELS];
@@ -57,17 +56,18 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
 #pragma unroll
     for (int k = 0; k < 4; ++k) valid[k] = (cell0 + k) < HW;
 
+    bool need = true;  // lane fetches the non-objectness planes (narrowed below in sparse mode)
     auto load4 = [&](int plane, float* v) {
         const float* q = base + (size_t)plane * HW;
         if (VEC) {
-            if (valid[0]) {
+            if (valid[0] && need) {
                 float4 w = hd_ldg_stream4(q);
                 v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
             }
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (valid[k]) v[k] = hd_ldg_stream(q + k);
+                if (valid[k] && need) v[k] = hd_ldg_stream(q + k);
         }
     };
 
@@ -78,9 +78,16 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
 #pragma unroll
     for (int k = 0; k < 4; ++k) gate_any |= valid[k] && (o[k] > p.gate);
     if (!p.dense && !__any_sync(HD_FULL, gate_any)) return;
+    // sparse mode: only lanes that own a possible survivor touch the other 84 planes, so the traffic of a
+    // surviving tile shrinks from 85 x 512 B to 85 x (one 32-byte sector per surviving lane)
+    need = p.dense || gate_any;
 
 #pragma unroll
-    for (int c = 0; c < 4; ++c) load4(c, bx[c]);
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bx[c][k] = 0.0f;
+        load4(c, bx[c]);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { m[k] = -INFINITY; L[k] = -INFINITY; j[k] = 0; }
 
@@ -178,7 +185,7 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) yolo_decode_filter_kernel(const __grid_constant__ YoloParams p,
+__global__ void __launch_bounds__(256, 4) yolo_decode_filter_kernel(const __grid_constant__ YoloParams p,
                                                                  float4* __restrict__ cand_box,
                                                                  float* __restrict__ cand_score,
                                                                  int* __restrict__ cand_cls,
@@ -187,117 +194,6 @@ __global__ void __launch_bounds__(256) yolo_decode_filter_kernel(const __grid_co
     const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.total_items) return;
     yolo_decode_item<VEC>(p, item, threadIdx.x & 31, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fused decode -> NMS.  Same decode as above; in addition every warp, after its tile, bumps a per-image
-// completion counter.  The warp that completes an image hands it to its CTA, which runs the whole per-image
-// tail in shared memory while the rest of the grid keeps streaming the next images from HBM:
-// enumeration sort on (score desc, anchor asc) -> sorted boxes -> lazy chunked greedy NMS -> padded output.
-// Images with more than FUSED_SMALL_N candidates are left to sort_nms_kernel (launched right after with
-// min_n = FUSED_SMALL_N), which owns the big radix-sort path.
-// ------------------------------------------------------------------------------------------------
-#define FUSED_SMALL_N 512
-struct FusedTail {
-    int* img_done;  // [B], zeroed
-    float thr;      // hd_thr_floor(iou)
-    int class_mode;
-    float offset_scale;
-    int max_nms, max_det;
-    float* out_det;
-    long long* out_idx;
-    int* out_count;
-};
-
-__device__ __forceinline__ float ldcg_f(const float* p) { return __ldcg(p); }
-
-__device__ void fused_small_nms(const YoloParams& p, const FusedTail& q, int b, const float4* cand_box, const float* cand_score,
-                                const int* cand_cls, const int* cand_anchor, const int* cand_count) {
-    __shared__ unsigned long long s_key[FUSED_SMALL_N];
-    __shared__ float4 s_box[FUSED_SMALL_N];
-    __shared__ unsigned short s_order[FUSED_SMALL_N];
-    __shared__ int s_cls[FUSED_SMALL_N];
-    __shared__ int s_keep[FUSED_SMALL_N];
-    __shared__ uint32_t s_removed[FUSED_SMALL_N / 32 + 4];
-    __shared__ HdNmsSmem nsm;
-    const int tid = threadIdx.x;
-    const int n = min(__ldcg(cand_count + b), p.cap);
-    if (n > FUSED_SMALL_N) return;  // big path (sort_nms_kernel)
-    if (n <= 0) {
-        if (tid == 0) q.out_count[b] = 0;
-        return;
-    }
-    const size_t off = (size_t)b * p.cap;
-    for (int i = tid; i < n; i += 256)
-        s_key[i] = ((unsigned long long)(~hd_orderable(__ldcg(cand_score + off + i))) << 32) | (uint32_t)__ldcg(cand_anchor + off + i);
-    __syncthreads();
-    // enumeration sort: keys are unique (anchor ids), rank = number of smaller keys
-    for (int i = tid; i < n; i += 256) {
-        const unsigned long long k = s_key[i];
-        int r = 0;
-#pragma unroll 4
-        for (int j = 0; j < n; ++j) r += (s_key[j] < k);
-        s_order[r] = (unsigned short)i;
-    }
-    __syncthreads();
-    const int n_use = (q.max_nms > 0) ? min(n, q.max_nms) : n;
-    for (int r = tid; r < n_use; r += 256) {
-        const int slot = s_order[r];
-        float4 bx = __ldcg(cand_box + off + slot);
-        const int c = __ldcg(cand_cls + off + slot);
-        if (q.class_mode == HD_NMS_CLASS_OFFSET) {
-            const float o = __fmul_rn((float)c, q.offset_scale);
-            bx.x = __fadd_rn(bx.x, o); bx.y = __fadd_rn(bx.y, o); bx.z = __fadd_rn(bx.z, o); bx.w = __fadd_rn(bx.w, o);
-        }
-        s_box[r] = bx;
-        s_cls[r] = c;
-    }
-    __syncthreads();
-    const int kc = hd_cta_greedy_nms<256>(s_box, (q.class_mode == HD_NMS_CLASS_EXACT) ? s_cls : nullptr, n_use, q.max_det, q.thr,
-                                          s_removed, s_keep, nsm);
-    for (int k = tid; k < kc; k += 256) {
-        const int r = s_keep[k];
-        const int slot = s_order[r];
-        if (q.out_det) {
-            const float4 bx = __ldcg(cand_box + off + slot);
-            float* o = q.out_det + ((size_t)b * q.max_det + k) * 6;
-            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-            o[4] = __ldcg(cand_score + off + slot);
-            o[5] = (float)s_cls[r];
-        }
-        if (q.out_idx) q.out_idx[(size_t)b * q.max_det + k] = (long long)__ldcg(cand_anchor + off + slot);
-    }
-    if (tid == 0) q.out_count[b] = kc;
-    __syncthreads();
-}
-
-template <bool VEC>
-__global__ void __launch_bounds__(256, 4) yolo_fused_kernel(const __grid_constant__ YoloParams p, const __grid_constant__ FusedTail q,
-                                                         float4* __restrict__ cand_box, float* __restrict__ cand_score,
-                                                         int* __restrict__ cand_cls, int* __restrict__ cand_anchor,
-                                                         int* __restrict__ cand_count) {
-    __shared__ int s_done[8];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long item = (long long)blockIdx.x * 8 + wid;
-    int done_img = -1;
-    if (item < p.total_items) {
-        yolo_decode_item<VEC>(p, item, lane, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
-        __threadfence();  // candidates + count visible before the completion counter moves
-        __syncwarp();
-        if (lane == 0) {
-            const int b = (int)(item / p.items_per_image);
-            if (atomicAdd(q.img_done + b, 1) == p.items_per_image - 1) done_img = b;
-        }
-    }
-    if (lane == 0) s_done[wid] = done_img;
-    __syncthreads();
-#pragma unroll 1
-    for (int w = 0; w < 8; ++w) {
-        const int b = s_done[w];
-        if (b < 0) continue;  // uniform across the CTA
-        __threadfence();
-        fused_small_nms(p, q, b, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -510,71 +406,45 @@ extern "C" HD_API int hd_yolo_filter_pred(const float* pred, int B, int N, int n
     return HD_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ fused host entry
-int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
-                            const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
-                            float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
-                            int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream, int min_n);
-
-static void fused_ws_layout(int B, int cap, size_t* offs, size_t* total) {
+// ------------------------------------------------------------------------------------------------ one-call entry
+static void post_ws_layout(int B, int cap, size_t* offs, size_t* total) {
     size_t n = (size_t)B * cap, o = 0;
     offs[0] = o; o = hd_align_up(o + n * 16, 256);           // cand_box
     offs[1] = o; o = hd_align_up(o + n * 4, 256);            // cand_score
     offs[2] = o; o = hd_align_up(o + n * 4, 256);            // cand_cls
     offs[3] = o; o = hd_align_up(o + n * 4, 256);            // cand_anchor
-    offs[4] = o; o = hd_align_up(o + (size_t)B * 8, 256);    // cand_count[B] | img_done[B]
-    offs[5] = o; o += hd_sort_nms_workspace_size(B, cap);    // big-image sort/NMS scratch
+    offs[4] = o; o = hd_align_up(o + (size_t)B * 4, 256);    // cand_count
+    offs[5] = o; o += hd_sort_nms_workspace_size(B, cap);    // sort/NMS scratch of the large images
     *total = o;
 }
 
 extern "C" HD_API size_t hd_yolo_postprocess_workspace_size(int B, int total_anchors) {
     size_t offs[6], total;
-    fused_ws_layout(B < 0 ? 0 : B, total_anchors < 0 ? 0 : total_anchors, offs, &total);
+    post_ws_layout(B < 0 ? 0 : B, total_anchors < 0 ? 0 : total_anchors, offs, &total);
     return total + 256;
 }
 
 extern "C" HD_API int hd_yolo_postprocess(const hd_yolo_level* levels, int n_levels, int B, int A, int nc, double conf_thres, double iou_thres,
                                           int flags, int class_mode, float offset_scale, int max_nms, int max_det, float* out_det,
                                           int64_t* out_idx, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
-    YoloParams p;
-    int rc = fill_params(p, levels, n_levels, B, A, nc, 128);
-    if (rc) return rc;
-    HD_CHECK_ARG(class_mode >= 0 && class_mode <= 2, "class_mode must be 0,1,2, got %d", class_mode);
-    HD_CHECK_ARG(max_det > 0, "max_det must be > 0, got %d", max_det);
+    HD_CHECK_ARG(levels != nullptr && n_levels >= 1 && n_levels <= HD_MAX_LEVELS, "n_levels must be in [1,%d], got %d", HD_MAX_LEVELS, n_levels);
     if (B == 0) return HD_OK;
-    HD_CHECK_ARG(out_count != nullptr, "out_count is NULL");
-    const int cap = p.level_off[n_levels];
+    long long cap_ll = 0;
+    for (int l = 0; l < n_levels; ++l) cap_ll += (long long)A * levels[l].H * levels[l].W;
+    HD_CHECK_ARG(cap_ll > 0 && cap_ll < (1ll << 31), "bad total anchor count");
+    const int cap = (int)cap_ll;
     size_t offs[6], total;
-    fused_ws_layout(B, cap, offs, &total);
+    post_ws_layout(B, cap, offs, &total);
     uintptr_t w0 = hd_align_up((uintptr_t)workspace, 256);
     if (!workspace || w0 + total > (uintptr_t)workspace + workspace_bytes)
         HD_FAIL(HD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", total + 256, workspace_bytes);
-    float4* cand_box = (float4*)(w0 + offs[0]);
+    float* cand_box = (float*)(w0 + offs[0]);
     float* cand_score = (float*)(w0 + offs[1]);
-    int* cand_cls = (int*)(w0 + offs[2]);
-    int* cand_anchor = (int*)(w0 + offs[3]);
-    int* cand_count = (int*)(w0 + offs[4]);
-    p.thr = (float)conf_thres;
-    p.gate = conf_gate(conf_thres);
-    p.ge = (flags & HD_FLAG_CONF_GE) ? 1 : 0;
-    p.dense = (flags & HD_FLAG_DENSE_READ) ? 1 : 0;
-    p.cap = cap;
-    FusedTail q;
-    q.img_done = cand_count + B;
-    q.thr = hd_thr_floor(iou_thres);
-    q.class_mode = class_mode; q.offset_scale = offset_scale; q.max_nms = max_nms; q.max_det = max_det;
-    q.out_det = out_det; q.out_idx = (long long*)out_idx; q.out_count = out_count;
-    cudaStream_t st = (cudaStream_t)stream;
-    HD_CUDA_CALL(cudaMemsetAsync(cand_count, 0, sizeof(int) * 2 * (size_t)B, st));
-    bool vec = true;
-    for (int l = 0; l < n_levels; ++l) vec = vec && (p.HW[l] % 4 == 0) && (((uintptr_t)p.data[l] & 15) == 0);
-    long long blocks = (p.total_items + 7) / 8;
-    HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
-    if (vec) yolo_fused_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(p, q, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
-    else yolo_fused_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(p, q, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
-    HD_CUDA_LAUNCH_CHECK("yolo_fused_kernel");
-    // images with more than FUSED_SMALL_N candidates: radix-sort path (no-op pass when there are none)
-    return hd_sort_nms_batched_min((const float*)cand_box, cand_score, cand_cls, cand_anchor, cand_count, 0, B, cap, iou_thres, class_mode,
-                                   offset_scale, max_nms, max_det, out_det, out_idx, out_count, (void*)(w0 + offs[5]),
-                                   hd_sort_nms_workspace_size(B, cap), stream, FUSED_SMALL_N);
+    int32_t* cand_cls = (int32_t*)(w0 + offs[2]);
+    int32_t* cand_anchor = (int32_t*)(w0 + offs[3]);
+    int32_t* cand_count = (int32_t*)(w0 + offs[4]);
+    int rc = hd_yolo_decode_filter(levels, n_levels, B, A, nc, conf_thres, flags, cand_box, cand_score, cand_cls, cand_anchor, cand_count, cap, stream);
+    if (rc) return rc;
+    return hd_sort_nms_batched(cand_box, cand_score, cand_cls, cand_anchor, cand_count, 0, B, cap, iou_thres, class_mode, offset_scale, max_nms,
+                               max_det, out_det, out_idx, out_count, (void*)(w0 + offs[5]), hd_sort_nms_workspace_size(B, cap), stream);
 }

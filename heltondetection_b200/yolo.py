@@ -1,7 +1,7 @@
 """YOLOv5 post-process host API (drop-in names of the reference lineage, README.md:9).
 
 ``decode_box`` / ``non_max_suppression`` keep the lineage signatures;
-``YoloPostprocessor`` is the fused fast path (raw heads -> detections, two kernels, no host sync).
+``YoloPostprocessor`` is the fast path (raw heads -> detections, decode kernel + NMS kernels, no host sync).
 """
 import ctypes as C
 import torch
@@ -79,18 +79,19 @@ def _run_nms(buf, iou_thres, class_mode, max_wh, max_nms):
 
 
 class YoloPostprocessor:
-    """Fused raw-head post-process: decode+filter+compaction kernel, then per-image sort+NMS kernel.
+    """Raw-head post-process: decode+filter+compaction kernel, then per-image sort+NMS kernels.
 
     __call__(outputs) -> (det [B,max_det,6] = x1,y1,x2,y2,conf,cls ; count [B] int32 ; idx [B,max_det] anchor ids)
     all on the device, padded, with no host synchronisation (CUDA-graph capturable)."""
 
     def __init__(self, anchors=DEFAULT_ANCHORS, strides=DEFAULT_STRIDES, conf_thres=0.25, iou_thres=0.45,
                  agnostic=False, max_det=300, max_nms=30000, max_wh=7680.0, class_mode="offset", ge=False,
-                 dense_read=False, fused=True, device=None):
-        """fused: one kernel decodes and runs each image's NMS as soon as its last tile is done (default);
-        False keeps the two-kernel path.  device: where the outputs live; needed when `outputs` are pinned HOST
-        tensors, which the kernel then reads directly over PCIe (zero-copy; only surviving tiles are fetched)."""
-        self.fused, self.device = bool(fused), (torch.device(device) if device is not None else None)
+                 dense_read=False, one_call=True, device=None):
+        """one_call: a single C-ABI call (hd_yolo_postprocess, internal workspace); False issues the decode and the
+        NMS entry points separately (same kernels, candidate buffers visible).  device: where the outputs live;
+        needed when `outputs` are pinned HOST tensors, which the kernel then reads directly over PCIe (zero-copy:
+        only the sectors of possible survivors are fetched)."""
+        self.one_call, self.device = bool(one_call), (torch.device(device) if device is not None else None)
         self._fkey = None
         self.anchors, self.strides = anchors, strides
         self.conf_thres, self.iou_thres = float(conf_thres), float(iou_thres)
@@ -112,7 +113,7 @@ class YoloPostprocessor:
             return keep[0].device
         return torch.device("cuda", torch.cuda.current_device())
 
-    def _fused_call(self, arr, keep, B, A, nc, total):
+    def _one_call(self, arr, keep, B, A, nc, total):
         dev = self._out_device(keep)
         key = (B, total, dev)
         if self._fkey != key:
@@ -131,15 +132,31 @@ class YoloPostprocessor:
         return self.f_det, self.f_count, self.f_idx
 
     def __call__(self, outputs):
-        arr, keep, B, A, nc, total = _levels(outputs, self.anchors, self.strides, host_ok=True)
-        if self.fused:
-            return self._fused_call(arr, keep, B, A, nc, total)
+        # the level table only depends on the pointers/shapes: rebuild it when they change
+        sig = tuple((x.data_ptr(), tuple(x.shape), x.dtype, x.is_contiguous()) for x in outputs)
+        if getattr(self, "_sig", None) != sig:
+            self._lv = _levels(outputs, self.anchors, self.strides, host_ok=True)
+            self._sig = sig
+        arr, keep, B, A, nc, total = self._lv
+        if self.one_call:
+            return self._one_call(arr, keep, B, A, nc, total)
         buf = self.buffers(B, total, self._out_device(keep))
         _lib.check(_lib.lib().hd_yolo_decode_filter(
             arr, len(keep), B, A, nc, self.conf_thres, self.flags, _lib.ptr(buf.box), _lib.ptr(buf.score),
             _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))
         _run_nms(buf, self.iou_thres, self.class_mode, self.max_wh, self.max_nms)
         return buf.det, buf.out_count, buf.idx
+
+    def graph(self, outputs, warmup=3):
+        """Capture one post-process of `outputs` (fixed buffers) into a CUDA graph; returns (replay, det, count, idx).
+        replay() re-runs the captured kernels on whatever the input buffers hold -- no per-call host work."""
+        for _ in range(warmup):
+            self(outputs)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            det, count, idx = self(outputs)
+        return g.replay, det, count, idx
 
     def candidates(self, outputs):
         """decode+filter only -> per image (cand [n,6], anchor idx [n]) sorted by anchor index (test helper)."""
@@ -169,7 +186,7 @@ def _slice(det, count, idx=None):
 
 
 def postprocess(outputs, conf_thres=0.25, iou_thres=0.45, return_index=False, **kw):
-    """Raw heads -> list of [k,6] detections (fused path)."""
+    """Raw heads -> list of [k,6] detections (fast path)."""
     det, count, idx = YoloPostprocessor(conf_thres=conf_thres, iou_thres=iou_thres, **kw)(outputs)
     return _slice(det, count, idx) if return_index else _slice(det, count)
 

@@ -80,11 +80,11 @@ HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels /*host*/, int n_lev
                           int flags, float* cand_box, float* cand_score, int32_t* cand_cls, int32_t* cand_anchor,
                           int32_t* cand_count, int cap, void* stream);
 
-/* One-call fused post-process: decode+filter+compaction, with the per-image sort + class-aware NMS of every image
- * run inside the same kernel by the CTA that completes the image's last tile (images with more than 512
- * candidates are finished by a second, radix-sort kernel).  Outputs as hd_sort_nms_batched; out_idx holds flat
- * anchor indices.  `data` pointers may also be pinned, mapped HOST memory (UVA zero-copy): with the default
- * objectness-tile skip only the surviving tiles cross PCIe. */
+/* One-call post-process: hd_yolo_decode_filter followed by hd_sort_nms_batched on an internal candidate buffer
+ * carved from `workspace` (three launches: 1 KB memset, decode kernel, small-image NMS kernel; a fourth,
+ * radix-sort kernel only does work for images with more than 512 candidates).  Outputs as hd_sort_nms_batched;
+ * out_idx holds flat anchor indices.  `data` pointers may also be pinned, mapped HOST memory (UVA zero-copy):
+ * with the default objectness skip only the 32-byte sectors of possible survivors cross PCIe. */
 HD_API size_t hd_yolo_postprocess_workspace_size(int B, int total_anchors);
 HD_API int hd_yolo_postprocess(const hd_yolo_level* levels /*host*/, int n_levels, int B, int A, int nc, double conf_thres,
                                double iou_thres, int flags, int class_mode, float offset_scale, int max_nms, int max_det,

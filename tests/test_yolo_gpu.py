@@ -112,13 +112,13 @@ def test_no_candidates_and_empty_batch():
 
 
 @pytest.mark.parametrize("thr", [0.25, 0.02, 0.001])
-def test_fused_kernel_equals_two_kernel_path(cfg1, thr):
-    """thr 0.25: every image takes the in-kernel small-n tail; 0.001: all go to the radix path; 0.02: mixed."""
+def test_one_call_entry_equals_separate_entry_points(cfg1, thr):
+    """thr 0.25: every image takes the small-image NMS kernel; 0.001: all go to the radix/grid path; 0.02: mixed."""
     from heltondetection_b200 import yolo
     heads = [h.cuda() for h in cfg1]
-    a = yolo.YoloPostprocessor(conf_thres=thr, fused=True)(heads)
+    a = yolo.YoloPostprocessor(conf_thres=thr, one_call=True)(heads)
     a = [t.clone() for t in a]
-    b = yolo.YoloPostprocessor(conf_thres=thr, fused=False)(heads)
+    b = yolo.YoloPostprocessor(conf_thres=thr, one_call=False)(heads)
     assert torch.equal(a[1], b[1])
     for i, n in enumerate(a[1].tolist()):
         assert torch.equal(a[0][i, :n], b[0][i, :n]) and torch.equal(a[2][i, :n], b[2][i, :n])

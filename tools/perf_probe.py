@@ -56,6 +56,12 @@ def yolo_cfg(tag, B, img, nc, G, seed, conf, iou, dense_scene):
         print(f"    candidates/img mean {cnt.mean().item():.0f} max {cnt.max().item():.0f}; kept mean {buf.out_count.float().mean().item():.0f}")
         t3 = timeit(lambda: pp(heads))
         report(f"{tag} full postprocess ({'dense' if mode else 'sparse'})", t3, nbytes, B)
+        rp = pp.graph(heads)[0]
+        t4 = timeit(rp, iters=50)
+        report(f"{tag} full postprocess, CUDA graph ({'dense' if mode else 'sparse'})", t4, nbytes, B)
+        pu = yolo.YoloPostprocessor(conf_thres=conf, iou_thres=iou, dense_read=mode, one_call=False)
+        t5 = timeit(pu.graph(heads)[0], iters=50)
+        report(f"{tag} two-kernel path, CUDA graph ({'dense' if mode else 'sparse'})", t5, nbytes, B)
     t = timeit(lambda: yolo.decode_box(heads), iters=5)
     report(f"{tag} decode_box (dense pred out)", t, 2 * nbytes, B)
     return heads_cpu, heads
