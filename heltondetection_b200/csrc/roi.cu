@@ -190,6 +190,158 @@ __global__ void __launch_bounds__(256) roi_align_nhwc_kernel(const __grid_consta
     tile_store(p.out + (size_t)k * p.C * nb, tile, p.C * nb, use_tma != 0);
 }
 
+// ------------------------------------------------------------------------------------------------ RoIAlign NHWC, float4
+// Channel-quad variant (C % 4 == 0): a thread owns 4 consecutive channels (one 128-bit load per corner), the 256
+// threads form 256/QT bin groups that walk the PH*PW bins side by side.  ~5x fewer instructions per channel than
+// the scalar kernel; zero-weight table padding is predicated off so it costs no L1 bandwidth; the four results
+// of a thread are written to the [C][PH*PW] tile in a lane-rotated order that is free of bank conflicts.
+template <int E>
+__device__ __forceinline__ void roi_align_bins_quad(const float* __restrict__ f, int q, int g, int groups, const AxisEntry* ytab,
+                                                    const AxisEntry* xtab, int PH, int PW, float count, float* tile, int rot) {
+    const int nb = PH * PW;
+    for (int bin = g; bin < nb; bin += groups) {
+        const int ph = bin / PW, pw = bin - ph * PW;
+        int xo[E]; float wx[E];
+#pragma unroll
+        for (int b = 0; b < E; ++b) { xo[b] = xtab[pw * E + b].off; wx[b] = xtab[pw * E + b].w; }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < E; ++a) {
+            const int yo = ytab[ph * E + a].off;
+            const float wy = ytab[ph * E + a].w;
+            if (wy == 0.0f) continue;  // padding (warp-uniform)
+            const float4* __restrict__ row = reinterpret_cast<const float4*>(f + yo) + q;
+            float4 v[E];
+#pragma unroll
+            for (int b = 0; b < E; ++b) v[b] = (wx[b] != 0.0f) ? __ldg(row + (xo[b] >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int b = 0; b < E; ++b) { r.x = fmaf(wx[b], v[b].x, r.x); r.y = fmaf(wx[b], v[b].y, r.y); r.z = fmaf(wx[b], v[b].z, r.z); r.w = fmaf(wx[b], v[b].w, r.w); }
+            acc.x = fmaf(wy, r.x, acc.x); acc.y = fmaf(wy, r.y, acc.y); acc.z = fmaf(wy, r.z, acc.z); acc.w = fmaf(wy, r.w, acc.w);
+        }
+        acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count); acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+        float* t = tile + (size_t)(4 * q) * nb + bin;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int k = (s + rot) & 3;
+            const float val = (k == 0) ? acc.x : (k == 1) ? acc.y : (k == 2) ? acc.z : acc.w;
+            t[k * nb] = val;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) roi_align_nhwc_quad_kernel(const __grid_constant__ RoiParams p, int use_tma, int QT) {
+    extern __shared__ __align__(128) float smem_f[];
+    float* tile = smem_f;                                  // [C][PH*PW]
+    AxisEntry* ytab = (AxisEntry*)(tile + (size_t)p.C * p.PH * p.PW);
+    AxisEntry* xtab = ytab + ROI_TAB;
+    __shared__ int ycnt[64], xcnt[64];
+
+    const long long k = blockIdx.x;
+    const float* roi = p.rois + k * 5;
+    const int lvl = p.level_ids ? p.level_ids[k] : 0;
+    const int H = p.H[lvl], W = p.W[lvl];
+    const float sc = p.scale[lvl];
+    const int bidx = (int)roi[0];
+    const float off = p.aligned ? 0.5f : 0.0f;
+    const float sw = __fsub_rn(__fmul_rn(roi[1], sc), off), sh = __fsub_rn(__fmul_rn(roi[2], sc), off);
+    const float ew = __fsub_rn(__fmul_rn(roi[3], sc), off), eh = __fsub_rn(__fmul_rn(roi[4], sc), off);
+    float rw = __fsub_rn(ew, sw), rh = __fsub_rn(eh, sh);
+    if (!p.aligned) { rw = fmaxf(rw, 1.0f); rh = fmaxf(rh, 1.0f); }
+    const float bh = __fdiv_rn(rh, (float)p.PH), bw = __fdiv_rn(rw, (float)p.PW);
+    const int gh = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)p.PH));
+    const int gw = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)p.PW));
+    const float count = (float)max(gh * gw, 1);
+    const int need = 2 * max(max(gh, gw), 0);
+    const int E = need <= 4 ? 4 : (need <= 8 ? 8 : (need <= 16 ? 16 : 0));
+    const int nb = p.PH * p.PW;
+    const float* __restrict__ f = p.data[lvl] + (size_t)bidx * H * W * p.C;
+    if (E && E * p.PH <= ROI_TAB && E * p.PW <= ROI_TAB) {
+        if (threadIdx.x < p.PH) build_axis(ytab, ycnt, threadIdx.x, E, sh, bh, gh, H, W * p.C, E);
+        else if (threadIdx.x >= 64 && threadIdx.x < 64 + p.PW) build_axis(xtab, xcnt, threadIdx.x - 64, E, sw, bw, gw, W, p.C, E);
+        __syncthreads();
+        const int nq = p.C >> 2, groups = 256 / QT, g = threadIdx.x / QT, rot = (threadIdx.x & 31) >> 3;
+        for (int q = threadIdx.x % QT; q < nq; q += QT) {
+            if (E == 4) roi_align_bins_quad<4>(f, q, g, groups, ytab, xtab, p.PH, p.PW, count, tile, rot);
+            else if (E == 8) roi_align_bins_quad<8>(f, q, g, groups, ytab, xtab, p.PH, p.PW, count, tile, rot);
+            else roi_align_bins_quad<16>(f, q, g, groups, ytab, xtab, p.PH, p.PW, count, tile, rot);
+        }
+    } else if ((long long)2 * max(gh, 1) * p.PH <= ROI_TAB && (long long)2 * max(gw, 1) * p.PW <= ROI_TAB) {
+        // large adaptive grids: merged tables with run-time entry counts (<= bin size + 1 cells per axis)
+        const int stride_y = 2 * max(gh, 1), stride_x = 2 * max(gw, 1);
+        if (threadIdx.x < p.PH) build_axis(ytab, ycnt, threadIdx.x, stride_y, sh, bh, gh, H, W * p.C, 0);
+        else if (threadIdx.x >= 64 && threadIdx.x < 64 + p.PW) build_axis(xtab, xcnt, threadIdx.x - 64, stride_x, sw, bw, gw, W, p.C, 0);
+        __syncthreads();
+        const int nq = p.C >> 2, groups = 256 / QT, g = threadIdx.x / QT, rot = (threadIdx.x & 31) >> 3;
+        for (int q = threadIdx.x % QT; q < nq; q += QT) {
+            for (int bin = g; bin < nb; bin += groups) {
+                const int ph = bin / p.PW, pw = bin - ph * p.PW;
+                const AxisEntry* yt = ytab + ph * stride_y;
+                const AxisEntry* xt = xtab + pw * stride_x;
+                const int ny = ycnt[ph], nx = xcnt[pw];
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int a = 0; a < ny; ++a) {
+                    const float4* __restrict__ row = reinterpret_cast<const float4*>(f + yt[a].off) + q;
+                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int b = 0;
+                    for (; b + 4 <= nx; b += 4) {
+                        const float4 v0 = __ldg(row + (xt[b].off >> 2)), v1 = __ldg(row + (xt[b + 1].off >> 2));
+                        const float4 v2 = __ldg(row + (xt[b + 2].off >> 2)), v3 = __ldg(row + (xt[b + 3].off >> 2));
+                        const float w0 = xt[b].w, w1 = xt[b + 1].w, w2 = xt[b + 2].w, w3 = xt[b + 3].w;
+                        r.x = fmaf(w0, v0.x, r.x); r.y = fmaf(w0, v0.y, r.y); r.z = fmaf(w0, v0.z, r.z); r.w = fmaf(w0, v0.w, r.w);
+                        r.x = fmaf(w1, v1.x, r.x); r.y = fmaf(w1, v1.y, r.y); r.z = fmaf(w1, v1.z, r.z); r.w = fmaf(w1, v1.w, r.w);
+                        r.x = fmaf(w2, v2.x, r.x); r.y = fmaf(w2, v2.y, r.y); r.z = fmaf(w2, v2.z, r.z); r.w = fmaf(w2, v2.w, r.w);
+                        r.x = fmaf(w3, v3.x, r.x); r.y = fmaf(w3, v3.y, r.y); r.z = fmaf(w3, v3.z, r.z); r.w = fmaf(w3, v3.w, r.w);
+                    }
+                    for (; b < nx; ++b) {
+                        const float4 v0 = __ldg(row + (xt[b].off >> 2));
+                        const float w0 = xt[b].w;
+                        r.x = fmaf(w0, v0.x, r.x); r.y = fmaf(w0, v0.y, r.y); r.z = fmaf(w0, v0.z, r.z); r.w = fmaf(w0, v0.w, r.w);
+                    }
+                    const float wy = yt[a].w;
+                    acc.x = fmaf(wy, r.x, acc.x); acc.y = fmaf(wy, r.y, acc.y); acc.z = fmaf(wy, r.z, acc.z); acc.w = fmaf(wy, r.w, acc.w);
+                }
+                acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count); acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+                float* t = tile + (size_t)(4 * q) * nb + bin;
+#pragma unroll
+                for (int s2 = 0; s2 < 4; ++s2) {
+                    const int k2 = (s2 + rot) & 3;
+                    t[k2 * nb] = (k2 == 0) ? acc.x : (k2 == 1) ? acc.y : (k2 == 2) ? acc.z : acc.w;
+                }
+            }
+        }
+    } else {
+        // grids beyond the table capacity: sample by sample (reference order), one channel per thread
+        for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+            const float* __restrict__ fc = f + c;
+            for (int ph = 0; ph < p.PH; ++ph)
+                for (int pw = 0; pw < p.PW; ++pw) {
+                    float acc = 0.0f;
+                    for (int iy = 0; iy < gh; ++iy) {
+                        float y = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)ph, bh)), __fdiv_rn(__fmul_rn(__fadd_rn((float)iy, 0.5f), bh), (float)gh));
+                        if (y < -1.0f || y > (float)H) continue;
+                        if (y <= 0.0f) y = 0.0f;
+                        int yl = (int)y, yh;
+                        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+                        const float ly = y - (float)yl, hy = 1.0f - ly;
+                        for (int ix = 0; ix < gw; ++ix) {
+                            float x = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)pw, bw)), __fdiv_rn(__fmul_rn(__fadd_rn((float)ix, 0.5f), bw), (float)gw));
+                            if (x < -1.0f || x > (float)W) continue;
+                            if (x <= 0.0f) x = 0.0f;
+                            int xl = (int)x, xh;
+                            if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+                            const float lx = x - (float)xl, hx = 1.0f - lx;
+                            acc += hy * hx * __ldg(fc + ((size_t)yl * W + xl) * p.C) + hy * lx * __ldg(fc + ((size_t)yl * W + xh) * p.C) +
+                                   ly * hx * __ldg(fc + ((size_t)yh * W + xl) * p.C) + ly * lx * __ldg(fc + ((size_t)yh * W + xh) * p.C);
+                        }
+                    }
+                    tile[c * nb + ph * p.PW + pw] = __fdiv_rn(acc, count);
+                }
+        }
+    }
+    tile_store(p.out + (size_t)k * p.C * nb, tile, p.C * nb, use_tma != 0);
+}
+
 // ------------------------------------------------------------------------------------------------ RoIPool NHWC
 __global__ void __launch_bounds__(256) roi_pool_nhwc_kernel(const __grid_constant__ RoiParams p, int use_tma) {
     extern __shared__ __align__(128) float smem_f[];
@@ -234,6 +386,65 @@ __global__ void __launch_bounds__(256) roi_pool_nhwc_kernel(const __grid_constan
                 }
                 tile[c * nb + ph * p.PW + pw] = mx;
                 if (p.argmax) p.argmax[((size_t)k * p.C + c) * nb + ph * p.PW + pw] = mi;
+            }
+        }
+    }
+    tile_store(p.out + (size_t)k * p.C * nb, tile, p.C * nb, use_tma != 0);
+}
+
+// ------------------------------------------------------------------------------------------------ RoIPool NHWC, float4
+__global__ void __launch_bounds__(256) roi_pool_nhwc_quad_kernel(const __grid_constant__ RoiParams p, int use_tma, int QT) {
+    extern __shared__ __align__(128) float smem_f[];
+    float* tile = smem_f;
+    const long long k = blockIdx.x;
+    const float* roi = p.rois + k * 5;
+    const int lvl = p.level_ids ? p.level_ids[k] : 0;
+    const int H = p.H[lvl], W = p.W[lvl];
+    const float sc = p.scale[lvl];
+    const int bidx = (int)roi[0];
+    const int x1 = (int)roundf(__fmul_rn(roi[1], sc)), y1 = (int)roundf(__fmul_rn(roi[2], sc));
+    const int x2 = (int)roundf(__fmul_rn(roi[3], sc)), y2 = (int)roundf(__fmul_rn(roi[4], sc));
+    const int rw = max(x2 - x1 + 1, 1), rh = max(y2 - y1 + 1, 1);
+    const float bh = __fdiv_rn((float)rh, (float)p.PH), bw = __fdiv_rn((float)rw, (float)p.PW);
+    const float* __restrict__ f = p.data[lvl] + (size_t)bidx * H * W * p.C;
+    const int nb = p.PH * p.PW, nq = p.C >> 2, groups = 256 / QT, g = threadIdx.x / QT, rot = (threadIdx.x & 31) >> 3;
+    for (int q = threadIdx.x % QT; q < nq; q += QT) {
+        const float4* __restrict__ fq = reinterpret_cast<const float4*>(f) + q;
+        for (int bin = g; bin < nb; bin += groups) {
+            const int ph = bin / p.PW, pw = bin - ph * p.PW;
+            const int hs = min(max((int)floorf(__fmul_rn((float)ph, bh)) + y1, 0), H);
+            const int he = min(max((int)ceilf(__fmul_rn((float)(ph + 1), bh)) + y1, 0), H);
+            const int ws = min(max((int)floorf(__fmul_rn((float)pw, bw)) + x1, 0), W);
+            const int we = min(max((int)ceilf(__fmul_rn((float)(pw + 1), bw)) + x1, 0), W);
+            const bool empty = (he <= hs) || (we <= ws);
+            const float init = empty ? 0.0f : -INFINITY;
+            float4 mx = make_float4(init, init, init, init);
+            int4 mi = make_int4(-1, -1, -1, -1);
+            auto upd = [&](const float4& v, int idx) {
+                if (v.x > mx.x) { mx.x = v.x; mi.x = idx; }
+                if (v.y > mx.y) { mx.y = v.y; mi.y = idx; }
+                if (v.z > mx.z) { mx.z = v.z; mi.z = idx; }
+                if (v.w > mx.w) { mx.w = v.w; mi.w = idx; }
+            };
+            for (int h = hs; h < he; ++h) {
+                const float4* __restrict__ row = fq + (size_t)h * W * nq;
+                int w = ws;
+                for (; w + 4 <= we; w += 4) {
+                    const float4 v0 = __ldg(row + (size_t)w * nq), v1 = __ldg(row + (size_t)(w + 1) * nq);
+                    const float4 v2 = __ldg(row + (size_t)(w + 2) * nq), v3 = __ldg(row + (size_t)(w + 3) * nq);
+                    upd(v0, h * W + w); upd(v1, h * W + w + 1); upd(v2, h * W + w + 2); upd(v3, h * W + w + 3);
+                }
+                for (; w < we; ++w) upd(__ldg(row + (size_t)w * nq), h * W + w);
+            }
+            float* t = tile + (size_t)(4 * q) * nb + bin;
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2) {
+                const int k2 = (s2 + rot) & 3;
+                t[k2 * nb] = (k2 == 0) ? mx.x : (k2 == 1) ? mx.y : (k2 == 2) ? mx.z : mx.w;
+            }
+            if (p.argmax) {
+                int* am = p.argmax + ((size_t)k * p.C + 4 * q) * nb + bin;
+                am[0] = mi.x; am[nb] = mi.y; am[2 * nb] = mi.z; am[3 * nb] = mi.w;
             }
         }
     }
@@ -391,11 +602,19 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
         if (!attr_set) {
             HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             HD_CUDA_CALL(cudaFuncSetAttribute(roi_pool_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            HD_CUDA_CALL(cudaFuncSetAttribute(roi_pool_nhwc_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             attr_set = true;
         }
         int threads = p.C >= 256 ? 256 : ((p.C + 31) / 32 * 32 < 128 ? 128 : (p.C + 31) / 32 * 32);
         for (int l = 0; l < p.n_levels; ++l) HD_CHECK_ARG((long long)p.H[l] * p.W[l] * p.C < (1ll << 31), "level %d: H*W*C must be < 2^31", l);
-        if (pool) roi_pool_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
+        bool quad = (p.C % 4 == 0);
+        for (int l = 0; l < p.n_levels; ++l) quad = quad && (((uintptr_t)p.data[l] & 15) == 0);
+        int nq = p.C / 4, QT = 8;               // threads per bin group: power of two >= channel quads, in [8,256]
+        while (QT < nq && QT < 256) QT <<= 1;
+        if (pool && quad) roi_pool_nhwc_quad_kernel<<<(unsigned)p.K, 256, smem, st>>>(p, use_tma, QT);
+        else if (pool) roi_pool_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
+        else if (quad) roi_align_nhwc_quad_kernel<<<(unsigned)p.K, 256, smem, st>>>(p, use_tma, QT);
         else roi_align_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
         HD_CUDA_LAUNCH_CHECK("roi_nhwc_kernel");
     } else if (layout == HD_LAYOUT_NCHW) {

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     __shared__ HdGridSmem gsm;
     __shared__ int s_hist[256];
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_need, s_valid, s_count;
+    __shared__ int s_need, s_valid, s_count, s_cand;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.x;
@@ -121,15 +121,50 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     float4* sbox = p.sbox + off;
     int* keep_r = p.keep_r + off;
 
-    // number of valid (key != 0) proposals
-    if (tid == 0) { s_valid = 0; s_count = 0; }
-    __syncthreads();
-    {
-        int c = 0;
-        for (int i = tid; i < p.N; i += RPN_NT) c += keys[i] != 0u;
+    // ---- radix select of the k-th largest composite.  Full scans of the keys are latency bound, so every scan
+    // keeps four independent loads in flight per thread, and after two digit passes (16 score bits) the few
+    // candidates that still match the prefix are pulled into shared memory, where the remaining digits are resolved.
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(&ssm.warp_cnt[0][0]);  // sort scratch, free until the sort
+    constexpr int CAND_CAP = (RPN_NT / 32) * 256 * 4 / 8;                                    // 4096 composites
+    auto scan_hist = [&](int sh, unsigned long long prefix, unsigned long long himask) {
+        if (tid < 256) s_hist[tid] = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < p.N; i0 += 4 * RPN_NT) {
+            uint32_t kk[4];
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(HD_FULL, c, d);
-        if (lane == 0 && c) atomicAdd(&s_valid, c);
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * RPN_NT + tid; kk[u] = (i < p.N) ? keys[i] : 0u; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * RPN_NT + tid;
+                int dg = 256 + lane;
+                if (kk[u] != 0u) {
+                    const unsigned long long comp = rpn_composite(kk[u], i);
+                    if (((comp ^ prefix) & himask) == 0ull) dg = (int)((comp >> sh) & 255);
+                }
+                const unsigned peers = __match_any_sync(HD_FULL, dg);
+                if (dg < 256 && (peers & hd_lanemask_lt()) == 0u) atomicAdd(&s_hist[dg], __popc(peers));
+            }
+        }
+        __syncthreads();
+    };
+    auto pick_digit = [&](int sh) {  // thread 0: digit holding the s_need-th largest, walking from the top
+        if (tid == 0) {
+            int need = s_need, d = 255;
+            for (; d > 0; --d) {
+                if (s_hist[d] >= need) break;
+                need -= s_hist[d];
+            }
+            s_need = need;
+            s_prefix |= ((unsigned long long)d << sh);
+        }
+        __syncthreads();
+    };
+    if (tid == 0) { s_count = 0; s_prefix = 0ull; }
+    scan_hist(56, 0ull, 0ull);  // byte 7 over every valid key: also yields the number of valid proposals
+    if (tid == 0) {
+        int v = 0;
+        for (int d = 0; d < 256; ++d) v += s_hist[d];
+        s_valid = v;
     }
     __syncthreads();
     const int k = (p.n_pre > 0) ? min(p.n_pre, s_valid) : s_valid;
@@ -143,46 +178,61 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
         if (tid == 0) p.out_count[b] = 0;
         return;
     }
-    // ---- radix select of the k-th largest composite
     uint64_t T = 0;
     if (k < s_valid) {
-        if (tid == 0) { s_prefix = 0ull; s_need = k; }
+        if (tid == 0) s_need = k;
         __syncthreads();
-        for (int byte = 7; byte >= 0; --byte) {
-            if (byte == 3) continue;  // index < 2^24: top byte of ~index is 0xff for every element
+        pick_digit(56);
+        scan_hist(48, s_prefix, ~0ull << 56);
+        pick_digit(48);
+        // candidates sharing the 16-bit prefix -> shared memory
+        if (tid == 0) s_cand = 0;
+        __syncthreads();
+        {
+            const unsigned long long prefix = s_prefix;
+            for (int i0 = 0; i0 < p.N; i0 += 4 * RPN_NT) {
+                uint32_t kk[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + u * RPN_NT + tid; kk[u] = (i < p.N) ? keys[i] : 0u; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * RPN_NT + tid;
+                    const unsigned long long comp = rpn_composite(kk[u], i);
+                    const bool hit = kk[u] != 0u && ((comp ^ prefix) >> 48) == 0ull;
+                    const unsigned m = __ballot_sync(HD_FULL, hit);
+                    if (m) {
+                        int basep = 0;
+                        if (lane == 0) basep = atomicAdd(&s_cand, __popc(m));
+                        basep = __shfl_sync(HD_FULL, basep, 0);
+                        const int slot = basep + __popc(m & hd_lanemask_lt());
+                        if (hit && slot < CAND_CAP) cand[slot] = comp;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int nc = s_cand;
+        for (int byte = 5; byte >= 0; --byte) {
+            if (byte == 3) continue;  // index < 2^24: byte 3 of ~index is 0xff for every element
             const int sh = byte * 8;
-            if (tid < 256) s_hist[tid] = 0;
-            __syncthreads();
-            const uint64_t prefix = s_prefix;
-            const uint64_t himask = (byte == 7) ? 0ull : (~0ull << (sh + 8));
-            for (int i0 = 0; i0 < p.N; i0 += RPN_NT) {
-                const int i = i0 + tid;
-                int dg = 256 + lane;
-                if (i < p.N) {
-                    const uint32_t key = keys[i];
-                    uint64_t comp = rpn_composite(key, i);
-                    if (byte <= 2) comp |= 0xff000000ull;  // skipped byte: treat as matching
-                    uint64_t pf = prefix;
-                    if (byte <= 2) pf |= 0xff000000ull;
-                    if (key != 0u && ((comp ^ pf) & himask) == 0ull) dg = (int)((comp >> sh) & 255);
+            const unsigned long long himask = ~0ull << (sh + 8);
+            const unsigned long long pf = s_prefix | (byte <= 2 ? 0xff000000ull : 0ull);
+            if (nc <= CAND_CAP) {
+                if (tid < 256) s_hist[tid] = 0;
+                __syncthreads();
+                for (int i = tid; i < nc; i += RPN_NT) {
+                    const unsigned long long comp = cand[i];
+                    if (((comp ^ pf) & himask) == 0ull) atomicAdd(&s_hist[(int)((comp >> sh) & 255)], 1);
                 }
-                const unsigned peers = __match_any_sync(HD_FULL, dg);
-                if (dg < 256 && (peers & hd_lanemask_lt()) == 0u) atomicAdd(&s_hist[dg], __popc(peers));
+                __syncthreads();
+            } else {
+                scan_hist(sh, pf, himask);  // pathological tie mass: keep scanning the full key array
             }
-            __syncthreads();
-            if (tid == 0) {
-                int need = s_need, d = 255;
-                for (; d > 0; --d) {
-                    if (s_hist[d] >= need) break;
-                    need -= s_hist[d];
-                }
-                s_need = need;
-                s_prefix = prefix | ((uint64_t)d << sh);
-            }
-            __syncthreads();
+            pick_digit(sh);
         }
         T = s_prefix | 0xff000000ull;
     }
+    __syncthreads();
     // ---- compaction of the selected set (unordered; the sort key carries the index)
     for (int i0 = 0; i0 < p.N; i0 += RPN_NT) {
         const int i = i0 + tid;

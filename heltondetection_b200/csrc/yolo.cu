@@ -223,18 +223,26 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const __grid_constant_
     const float* __restrict__ base = p.data[l] + ((size_t)(b * p.A + a) * p.no) * HW + cell;
     const float s = p.stride[l];
     const int gi = cell / W, gj = cell - gi * W;
-    for (int c = 0; c < p.no; ++c) {
-        float v = 0.f;
-        if (valid) {
-            float pr = hd_sigmoid(hd_ldg_stream(base + (size_t)c * HW));
-            if (c == 0) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(pr, 2.0f), 0.5f), (float)gj), s);
-            else if (c == 1) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(pr, 2.0f), 0.5f), (float)gi), s);
-            else if (c == 2 || c == 3) {
-                float q2 = __fmul_rn(pr, 2.0f);
-                v = __fmul_rn(__fmul_rn(q2, q2), p.anchor[l][2 * a + (c - 2)]);
-            } else v = pr;
+    for (int c0 = 0; c0 < p.no; c0 += 8) {  // eight independent plane loads in flight per lane
+        float raw[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) raw[u] = (valid && c0 + u < p.no) ? hd_ldg_stream(base + (size_t)(c0 + u) * HW) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u;
+            if (c >= p.no) break;
+            float v = 0.f;
+            if (valid) {
+                const float pr = hd_sigmoid(raw[u]);
+                if (c == 0) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(pr, 2.0f), 0.5f), (float)gj), s);
+                else if (c == 1) v = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(pr, 2.0f), 0.5f), (float)gi), s);
+                else if (c == 2 || c == 3) {
+                    const float q2 = __fmul_rn(pr, 2.0f);
+                    v = __fmul_rn(__fmul_rn(q2, q2), p.anchor[l][2 * a + (c - 2)]);
+                } else v = pr;
+            }
+            tile[c * 33 + lane] = v;
         }
-        tile[c * 33 + lane] = v;
     }
     __syncwarp();
     const int rows = min(32, HW - t * 32);
@@ -372,7 +380,7 @@ extern "C" HD_API int hd_yolo_decode(const hd_yolo_level* levels, int n_levels, 
     if (rc) return rc;
     if (B == 0) return HD_OK;
     HD_CHECK_ARG(pred != nullptr, "pred is NULL");
-    const int warps = 8;
+    const int warps = 4;
     size_t smem = (size_t)warps * p.no * 33 * sizeof(float);
     HD_CHECK_ARG(smem <= 200 * 1024, "nc=%d too large for the decode transpose tile", nc);
     static bool attr_set = false;
