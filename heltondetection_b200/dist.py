@@ -30,22 +30,50 @@ def unpack_records(rec, max_det):
 
 
 class DetectionGather:
-    """Preallocated all-gather of the padded detections of equally sized shards."""
+    """Preallocated all-gather of the padded detections of equally sized shards.
+
+    On CUDA the collective runs on a side stream with double-buffered records, so it overlaps the next batch's
+    kernels (the payload is ~1.8 MB per 256 images: latency bound, not bandwidth bound).  __call__ returns the
+    buffer slot; result(slot) makes the current stream wait for that gather; finish() joins the side stream."""
 
     def __init__(self, B, max_det, device, group=None):
         self.group, self.max_det = group, max_det
         self.world = dist.get_world_size(group)
-        self.rec = torch.empty((B, 1 + max_det * 6), dtype=torch.float32, device=device)
-        self.out = torch.empty((self.world * B, 1 + max_det * 6), dtype=torch.float32, device=device)
+        self.cuda = torch.device(device).type == "cuda"
+        nbuf = 2 if self.cuda else 1
+        self.rec = [torch.empty((B, 1 + max_det * 6), dtype=torch.float32, device=device) for _ in range(nbuf)]
+        self.out = [torch.empty((self.world * B, 1 + max_det * 6), dtype=torch.float32, device=device) for _ in range(nbuf)]
+        self.k = 0
+        if self.cuda:
+            self.side = torch.cuda.Stream(device)
+            self.ready = [torch.cuda.Event() for _ in range(nbuf)]
+            self.done = [torch.cuda.Event() for _ in range(nbuf)]
 
     def __call__(self, det, count):
-        pack_records(det, count, self.rec)
-        if dist.get_backend(self.group) == "nccl":
-            dist.all_gather_into_tensor(self.out, self.rec, group=self.group)
-        else:
-            chunks = list(self.out.chunk(self.world, 0))
-            dist.all_gather(chunks, self.rec, group=self.group)
-        return unpack_records(self.out, self.max_det)
+        if not self.cuda:
+            pack_records(det, count, self.rec[0])
+            chunks = list(self.out[0].chunk(self.world, 0))
+            dist.all_gather(chunks, self.rec[0], group=self.group)
+            return unpack_records(self.out[0], self.max_det)
+        i = self.k & 1
+        self.k += 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.done[i])          # slot i is free again (no-op the first two times)
+        pack_records(det, count, self.rec[i])
+        self.ready[i].record(cur)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ready[i])
+            dist.all_gather_into_tensor(self.out[i], self.rec[i], group=self.group)
+            self.done[i].record(self.side)
+        return i
+
+    def result(self, slot):
+        torch.cuda.current_stream().wait_event(self.done[slot])
+        return unpack_records(self.out[slot], self.max_det)
+
+    def finish(self):
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.side)
 
 
 def gather_ragged(det, count, n_images, group=None):
