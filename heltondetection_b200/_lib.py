@@ -40,6 +40,7 @@ _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_doub
 SIGNATURES = {
     "hd_version": (_i, []),
     "hd_last_error": (C.c_char_p, []),
+    "hd_debug_phases": (_i, [_i, C.POINTER(C.c_longlong)]),
     "hd_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _vp, _vp]),
     "hd_yolo_decode_filter": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "hd_yolo_postprocess_workspace_size": (_sz, [_i, _i]),

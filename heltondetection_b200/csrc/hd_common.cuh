@@ -49,6 +49,10 @@ static inline size_t hd_align_up(size_t x, size_t a) { return (x + a - 1) / a * 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 #define HD_FULL 0xffffffffu
+// phase clocks of block 0 of the per-image kernels (developer aid, read back with hd_debug_phases)
+static __device__ long long hd_dbg_phase[16];  // one copy per translation unit
+#define HD_DEFINE_PHASE_READER(fn) int fn(long long* out16) { HD_CUDA_CALL(cudaDeviceSynchronize()); HD_CUDA_CALL(cudaMemcpyFromSymbol(out16, hd_dbg_phase, sizeof(long long) * 16)); return HD_OK; }
+#define HD_PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) hd_dbg_phase[i] = clock64(); } while (0)
 
 // streaming 128-bit load: read-only path, do not allocate in L1 (each byte is touched once)
 __device__ __forceinline__ float4 hd_ldg_stream4(const float* p) {

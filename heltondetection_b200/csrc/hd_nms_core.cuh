@@ -25,8 +25,17 @@ __device__ __forceinline__ bool hd_iou_gt(const float4& a, float area_a, const f
     float w = hd_stdmax(0.0f, __fsub_rn(xx2, xx1));
     float h = hd_stdmax(0.0f, __fsub_rn(yy2, yy1));
     if (thr >= 0.0f && !(w > 0.0f && h > 0.0f)) return false;  // inter == 0 -> iou is 0, -0 or NaN: never > thr
-    float inter = __fmul_rn(w, h);
-    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter)) > thr;
+    const float inter = __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    // two-sided filter: when inter is not within 1e-5*union of thr*union the correctly rounded quotient cannot land on
+    // the other side of thr (its relative error is < 1e-6), so the division is only paid for the borderline pairs
+    const float d = __fsub_rn(inter, __fmul_rn(thr, uni));
+    const float tol = 1.0e-5f * uni;
+    if (uni > 0.0f && uni < 3.0e38f) {
+        if (d > tol) return true;
+        if (d < -tol) return false;
+    }
+    return __fdiv_rn(inter, uni) > thr;
 }
 
 // all threads of the CTA must call; blockDim.x == NT (a multiple of 64, <= 1024)
@@ -146,7 +155,7 @@ __device__ __forceinline__ uint32_t hd_cell_hash(int gx, int gy, int log2T) {
 
 template <int NT, typename KeepT>
 __device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n_use, int max_det, float thr, uint32_t* removed,
-                                      KeepT* keep_r, HdNmsSmem& sm, HdGridSmem& gs, int* bucket, int log2T, uint32_t* items) {
+                                      KeepT* keep_r, HdNmsSmem& sm, HdGridSmem& gs, int* bucket, int log2T, uint32_t* items, float2* icen) {
     constexpr int ROWT = NT / 64, COLS = 64 / ROWT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = 1 << log2T;
@@ -209,19 +218,67 @@ __device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n
         const float4 b = sbox[r];
         if (hd_box_proper(b)) {
             const uint32_t h = hd_cell_hash(hd_cell(0.5f * (b.x + b.z), invS), hd_cell(0.5f * (b.y + b.w), invS), log2T);
-            items[atomicAdd(&bucket[h], 1)] = (uint32_t)r;   // afterwards bucket[h] = end of h = start of h+1
+            const int pos = atomicAdd(&bucket[h], 1);        // afterwards bucket[h] = end of h = start of h+1
+            items[pos] = (uint32_t)r;
+            icen[pos] = make_float2(0.5f * (b.x + b.z), 0.5f * (b.y + b.w));  // centre next to the id: the pair pass streams these
         }
     }
     __syncthreads();
 
-    int kc = 0;
-    for (int base = 0; base < n_use; base += HD_NMS_CHUNK) {
-        const int m = min(HD_NMS_CHUNK, n_use - base);
+    HD_PHASE(8);   // grid built
+    // chunk_rank[s] = sorted rank of the s-th box of the current chunk: chunks are made of the next 64 boxes that
+    // are still ALIVE, so already-suppressed boxes never cost a chunk (dense scenes: ~10x fewer chunks)
+    int* chunk_rank = gs.qy1;          // reused after the gather (query rows are rebuilt every chunk)
+    __shared__ int s_next, s_m, s_rank[HD_NMS_CHUNK];
+    if (tid == 0) s_next = 0;
+    __syncthreads();
+    int kc = 0, nchunk = 0;
+    for (;;) {
+        // ---- warp 0 gathers the next (up to) 64 alive ranks starting at s_next
+        if (wid == 0) {
+            int m = 0, pos = s_next;
+            while (m < HD_NMS_CHUNK && pos < n_use) {
+                const int w = (pos >> 5) + lane;
+                uint32_t bits = 0u;
+                if (w * 32 < n_use) {
+                    bits = ~removed[w];
+                    if (w * 32 + 32 > n_use) bits &= (1u << (n_use - w * 32)) - 1u;
+                    if (lane == 0) bits &= ~0u << (pos & 31);
+                }
+                const int c = __popc(bits);
+                int incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
+                const int excl = incl - c, total = __shfl_sync(HD_FULL, incl, 31);
+                const int room = HD_NMS_CHUNK - m;
+                const int take = min(c, max(room - excl, 0));
+                uint32_t bb = bits;
+                int last = -1;
+                for (int t = 0; t < take; ++t) { const int bp = __ffs(bb) - 1; bb &= bb - 1u; last = w * 32 + bp; s_rank[m + excl + t] = last; }
+                if (total >= room) {
+                    // the lane that placed the room-th box knows where the next gather starts
+                    const unsigned holder = __ballot_sync(HD_FULL, take > 0 && excl + take == room);
+                    const int src = __ffs(holder) - 1;
+                    pos = __shfl_sync(HD_FULL, last, src) + 1;
+                    m = HD_NMS_CHUNK;
+                } else {
+                    m += total;
+                    pos = ((pos >> 5) + 32) << 5;
+                }
+            }
+            if (lane == 0) { s_m = m; s_next = min(pos, n_use); }
+        }
+        __syncthreads();
+        const int m = s_m;
+        if (m == 0) break;
+        if (nchunk++ == 16) HD_PHASE(9);
+        const int last_rank = s_rank[m - 1];
         if (tid < HD_NMS_CHUNK) {
-            sm.cmask[tid] = 0ull;   // used as the column mask: bit i of cmask[j] <=> box i (i<j) suppresses box j
+            sm.cmask[tid] = 0ull;   // column mask: bit i of cmask[j] <=> box i (i<j) suppresses box j
             if (tid < m) {
-                const float4 bx = sbox[base + tid];
-                sm.cbox[tid] = bx; sm.carea[tid] = hd_area(bx); sm.ccls[tid] = scls ? scls[base + tid] : 0;
+                const int r = s_rank[tid];
+                const float4 bx = sbox[r];
+                sm.cbox[tid] = bx; sm.carea[tid] = hd_area(bx); sm.ccls[tid] = scls ? scls[r] : 0;
             }
         }
         __syncthreads();
@@ -240,8 +297,7 @@ __device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n
         }
         __syncthreads();
         if (wid == 0) {
-            const unsigned long long rem = (unsigned long long)removed[base >> 5] | ((unsigned long long)removed[(base >> 5) + 1] << 32);
-            const unsigned long long alive = ~rem & ((m == 64) ? ~0ull : ((1ull << m) - 1ull));
+            const unsigned long long alive = (m == 64) ? ~0ull : ((1ull << m) - 1ull);
             const unsigned long long c0 = sm.cmask[lane], c1 = sm.cmask[lane + 32];
             unsigned long long kept = alive;
             for (int it = 0; it < 64; ++it) {
@@ -253,25 +309,23 @@ __device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n
             }
             const int room = max_det - kc;
             while (__popcll(kept) > room) kept &= ~(1ull << (63 - __clzll((long long)kept)));
-            // query ranges of the kept boxes
             int ncell[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int bit = lane + 32 * h;
                 ncell[h] = 0;
                 if ((kept >> bit) & 1ull) {
-                    keep_r[kc + __popcll(kept & ((1ull << bit) - 1ull))] = (KeepT)(base + bit);
+                    keep_r[kc + __popcll(kept & ((1ull << bit) - 1ull))] = (KeepT)s_rank[bit];
                     const float4 b = sm.cbox[bit];
                     if (hd_box_proper(b)) {
                         const int x1 = hd_cell(b.x - qdx, invS), x2 = hd_cell(b.z + qdx, invS);
                         const int y1 = hd_cell(b.y - qdy, invS), y2 = hd_cell(b.w + qdy, invS);
                         const long long nx = (long long)x2 - x1 + 1, ny = (long long)y2 - y1 + 1;
                         if (nx * ny >= (long long)T) { gs.qnx[bit] = 0; ncell[h] = T; }      // huge box: walk every bucket
-                        else { gs.qx1[bit] = x1; gs.qy1[bit] = y1; gs.qnx[bit] = (int)nx; ncell[h] = (int)(nx * ny); }
+                        else { gs.qx1[bit] = x1; chunk_rank[bit] = y1; gs.qnx[bit] = (int)nx; ncell[h] = (int)(nx * ny); }
                     }
                 }
             }
-            // exclusive prefix over the 64 slots (slot = chunk position)
             int i0 = ncell[0], i1 = ncell[1];
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -289,31 +343,35 @@ __device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n
         kc = sm.s_kc;
         const bool done = kc >= max_det;
         const int total = gs.qpref[64];
-        if (!done && kept && base + HD_NMS_CHUNK < n_use) {
+        if (!done && kept && last_rank + 1 < n_use) {
+            int i = 0;   // slot of the current pair: t grows monotonically per thread, so the slot pointer only moves forward
             for (int t = tid; t < total; t += NT) {
-                // slot i with qpref[i] <= t < qpref[i+1]
-                int lo = 0, hi = 64;
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (gs.qpref[mid] <= t) lo = mid; else hi = mid; }
-                const int i = lo, local = t - gs.qpref[i];
+                while (gs.qpref[i + 1] <= t) ++i;
+                const int local = t - gs.qpref[i];
                 uint32_t hb;
                 if (gs.qnx[i] == 0) hb = (uint32_t)local;
-                else { const int nx = gs.qnx[i]; const int gy = local / nx; hb = hd_cell_hash(gs.qx1[i] + (local - gy * nx), gs.qy1[i] + gy, log2T); }
+                else { const int nx = gs.qnx[i]; const int gy = local / nx; hb = hd_cell_hash(gs.qx1[i] + (local - gy * nx), chunk_rank[i] + gy, log2T); }
                 const int s0 = hb ? bucket[hb - 1] : 0, s1 = bucket[hb];
                 if (s1 <= s0) continue;
                 const float4 bi = sm.cbox[i];
                 const float ai = sm.carea[i];
                 const int ci = sm.ccls[i];
                 const float lx = bi.x - qdx, hx = bi.z + qdx, ly = bi.y - qdy, hy = bi.w + qdy;
-                for (int k = s0; k < s1; ++k) {
+                auto test = [&](int k, const float2 c) {
+                    if (c.x < lx || c.x > hx || c.y < ly || c.y > hy) return;   // also rejects hash collisions
                     const int jr = (int)items[k];
-                    if (jr < base + HD_NMS_CHUNK) continue;
-                    if ((removed[jr >> 5] >> (jr & 31)) & 1u) continue;
+                    if (jr <= last_rank) return;      // earlier boxes, or members of this chunk (handled by the mask)
+                    if ((removed[jr >> 5] >> (jr & 31)) & 1u) return;
+                    if ((scls ? scls[jr] : 0) != ci) return;
                     const float4 bj = sbox[jr];
-                    const float cx = 0.5f * (bj.x + bj.z), cy = 0.5f * (bj.y + bj.w);
-                    if (cx < lx || cx > hx || cy < ly || cy > hy) continue;
-                    if ((scls ? scls[jr] : 0) != ci) continue;
                     if (hd_iou_gt(bi, ai, bj, hd_area(bj), thr)) atomicOr(&removed[jr >> 5], 1u << (jr & 31));
+                };
+                int k = s0;
+                for (; k + 4 <= s1; k += 4) {   // centres are contiguous per bucket: four independent loads in flight
+                    const float2 c0 = icen[k], c1 = icen[k + 1], c2 = icen[k + 2], c3 = icen[k + 3];
+                    test(k, c0); test(k + 1, c1); test(k + 2, c2); test(k + 3, c3);
                 }
+                for (; k < s1; ++k) test(k, icen[k]);
             }
         }
         __syncthreads();

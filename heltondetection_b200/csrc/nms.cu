@@ -53,13 +53,16 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     int* scls = p.scls + off;
     int* keep_r = p.keep_r + off;
 
+    HD_PHASE(0);
     for (int i = tid; i < n; i += NMS_NT) {
         uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + i] : (uint32_t)i;
         k0[i] = ((uint64_t)(~hd_orderable(p.scores[off + i])) << 32) | tb;
         v0[i] = (uint32_t)i;
     }
     __syncthreads();
+    HD_PHASE(2);
     const int res = hd_cta_radix_sort<NMS_NT>(k0, v0, k1, v1, n, ssm);
+    HD_PHASE(3);
     const uint32_t* order = res ? v1 : v0;
 
     const int n_use = (p.max_nms > 0) ? min(n, p.max_nms) : n;
@@ -77,15 +80,17 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     }
     __syncthreads();
     const int* clsp = (p.class_mode == HD_NMS_CLASS_EXACT) ? scls : nullptr;
+    HD_PHASE(4);
     int kc;
     if (n_use > HD_GRID_MIN_N && p.thr > 0.05f) {
         // big segment: spatially pruned pass; buckets alias the (finished) sort scratch, items use the free key buffer
         kc = hd_cta_greedy_nms_grid<NMS_NT, int>(sbox, clsp, n_use, max_det, p.thr, removed, keep_r, nsm, gsm, &ssm.warp_cnt[0][0], 12,
-                                                 (uint32_t*)(res ? k0 : k1));
+                                                 (uint32_t*)(res ? v0 : v1), (float2*)(res ? k0 : k1));
     } else {
         kc = hd_cta_greedy_nms<NMS_NT, int>(sbox, clsp, n_use, max_det, p.thr, removed, keep_r, nsm);
     }
 
+    HD_PHASE(5);
     for (int q = tid; q < kc; q += NMS_NT) {
         const int r = keep_r[q];
         const uint32_t slot = order[r];
@@ -242,3 +247,5 @@ extern "C" HD_API int hd_box_iou(const float* boxes1, int64_t N, const float* bo
     HD_CUDA_LAUNCH_CHECK("box_iou_kernel");
     return HD_OK;
 }
+
+HD_DEFINE_PHASE_READER(hd_phase_reader_nms)

@@ -199,11 +199,15 @@ template <int E>
 __device__ __forceinline__ void roi_align_bins_quad(const float* __restrict__ f, int q, int g, int groups, const AxisEntry* ytab,
                                                     const AxisEntry* xtab, int PH, int PW, float count, float* tile, int rot) {
     const int nb = PH * PW;
+    const unsigned magic = 0xffffffffu / (unsigned)PW + 1u;            // bin / PW == umulhi(bin, magic) for bin < 2^16
+    const int icount = (int)count;
+    const bool pow2 = (icount & (icount - 1)) == 0;                   // x / 2^k == x * 2^-k exactly
+    const float inv = 1.0f / count;
     for (int bin = g; bin < nb; bin += groups) {
-        const int ph = bin / PW, pw = bin - ph * PW;
+        const int ph = (int)__umulhi((unsigned)bin, magic), pw = bin - ph * PW;
         int xo[E]; float wx[E];
 #pragma unroll
-        for (int b = 0; b < E; ++b) { xo[b] = xtab[pw * E + b].off; wx[b] = xtab[pw * E + b].w; }
+        for (int b = 0; b < E; ++b) { xo[b] = xtab[pw * E + b].off >> 2; wx[b] = xtab[pw * E + b].w; }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int a = 0; a < E; ++a) {
@@ -211,30 +215,29 @@ __device__ __forceinline__ void roi_align_bins_quad(const float* __restrict__ f,
             const float wy = ytab[ph * E + a].w;
             if (wy == 0.0f) continue;  // padding (warp-uniform)
             const float4* __restrict__ row = reinterpret_cast<const float4*>(f + yo) + q;
-            float4 v[E];
+            float4 v[E];   // padded entries re-read a real cell with weight 0: costs L1 bandwidth (not the limiter), no instructions
 #pragma unroll
-            for (int b = 0; b < E; ++b) v[b] = (wx[b] != 0.0f) ? __ldg(row + (xo[b] >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int b = 0; b < E; ++b) v[b] = __ldg(row + xo[b]);
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int b = 0; b < E; ++b) { r.x = fmaf(wx[b], v[b].x, r.x); r.y = fmaf(wx[b], v[b].y, r.y); r.z = fmaf(wx[b], v[b].z, r.z); r.w = fmaf(wx[b], v[b].w, r.w); }
             acc.x = fmaf(wy, r.x, acc.x); acc.y = fmaf(wy, r.y, acc.y); acc.z = fmaf(wy, r.z, acc.z); acc.w = fmaf(wy, r.w, acc.w);
         }
-        acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count); acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+        if (pow2) { acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
+        else { acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count); acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count); }
+        // lane-rotated store order (rot = lane/8): at every step the 32 lanes hit 32 different banks
         float* t = tile + (size_t)(4 * q) * nb + bin;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const int k = (s + rot) & 3;
-            const float val = (k == 0) ? acc.x : (k == 1) ? acc.y : (k == 2) ? acc.z : acc.w;
-            t[k * nb] = val;
-        }
+        const float a0 = (rot & 1) ? acc.y : acc.x, a1 = (rot & 1) ? acc.z : acc.y, a2 = (rot & 1) ? acc.w : acc.z, a3 = (rot & 1) ? acc.x : acc.w;
+        const float b0 = (rot & 2) ? a2 : a0, b1 = (rot & 2) ? a3 : a1, b2 = (rot & 2) ? a0 : a2, b3 = (rot & 2) ? a1 : a3;  // b_s = acc[(s+rot)&3]
+        t[((0 + rot) & 3) * nb] = b0; t[((1 + rot) & 3) * nb] = b1; t[((2 + rot) & 3) * nb] = b2; t[((3 + rot) & 3) * nb] = b3;
     }
 }
 
-__global__ void __launch_bounds__(256) roi_align_nhwc_quad_kernel(const __grid_constant__ RoiParams p, int use_tma, int QT) {
+__global__ void __launch_bounds__(256) roi_align_nhwc_quad_kernel(const __grid_constant__ RoiParams p, int use_tma, int QT, int tab) {
     extern __shared__ __align__(128) float smem_f[];
     float* tile = smem_f;                                  // [C][PH*PW]
     AxisEntry* ytab = (AxisEntry*)(tile + (size_t)p.C * p.PH * p.PW);
-    AxisEntry* xtab = ytab + ROI_TAB;
+    AxisEntry* xtab = ytab + tab;                           // tab entries per axis (host: small when sampling_ratio is fixed)
     __shared__ int ycnt[64], xcnt[64];
 
     const long long k = blockIdx.x;
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(256) roi_align_nhwc_quad_kernel(const __grid_c
     const int E = need <= 4 ? 4 : (need <= 8 ? 8 : (need <= 16 ? 16 : 0));
     const int nb = p.PH * p.PW;
     const float* __restrict__ f = p.data[lvl] + (size_t)bidx * H * W * p.C;
-    if (E && E * p.PH <= ROI_TAB && E * p.PW <= ROI_TAB) {
+    if (E && E * p.PH <= tab && E * p.PW <= tab) {
         if (threadIdx.x < p.PH) build_axis(ytab, ycnt, threadIdx.x, E, sh, bh, gh, H, W * p.C, E);
         else if (threadIdx.x >= 64 && threadIdx.x < 64 + p.PW) build_axis(xtab, xcnt, threadIdx.x - 64, E, sw, bw, gw, W, p.C, E);
         __syncthreads();
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(256) roi_align_nhwc_quad_kernel(const __grid_c
             else if (E == 8) roi_align_bins_quad<8>(f, q, g, groups, ytab, xtab, p.PH, p.PW, count, tile, rot);
             else roi_align_bins_quad<16>(f, q, g, groups, ytab, xtab, p.PH, p.PW, count, tile, rot);
         }
-    } else if ((long long)2 * max(gh, 1) * p.PH <= ROI_TAB && (long long)2 * max(gw, 1) * p.PW <= ROI_TAB) {
+    } else if ((long long)2 * max(gh, 1) * p.PH <= tab && (long long)2 * max(gw, 1) * p.PW <= tab) {
         // large adaptive grids: merged tables with run-time entry counts (<= bin size + 1 cells per axis)
         const int stride_y = 2 * max(gh, 1), stride_x = 2 * max(gw, 1);
         if (threadIdx.x < p.PH) build_axis(ytab, ycnt, threadIdx.x, stride_y, sh, bh, gh, H, W * p.C, 0);
@@ -594,7 +597,12 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
     HD_CHECK_ARG(p.rois && p.out, "rois/out is NULL");
     if (layout == HD_LAYOUT_NHWC) {
         size_t tile = (size_t)p.C * p.PH * p.PW * 4;
-        size_t smem = tile + (pool ? 0 : 2 * ROI_TAB * sizeof(AxisEntry));
+        // fixed sampling_ratio <= 8: at most 16 entries per bin -> small tables leave more of the SM's 228 KB to L1
+        int mx = p.PH > p.PW ? p.PH : p.PW;
+        int tab = (!pool && p.sampling_ratio > 0 && p.sampling_ratio <= 8) ? 16 * mx : ROI_TAB;
+        if (tab > ROI_TAB) tab = ROI_TAB;
+        size_t smem = tile + (pool ? 0 : 2 * (size_t)ROI_TAB * sizeof(AxisEntry));
+        size_t smem_quad = tile + 2 * (size_t)tab * sizeof(AxisEntry);
         HD_CHECK_ARG(smem <= 220 * 1024, "C*PH*PW=%d floats exceed the shared-memory tile", p.C * p.PH * p.PW);
         HD_CHECK_ARG(p.K < (1ll << 31), "too many RoIs");
         int use_tma = (tile % 16 == 0) && (((uintptr_t)p.out & 15) == 0);
@@ -614,7 +622,7 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
         while (QT < nq && QT < 256) QT <<= 1;
         if (pool && quad) roi_pool_nhwc_quad_kernel<<<(unsigned)p.K, 256, smem, st>>>(p, use_tma, QT);
         else if (pool) roi_pool_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
-        else if (quad) roi_align_nhwc_quad_kernel<<<(unsigned)p.K, 256, smem, st>>>(p, use_tma, QT);
+        else if (quad) roi_align_nhwc_quad_kernel<<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
         else roi_align_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
         HD_CUDA_LAUNCH_CHECK("roi_nhwc_kernel");
     } else if (layout == HD_LAYOUT_NCHW) {

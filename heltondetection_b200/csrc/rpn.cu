@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
         }
         __syncthreads();
     };
+    HD_PHASE(0);
     if (tid == 0) { s_count = 0; s_prefix = 0ull; }
     scan_hist(56, 0ull, 0ull);  // byte 7 over every valid key: also yields the number of valid proposals
     if (tid == 0) {
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
         T = s_prefix | 0xff000000ull;
     }
     __syncthreads();
+    HD_PHASE(1);
     // ---- compaction of the selected set (unordered; the sort key carries the index)
     for (int i0 = 0; i0 < p.N; i0 += RPN_NT) {
         const int i = i0 + tid;
@@ -258,17 +260,21 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     }
     __syncthreads();
     const int n = min(s_count, p.cap);
+    HD_PHASE(2);
     const int res = hd_cta_radix_sort<RPN_NT>(k0, v0, k1, v1, n, ssm);
+    HD_PHASE(3);
     const uint32_t* order = res ? v1 : v0;
     const float4* __restrict__ boxes = p.boxes + (size_t)b * p.N;
     for (int r = tid; r < n; r += RPN_NT) sbox[r] = boxes[order[r]];
     __syncthreads();
+    HD_PHASE(4);
     int kc;
     if (n > HD_GRID_MIN_N && p.thr > 0.05f)
         kc = hd_cta_greedy_nms_grid<RPN_NT, int>(sbox, nullptr, n, p.n_post, p.thr, removed, keep_r, nsm, gsm, &ssm.warp_cnt[0][0], 12,
-                                                 (uint32_t*)(res ? k0 : k1));
+                                                 (uint32_t*)(res ? v0 : v1), (float2*)(res ? k0 : k1));
     else
         kc = hd_cta_greedy_nms<RPN_NT, int>(sbox, nullptr, n, p.n_post, p.thr, removed, keep_r, nsm);
+    HD_PHASE(5);
     for (int q = tid; q < p.n_post; q += RPN_NT) {
         float* o = p.out_rois + ((size_t)b * p.n_post + q) * 5;
         o[0] = (float)b;
@@ -285,6 +291,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
         }
     }
     if (tid == 0) p.out_count[b] = kc;
+    HD_PHASE(6);
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -409,3 +416,5 @@ extern "C" HD_API int hd_rpn_proposals(const hd_rpn_level* levels, int n_levels,
     return hd_rpn_select_nms(boxes, scores, keys, B, N, n_pre, n_post, nms_iou, out_rois, out_scores, out_idx, out_count, (void*)w,
                              (size_t)((uintptr_t)workspace + workspace_bytes - w), stream);
 }
+
+HD_DEFINE_PHASE_READER(hd_phase_reader_rpn)

@@ -54,6 +54,9 @@ extern "C" {
 #define HD_NMS_CLASS_OFFSET 2 /* nms(boxes + cls*offset_scale), fp32 add (= ultralytics max_wh trick) */
 
 HD_API int hd_version(void);
+/* developer aid: SM clock stamps of the phases of block 0 of the last sort_nms_kernel (which=0) or
+ * rpn_select_nms_kernel (which=1); host array of 16; synchronises the device */
+HD_API int hd_debug_phases(int which, long long* out16 /*host*/);
 HD_API const char* hd_last_error(void);
 
 /* ---------------------------------------------------------------------------------------------
