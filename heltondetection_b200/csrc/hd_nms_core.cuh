@@ -8,6 +8,9 @@
 #include "hd_common.cuh"
 
 #define HD_NMS_CHUNK 64
+#ifndef HD_GRID_CELL
+#define HD_GRID_CELL 0.5f
+#endif
 #define HD_GRID_MIN_N 768  // segments larger than this take the grid-pruned pass
 
 struct HdNmsSmem {
@@ -140,6 +143,7 @@ __device__ int hd_cta_greedy_nms(const float4* sbox, const int* scls, int n_use,
 // ------------------------------------------------------------------------------------------------------------
 struct HdGridSmem {
     int qx1[HD_NMS_CHUNK], qy1[HD_NMS_CHUNK], qnx[HD_NMS_CHUNK], qpref[HD_NMS_CHUNK + 1];
+    unsigned qmagic[HD_NMS_CHUNK];  // umulhi(local, qmagic) == local / qnx
     float red[32][6];
     float invS, dx, dy;
     int log2T;
@@ -155,7 +159,7 @@ __device__ __forceinline__ uint32_t hd_cell_hash(int gx, int gy, int log2T) {
 
 template <int NT, typename KeepT>
 __device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n_use, int max_det, float thr, uint32_t* removed,
-                                      KeepT* keep_r, HdNmsSmem& sm, HdGridSmem& gs, int* bucket, int log2T, uint32_t* items, float2* icen) {
+                                      KeepT* keep_r, HdNmsSmem& sm, HdGridSmem& gs, int* bucket, int log2T, float4* gitem) {
     constexpr int ROWT = NT / 64, COLS = 64 / ROWT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = 1 << log2T;
@@ -183,7 +187,7 @@ __device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n
     if (tid == 0) {
         float c = 0.f, sa = 0.f, wm = 0.f, hm = 0.f, cm = 0.f;
         for (int w = 0; w < NT / 32; ++w) { c += gs.red[w][0]; sa += gs.red[w][1]; wm = fmaxf(wm, gs.red[w][2]); hm = fmaxf(hm, gs.red[w][3]); cm = fmaxf(cm, gs.red[w][4]); }
-        float S = (c > 0.f) ? 0.5f * sa / c : 1.0f;       // half the mean box side
+        float S = (c > 0.f) ? HD_GRID_CELL * sa / c : 1.0f;   // cell = HD_GRID_CELL x mean box side
         if (!(S > 0.f) || !(S < 3.0e38f)) S = 1.0f;
         const float f = fmaxf(0.0f, 0.5f - (thr - 1.0e-3f));
         gs.invS = 1.0f / S;
@@ -219,8 +223,8 @@ __device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n
         if (hd_box_proper(b)) {
             const uint32_t h = hd_cell_hash(hd_cell(0.5f * (b.x + b.z), invS), hd_cell(0.5f * (b.y + b.w), invS), log2T);
             const int pos = atomicAdd(&bucket[h], 1);        // afterwards bucket[h] = end of h = start of h+1
-            items[pos] = (uint32_t)r;
-            icen[pos] = make_float2(0.5f * (b.x + b.z), 0.5f * (b.y + b.w));  // centre next to the id: the pair pass streams these
+            // {centre x, centre y, area, rank}: the pair pass streams these 16-byte records bucket by bucket
+            gitem[pos] = make_float4(0.5f * (b.x + b.z), 0.5f * (b.y + b.w), hd_area(b), __int_as_float(r));
         }
     }
     __syncthreads();
@@ -322,7 +326,7 @@ __device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n
                         const int y1 = hd_cell(b.y - qdy, invS), y2 = hd_cell(b.w + qdy, invS);
                         const long long nx = (long long)x2 - x1 + 1, ny = (long long)y2 - y1 + 1;
                         if (nx * ny >= (long long)T) { gs.qnx[bit] = 0; ncell[h] = T; }      // huge box: walk every bucket
-                        else { gs.qx1[bit] = x1; chunk_rank[bit] = y1; gs.qnx[bit] = (int)nx; ncell[h] = (int)(nx * ny); }
+                        else { gs.qx1[bit] = x1; chunk_rank[bit] = y1; gs.qnx[bit] = (int)nx; gs.qmagic[bit] = (nx > 1) ? 0xffffffffu / (unsigned)nx + 1u : 0u; /* nx == 1: local / nx == local */ ncell[h] = (int)(nx * ny); }
                     }
                 }
             }
@@ -350,28 +354,31 @@ __device__ int hd_cta_greedy_nms_grid(const float4* sbox, const int* scls, int n
                 const int local = t - gs.qpref[i];
                 uint32_t hb;
                 if (gs.qnx[i] == 0) hb = (uint32_t)local;
-                else { const int nx = gs.qnx[i]; const int gy = local / nx; hb = hd_cell_hash(gs.qx1[i] + (local - gy * nx), chunk_rank[i] + gy, log2T); }
+                else { const int nx = gs.qnx[i]; const int gy = (nx > 1) ? (int)__umulhi((unsigned)local, gs.qmagic[i]) : local; hb = hd_cell_hash(gs.qx1[i] + (local - gy * nx), chunk_rank[i] + gy, log2T); }
                 const int s0 = hb ? bucket[hb - 1] : 0, s1 = bucket[hb];
                 if (s1 <= s0) continue;
                 const float4 bi = sm.cbox[i];
                 const float ai = sm.carea[i];
                 const int ci = sm.ccls[i];
                 const float lx = bi.x - qdx, hx = bi.z + qdx, ly = bi.y - qdy, hy = bi.w + qdy;
-                auto test = [&](int k, const float2 c) {
-                    if (c.x < lx || c.x > hx || c.y < ly || c.y > hy) return;   // also rejects hash collisions
-                    const int jr = (int)items[k];
+                const float tq = thr - 1.0e-3f;          // iou <= min(area)/max(area): size-mismatched pairs cannot pass
+                const float amin = tq * ai, amax = (tq > 0.0f) ? ai / tq : 3.0e38f;
+                auto test = [&](const float4 it) {
+                    if (it.x < lx || it.x > hx || it.y < ly || it.y > hy) return;   // centre outside (also rejects hash collisions)
+                    if (it.z < amin || it.z > amax) return;
+                    const int jr = __float_as_int(it.w);
                     if (jr <= last_rank) return;      // earlier boxes, or members of this chunk (handled by the mask)
                     if ((removed[jr >> 5] >> (jr & 31)) & 1u) return;
                     if ((scls ? scls[jr] : 0) != ci) return;
                     const float4 bj = sbox[jr];
-                    if (hd_iou_gt(bi, ai, bj, hd_area(bj), thr)) atomicOr(&removed[jr >> 5], 1u << (jr & 31));
+                    if (hd_iou_gt(bi, ai, bj, it.z, thr)) atomicOr(&removed[jr >> 5], 1u << (jr & 31));
                 };
                 int k = s0;
-                for (; k + 4 <= s1; k += 4) {   // centres are contiguous per bucket: four independent loads in flight
-                    const float2 c0 = icen[k], c1 = icen[k + 1], c2 = icen[k + 2], c3 = icen[k + 3];
-                    test(k, c0); test(k + 1, c1); test(k + 2, c2); test(k + 3, c3);
+                for (; k + 4 <= s1; k += 4) {   // records are contiguous per bucket: four independent 16-byte loads in flight
+                    const float4 c0 = gitem[k], c1 = gitem[k + 1], c2 = gitem[k + 2], c3 = gitem[k + 3];
+                    test(c0); test(c1); test(c2); test(c3);
                 }
-                for (; k < s1; ++k) test(k, icen[k]);
+                for (; k < s1; ++k) test(gitem[k]);
             }
         }
         __syncthreads();

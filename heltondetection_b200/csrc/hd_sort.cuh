@@ -16,16 +16,16 @@ struct HdSortSmem {
 };
 
 // returns 0 if the sorted data ended in (k0,v0), 1 if in (k1,v1)
-template <int NT>
-__device__ int hd_cta_radix_sort(uint64_t* k0, uint32_t* v0, uint64_t* k1, uint32_t* v1, int n, HdSortSmem<NT>& sm,
-                                 int first_byte = 0, int last_byte = 7) {
+template <int NT, typename KeyT = uint64_t>
+__device__ int hd_cta_radix_sort(KeyT* k0, uint32_t* v0, KeyT* k1, uint32_t* v1, int n, HdSortSmem<NT>& sm,
+                                 int first_byte = 0, int last_byte = (int)sizeof(KeyT) - 1) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int i = tid; i < (NT / 32) * 256; i += NT) (&sm.warp_cnt[0][0])[i] = 0;
     int cur = 0;
     for (int byte = first_byte; byte <= last_byte; ++byte) {
-        uint64_t* kin = cur ? k1 : k0;
+        KeyT* kin = cur ? k1 : k0;
         uint32_t* vin = cur ? v1 : v0;
-        uint64_t* kout = cur ? k0 : k1;
+        KeyT* kout = cur ? k0 : k1;
         uint32_t* vout = cur ? v0 : v1;
         const int sh = byte * 8;
         if (tid < 256) sm.hist[tid] = 0;
@@ -60,7 +60,7 @@ __device__ int hd_cta_radix_sort(uint64_t* k0, uint32_t* v0, uint64_t* k1, uint3
         for (int tb = 0; tb < n; tb += NT) {
             const int i = tb + tid;
             const bool act = i < n;
-            uint64_t key = 0;
+            KeyT key = 0;
             uint32_t val = 0;
             int dg = 256 + lane;  // unique sentinel for idle lanes
             if (act) {

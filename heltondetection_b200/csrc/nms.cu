@@ -29,11 +29,11 @@ struct NmsParams {
     int* out_count;
     // workspace (per image stride = cap)
     uint64_t* k0; uint64_t* k1; uint32_t* v0; uint32_t* v1;
-    float4* sbox; int* scls; int* keep_r;
+    float4* sbox; int* scls; int* keep_r; float4* gitem;
 };
 
 __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_constant__ NmsParams p) {
-    extern __shared__ uint32_t removed[];  // ceil(cap/32) words (+1 pad)
+    extern __shared__ uint32_t removed[];  // ceil(cap/32)+4 words, (+pad)
     __shared__ HdSortSmem<NMS_NT> ssm;
     __shared__ HdNmsSmem nsm;
     __shared__ HdGridSmem gsm;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     if (n_use > HD_GRID_MIN_N && p.thr > 0.05f) {
         // big segment: spatially pruned pass; buckets alias the (finished) sort scratch, items use the free key buffer
         kc = hd_cta_greedy_nms_grid<NMS_NT, int>(sbox, clsp, n_use, max_det, p.thr, removed, keep_r, nsm, gsm, &ssm.warp_cnt[0][0], 12,
-                                                 (uint32_t*)(res ? v0 : v1), (float2*)(res ? k0 : k1));
+                                                 p.gitem + off);
     } else {
         kc = hd_cta_greedy_nms<NMS_NT, int>(sbox, clsp, n_use, max_det, p.thr, removed, keep_r, nsm);
     }
@@ -154,11 +154,12 @@ static void nms_ws_layout(int B, int cap, size_t* offs, size_t* total) {
     offs[4] = o; o = hd_align_up(o + n * 16, 256);  // sbox
     offs[5] = o; o = hd_align_up(o + n * 4, 256);   // scls
     offs[6] = o; o = hd_align_up(o + n * 4, 256);   // keep_r
+    offs[7] = o; o = hd_align_up(o + n * 16, 256);  // grid records
     *total = o;
 }
 
 extern "C" HD_API size_t hd_sort_nms_workspace_size(int B, int cap) {
-    size_t offs[7], total;
+    size_t offs[8], total;
     nms_ws_layout(B < 0 ? 0 : B, cap < 0 ? 0 : cap, offs, &total);
     return total + 256;
 }
@@ -194,7 +195,7 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
     }
     HD_CHECK_ARG(boxes && scores, "boxes/scores is NULL");
     HD_CHECK_ARG(max_det > 0, "max_det must be > 0 (row stride of out_det/out_idx), got %d", max_det);
-    size_t offs[7], total;
+    size_t offs[8], total;
     nms_ws_layout(B, cap, offs, &total);
     uintptr_t w0 = hd_align_up((uintptr_t)workspace, 256);
     if (!workspace || w0 + total > (uintptr_t)workspace + workspace_bytes)
@@ -207,13 +208,14 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
     p.out_det = out_det; p.out_idx = (long long*)out_idx; p.out_count = out_count;
     p.k0 = (uint64_t*)(w0 + offs[0]); p.k1 = (uint64_t*)(w0 + offs[1]);
     p.v0 = (uint32_t*)(w0 + offs[2]); p.v1 = (uint32_t*)(w0 + offs[3]);
-    p.sbox = (float4*)(w0 + offs[4]); p.scls = (int*)(w0 + offs[5]); p.keep_r = (int*)(w0 + offs[6]);
-    size_t smem = ((size_t)(cap + 31) / 32 + 4) * 4;
-    HD_CHECK_ARG(smem <= 160 * 1024, "cap=%d too large for the shared-memory removed bitmap", cap);
+    p.sbox = (float4*)(w0 + offs[4]); p.scls = (int*)(w0 + offs[5]); p.keep_r = (int*)(w0 + offs[6]); p.gitem = (float4*)(w0 + offs[7]);
+    size_t words = ((size_t)(cap + 31) / 32 + 4 + 1) & ~(size_t)1;   // 8-byte aligned end
+    HD_CHECK_ARG(words * 4 <= 64 * 1024, "cap=%d too large for the shared-memory removed bitmap", cap);
+    size_t smem = words * 4;
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        HD_CUDA_CALL(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        smem_set = 160 * 1024;
+        HD_CUDA_CALL(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 186 * 1024));
+        smem_set = 186 * 1024;
     }
     if (min_n < 0 && (counts != nullptr || n_fixed <= HD_SMALL_N)) {
         // images with <= HD_SMALL_N candidates: shared-memory kernel; the radix-sort kernel below then only

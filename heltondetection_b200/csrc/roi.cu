@@ -233,7 +233,9 @@ __device__ __forceinline__ void roi_align_bins_quad(const float* __restrict__ f,
     }
 }
 
-__global__ void __launch_bounds__(256) roi_align_nhwc_quad_kernel(const __grid_constant__ RoiParams p, int use_tma, int QT, int tab) {
+// FIXED: sampling_ratio in 1..8 (small tables, 4 CTAs/SM); otherwise the adaptive variant (3 CTAs/SM, more registers)
+template <bool FIXED>
+__global__ void __launch_bounds__(256, FIXED ? 4 : 3) roi_align_nhwc_quad_kernel(const __grid_constant__ RoiParams p, int use_tma, int QT, int tab) {
     extern __shared__ __align__(128) float smem_f[];
     float* tile = smem_f;                                  // [C][PH*PW]
     AxisEntry* ytab = (AxisEntry*)(tile + (size_t)p.C * p.PH * p.PW);
@@ -610,7 +612,8 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
         if (!attr_set) {
             HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             HD_CUDA_CALL(cudaFuncSetAttribute(roi_pool_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             HD_CUDA_CALL(cudaFuncSetAttribute(roi_pool_nhwc_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             attr_set = true;
         }
@@ -622,7 +625,8 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
         while (QT < nq && QT < 256) QT <<= 1;
         if (pool && quad) roi_pool_nhwc_quad_kernel<<<(unsigned)p.K, 256, smem, st>>>(p, use_tma, QT);
         else if (pool) roi_pool_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
-        else if (quad) roi_align_nhwc_quad_kernel<<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+        else if (quad && tab < ROI_TAB) roi_align_nhwc_quad_kernel<true><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+        else if (quad) roi_align_nhwc_quad_kernel<false><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
         else roi_align_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
         HD_CUDA_LAUNCH_CHECK("roi_nhwc_kernel");
     } else if (layout == HD_LAYOUT_NCHW) {

@@ -98,7 +98,7 @@ struct RpnSelParams {
     long long* out_idx;  // [B, n_post] nullable
     int* out_count;
     int cap;           // per-image workspace stride (>= min(n_pre, N))
-    uint64_t* k0; uint64_t* k1; uint32_t* v0; uint32_t* v1; float4* sbox; int* keep_r;
+    uint64_t* k0; uint64_t* k1; uint32_t* v0; uint32_t* v1; float4* sbox; int* keep_r; float4* gitem;
 };
 
 __device__ __forceinline__ uint64_t rpn_composite(uint32_t key, int idx) { return ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)idx); }
@@ -141,8 +141,15 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
                     const unsigned long long comp = rpn_composite(kk[u], i);
                     if (((comp ^ prefix) & himask) == 0ull) dg = (int)((comp >> sh) & 255);
                 }
-                const unsigned peers = __match_any_sync(HD_FULL, dg);
-                if (dg < 256 && (peers & hd_lanemask_lt()) == 0u) atomicAdd(&s_hist[dg], __popc(peers));
+                // scores cluster in a few digits: lanes agreeing with the first active lane are counted with one
+                // ballot + one atomic, the rest add individually (cheaper than MATCH.ANY on every key)
+                const unsigned act = __ballot_sync(HD_FULL, dg < 256);
+                if (act) {
+                    const int d0 = __shfl_sync(HD_FULL, dg, __ffs(act) - 1);
+                    const unsigned same = __ballot_sync(HD_FULL, dg == d0);
+                    if (dg == d0) { if ((same & hd_lanemask_lt()) == 0u) atomicAdd(&s_hist[d0], __popc(same)); }
+                    else if (dg < 256) atomicAdd(&s_hist[dg], 1);
+                }
             }
         }
         __syncthreads();
@@ -235,33 +242,49 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     }
     __syncthreads();
     HD_PHASE(1);
-    // ---- compaction of the selected set (unordered; the sort key carries the index)
-    for (int i0 = 0; i0 < p.N; i0 += RPN_NT) {
-        const int i = i0 + tid;
-        bool sel = false;
-        uint32_t key = 0;
-        if (i < p.N) {
-            key = keys[i];
-            sel = key != 0u && rpn_composite(key, i) >= T;
+    // ---- ordered compaction of the selected set: index order is kept, so a STABLE sort on the 32-bit score key alone
+    // reproduces (score desc, index asc) -- half the radix passes of a 64-bit (score, index) key
+    uint32_t* kk0 = reinterpret_cast<uint32_t*>(k0);
+    uint32_t* kk1 = reinterpret_cast<uint32_t*>(k1);
+    __shared__ int s_wsum[RPN_NT / 32];
+    __shared__ int s_base;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < p.N; i0 += 4 * RPN_NT) {
+        const int ib = i0 + 4 * tid;            // four consecutive proposals per thread
+        uint32_t kk[4];
+        bool sel[4];
+        int c = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = ib + u;
+            kk[u] = (i < p.N) ? keys[i] : 0u;
+            sel[u] = kk[u] != 0u && rpn_composite(kk[u], i) >= T;
+            c += sel[u];
         }
-        const unsigned m = __ballot_sync(HD_FULL, sel);
-        if (m) {
-            int basep = 0;
-            if (lane == 0) basep = atomicAdd(&s_count, __popc(m));
-            basep = __shfl_sync(HD_FULL, basep, 0);
-            if (sel) {
-                const int slot = basep + __popc(m & hd_lanemask_lt());
-                if (slot < p.cap) {
-                    k0[slot] = ((uint64_t)(~key) << 32) | (uint32_t)i;
-                    v0[slot] = (uint32_t)i;
-                }
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
+        if (lane == 31) s_wsum[tid >> 5] = incl;
+        __syncthreads();
+        int pre = s_base + incl - c;
+        for (int w = 0; w < (tid >> 5); ++w) pre += s_wsum[w];
+        int tot = 0;
+        if (tid == RPN_NT - 1) tot = pre + c;   // last thread knows the new running total
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (sel[u]) {
+                if (pre < p.cap) { kk0[pre] = ~kk[u]; v0[pre] = (uint32_t)(ib + u); }
+                ++pre;
             }
         }
+        __syncthreads();
+        if (tid == RPN_NT - 1) s_base = tot;
+        __syncthreads();
     }
-    __syncthreads();
-    const int n = min(s_count, p.cap);
+    const int n = min(s_base, p.cap);
     HD_PHASE(2);
-    const int res = hd_cta_radix_sort<RPN_NT>(k0, v0, k1, v1, n, ssm);
+    const int res = hd_cta_radix_sort<RPN_NT, uint32_t>(kk0, v0, kk1, v1, n, ssm);
     HD_PHASE(3);
     const uint32_t* order = res ? v1 : v0;
     const float4* __restrict__ boxes = p.boxes + (size_t)b * p.N;
@@ -271,7 +294,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     int kc;
     if (n > HD_GRID_MIN_N && p.thr > 0.05f)
         kc = hd_cta_greedy_nms_grid<RPN_NT, int>(sbox, nullptr, n, p.n_post, p.thr, removed, keep_r, nsm, gsm, &ssm.warp_cnt[0][0], 12,
-                                                 (uint32_t*)(res ? v0 : v1), (float2*)(res ? k0 : k1));
+                                                 p.gitem + off);
     else
         kc = hd_cta_greedy_nms<RPN_NT, int>(sbox, nullptr, n, p.n_post, p.thr, removed, keep_r, nsm);
     HD_PHASE(5);
@@ -350,12 +373,13 @@ static void rpn_ws_layout(int B, int cap, size_t* offs, size_t* total) {
     offs[3] = o; o = hd_align_up(o + n * 4, 256);
     offs[4] = o; o = hd_align_up(o + n * 16, 256);
     offs[5] = o; o = hd_align_up(o + n * 4, 256);
+    offs[6] = o; o = hd_align_up(o + n * 16, 256);
     *total = o;
 }
 static int rpn_cap(int N, int n_pre) { return (n_pre > 0 && n_pre < N) ? n_pre : N; }
 
 extern "C" HD_API size_t hd_rpn_select_nms_workspace_size(int B, int N, int n_pre) {
-    size_t offs[6], total;
+    size_t offs[7], total;
     rpn_ws_layout(B < 0 ? 0 : B, rpn_cap(N < 0 ? 0 : N, n_pre), offs, &total);
     return total + 256;
 }
@@ -369,7 +393,7 @@ extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores,
     HD_CHECK_ARG(out_rois && out_count, "null output");
     HD_CHECK_ARG(N == 0 || (boxes && scores && keys), "null input");
     const int cap = rpn_cap(N, n_pre) > 0 ? rpn_cap(N, n_pre) : 1;
-    size_t offs[6], total;
+    size_t offs[7], total;
     rpn_ws_layout(B, cap, offs, &total);
     uintptr_t w0 = hd_align_up((uintptr_t)workspace, 256);
     if (!workspace || w0 + total > (uintptr_t)workspace + workspace_bytes)
@@ -379,12 +403,13 @@ extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores,
     p.thr = hd_thr_floor(nms_iou);
     p.out_rois = out_rois; p.out_scores = out_scores; p.out_idx = (long long*)out_idx; p.out_count = out_count; p.cap = cap;
     p.k0 = (uint64_t*)(w0 + offs[0]); p.k1 = (uint64_t*)(w0 + offs[1]); p.v0 = (uint32_t*)(w0 + offs[2]); p.v1 = (uint32_t*)(w0 + offs[3]);
-    p.sbox = (float4*)(w0 + offs[4]); p.keep_r = (int*)(w0 + offs[5]);
-    size_t smem = ((size_t)(cap + 31) / 32 + 4) * 4;
-    HD_CHECK_ARG(smem <= 150 * 1024, "n_pre too large for the shared-memory bitmap");
+    p.sbox = (float4*)(w0 + offs[4]); p.keep_r = (int*)(w0 + offs[5]); p.gitem = (float4*)(w0 + offs[6]);
+    size_t words = ((size_t)(cap + 31) / 32 + 4 + 1) & ~(size_t)1;
+    HD_CHECK_ARG(words * 4 <= 56 * 1024, "n_pre too large for the shared-memory bitmap");
+    size_t smem = words * 4;
     static bool attr_set = false;
     if (!attr_set) {
-        HD_CUDA_CALL(cudaFuncSetAttribute(rpn_select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024));
+        HD_CUDA_CALL(cudaFuncSetAttribute(rpn_select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 186 * 1024));
         attr_set = true;
     }
     rpn_select_nms_kernel<<<B, RPN_NT, smem, (cudaStream_t)stream>>>(p);

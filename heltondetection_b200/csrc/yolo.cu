@@ -247,9 +247,14 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const __grid_constant_
     __syncwarp();
     const int rows = min(32, HW - t * 32);
     float* out = pred + ((size_t)b * total_anchors + p.level_off[l] + a * HW + t * 32) * p.no;
-    for (int k = lane; k < rows * p.no; k += 32) {
-        int row = k / p.no, c = k - row * p.no;
-        out[k] = tile[c * 33 + row];
+    {   // k = row*no + c walks the contiguous output; (row, c) advance incrementally (no >= 6, stride 32)
+        int row = lane / p.no, c = lane - row * p.no;
+        const int row_step = 32 / p.no, c_step = 32 - row_step * p.no;
+        for (int k = lane; k < rows * p.no; k += 32) {
+            out[k] = tile[c * 33 + row];
+            c += c_step; row += row_step;
+            if (c >= p.no) { c -= p.no; ++row; }
+        }
     }
 }
 
