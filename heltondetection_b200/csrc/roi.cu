@@ -195,33 +195,55 @@ __global__ void __launch_bounds__(256) roi_align_nhwc_kernel(const __grid_consta
 // threads form 256/QT bin groups that walk the PH*PW bins side by side.  ~5x fewer instructions per channel than
 // the scalar kernel; zero-weight table padding is predicated off so it costs no L1 bandwidth; the four results
 // of a thread are written to the [C][PH*PW] tile in a lane-rotated order that is free of bank conflicts.
+// one table row (fixed y cell) of a bin: NX real x entries, all loads independent
+template <int NX>
+__device__ __forceinline__ float4 roi_row_quad(const float4* __restrict__ row, const int* xo, const float* wx) {
+    float4 v[NX];
+#pragma unroll
+    for (int b = 0; b < NX; ++b) v[b] = __ldg(row + xo[b]);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int b = 0; b < NX; ++b) { r.x = fmaf(wx[b], v[b].x, r.x); r.y = fmaf(wx[b], v[b].y, r.y); r.z = fmaf(wx[b], v[b].z, r.z); r.w = fmaf(wx[b], v[b].w, r.w); }
+    return r;
+}
+
 template <int E>
 __device__ __forceinline__ void roi_align_bins_quad(const float* __restrict__ f, int q, int g, int groups, const AxisEntry* ytab,
-                                                    const AxisEntry* xtab, int PH, int PW, float count, float* tile, int rot) {
+                                                    const AxisEntry* xtab, const int* ycnt, const int* xcnt, int PH, int PW, float count,
+                                                    float* tile, int rot) {
     const int nb = PH * PW;
-    const unsigned magic = 0xffffffffu / (unsigned)PW + 1u;            // bin / PW == umulhi(bin, magic) for bin < 2^16
+    const unsigned magic = 0xffffffffu / (unsigned)PW + 1u;            // bin / PW == umulhi(bin, magic) for bin < 2^16 (PW > 1)
     const int icount = (int)count;
     const bool pow2 = (icount & (icount - 1)) == 0;                   // x / 2^k == x * 2^-k exactly
     const float inv = 1.0f / count;
     for (int bin = g; bin < nb; bin += groups) {
-        const int ph = (int)__umulhi((unsigned)bin, magic), pw = bin - ph * PW;
+        const int ph = (PW > 1) ? (int)__umulhi((unsigned)bin, magic) : bin, pw = bin - ph * PW;
         int xo[E]; float wx[E];
 #pragma unroll
         for (int b = 0; b < E; ++b) { xo[b] = xtab[pw * E + b].off >> 2; wx[b] = xtab[pw * E + b].w; }
+        const int ny = ycnt[ph], nx = xcnt[pw];   // real (merged) entries; the rest of the table is zero-weight padding
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (E == 4) {
+            for (int a = 0; a < ny; ++a) {
+                const float wy = ytab[ph * E + a].w;
+                const float4* __restrict__ row = reinterpret_cast<const float4*>(f + ytab[ph * E + a].off) + q;
+                float4 r;   // warp-uniform switch: only the real cells are fetched
+                if (nx == 2) r = roi_row_quad<2>(row, xo, wx);
+                else if (nx == 3) r = roi_row_quad<3>(row, xo, wx);
+                else if (nx == 4) r = roi_row_quad<4>(row, xo, wx);
+                else if (nx == 1) r = roi_row_quad<1>(row, xo, wx);
+                else continue;
+                acc.x = fmaf(wy, r.x, acc.x); acc.y = fmaf(wy, r.y, acc.y); acc.z = fmaf(wy, r.z, acc.z); acc.w = fmaf(wy, r.w, acc.w);
+            }
+        } else {
 #pragma unroll
-        for (int a = 0; a < E; ++a) {
-            const int yo = ytab[ph * E + a].off;
-            const float wy = ytab[ph * E + a].w;
-            if (wy == 0.0f) continue;  // padding (warp-uniform)
-            const float4* __restrict__ row = reinterpret_cast<const float4*>(f + yo) + q;
-            float4 v[E];   // padded entries re-read a real cell with weight 0: costs L1 bandwidth (not the limiter), no instructions
-#pragma unroll
-            for (int b = 0; b < E; ++b) v[b] = __ldg(row + xo[b]);
-            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int b = 0; b < E; ++b) { r.x = fmaf(wx[b], v[b].x, r.x); r.y = fmaf(wx[b], v[b].y, r.y); r.z = fmaf(wx[b], v[b].z, r.z); r.w = fmaf(wx[b], v[b].w, r.w); }
-            acc.x = fmaf(wy, r.x, acc.x); acc.y = fmaf(wy, r.y, acc.y); acc.z = fmaf(wy, r.z, acc.z); acc.w = fmaf(wy, r.w, acc.w);
+            for (int a = 0; a < E; ++a) {   // wide tables: fully unrolled over the padded table (zero-weight rows skipped)
+                const float wy = ytab[ph * E + a].w;
+                if (wy == 0.0f) continue;
+                const float4* __restrict__ row = reinterpret_cast<const float4*>(f + ytab[ph * E + a].off) + q;
+                const float4 r = roi_row_quad<E>(row, xo, wx);
+                acc.x = fmaf(wy, r.x, acc.x); acc.y = fmaf(wy, r.y, acc.y); acc.z = fmaf(wy, r.z, acc.z); acc.w = fmaf(wy, r.w, acc.w);
+            }
         }
         if (pow2) { acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
         else { acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count); acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count); }
@@ -233,9 +255,10 @@ __device__ __forceinline__ void roi_align_bins_quad(const float* __restrict__ f,
     }
 }
 
-// FIXED: sampling_ratio in 1..8 (small tables, 4 CTAs/SM); otherwise the adaptive variant (3 CTAs/SM, more registers)
-template <bool FIXED>
-__global__ void __launch_bounds__(256, FIXED ? 4 : 3) roi_align_nhwc_quad_kernel(const __grid_constant__ RoiParams p, int use_tma, int QT, int tab) {
+// EFIX = table width fixed by the host from sampling_ratio (4: sr<=2, 8: sr<=4, 16: sr<=8; small tables, the sr<=2 variant
+// runs 4 CTAs/SM); EFIX = 0: adaptive sampling, width chosen per RoI (3 CTAs/SM, more registers)
+template <int EFIX>
+__global__ void __launch_bounds__(256, EFIX == 4 ? 4 : 3) roi_align_nhwc_quad_kernel(const __grid_constant__ RoiParams p, int use_tma, int QT, int tab) {
     extern __shared__ __align__(128) float smem_f[];
     float* tile = smem_f;                                  // [C][PH*PW]
     AxisEntry* ytab = (AxisEntry*)(tile + (size_t)p.C * p.PH * p.PW);
@@ -258,7 +281,7 @@ __global__ void __launch_bounds__(256, FIXED ? 4 : 3) roi_align_nhwc_quad_kernel
     const int gw = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)p.PW));
     const float count = (float)max(gh * gw, 1);
     const int need = 2 * max(max(gh, gw), 0);
-    const int E = need <= 4 ? 4 : (need <= 8 ? 8 : (need <= 16 ? 16 : 0));
+    const int E = EFIX ? EFIX : (need <= 4 ? 4 : (need <= 8 ? 8 : (need <= 16 ? 16 : 0)));
     const int nb = p.PH * p.PW;
     const float* __restrict__ f = p.data[lvl] + (size_t)bidx * H * W * p.C;
     if (E && E * p.PH <= tab && E * p.PW <= tab) {
@@ -267,9 +290,10 @@ __global__ void __launch_bounds__(256, FIXED ? 4 : 3) roi_align_nhwc_quad_kernel
         __syncthreads();
         const int nq = p.C >> 2, groups = 256 / QT, g = threadIdx.x / QT, rot = (threadIdx.x & 31) >> 3;
         for (int q = threadIdx.x % QT; q < nq; q += QT) {
-            if (E == 4) roi_align_bins_quad<4>(f, q, g, groups, ytab, xtab, p.PH, p.PW, count, tile, rot);
-            else if (E == 8) roi_align_bins_quad<8>(f, q, g, groups, ytab, xtab, p.PH, p.PW, count, tile, rot);
-            else roi_align_bins_quad<16>(f, q, g, groups, ytab, xtab, p.PH, p.PW, count, tile, rot);
+            if (EFIX) roi_align_bins_quad<(EFIX ? EFIX : 4)>(f, q, g, groups, ytab, xtab, ycnt, xcnt, p.PH, p.PW, count, tile, rot);
+            else if (E == 4) roi_align_bins_quad<4>(f, q, g, groups, ytab, xtab, ycnt, xcnt, p.PH, p.PW, count, tile, rot);
+            else if (E == 8) roi_align_bins_quad<8>(f, q, g, groups, ytab, xtab, ycnt, xcnt, p.PH, p.PW, count, tile, rot);
+            else roi_align_bins_quad<16>(f, q, g, groups, ytab, xtab, ycnt, xcnt, p.PH, p.PW, count, tile, rot);
         }
     } else if ((long long)2 * max(gh, 1) * p.PH <= tab && (long long)2 * max(gw, 1) * p.PW <= tab) {
         // large adaptive grids: merged tables with run-time entry counts (<= bin size + 1 cells per axis)
@@ -612,8 +636,10 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
         if (!attr_set) {
             HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             HD_CUDA_CALL(cudaFuncSetAttribute(roi_pool_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             HD_CUDA_CALL(cudaFuncSetAttribute(roi_pool_nhwc_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             attr_set = true;
         }
@@ -625,8 +651,10 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
         while (QT < nq && QT < 256) QT <<= 1;
         if (pool && quad) roi_pool_nhwc_quad_kernel<<<(unsigned)p.K, 256, smem, st>>>(p, use_tma, QT);
         else if (pool) roi_pool_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
-        else if (quad && tab < ROI_TAB) roi_align_nhwc_quad_kernel<true><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
-        else if (quad) roi_align_nhwc_quad_kernel<false><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+        else if (quad && tab < ROI_TAB && p.sampling_ratio <= 2) roi_align_nhwc_quad_kernel<4><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+        else if (quad && tab < ROI_TAB && p.sampling_ratio <= 4) roi_align_nhwc_quad_kernel<8><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+        else if (quad && tab < ROI_TAB) roi_align_nhwc_quad_kernel<16><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+        else if (quad) roi_align_nhwc_quad_kernel<0><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
         else roi_align_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
         HD_CUDA_LAUNCH_CHECK("roi_nhwc_kernel");
     } else if (layout == HD_LAYOUT_NCHW) {
