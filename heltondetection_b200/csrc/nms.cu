@@ -30,6 +30,7 @@ struct NmsParams {
     // workspace (per image stride = cap)
     uint64_t* k0; uint64_t* k1; uint32_t* v0; uint32_t* v1;
     float4* sbox; int* scls; int* keep_r; float4* gitem;
+    int sort_off, bitonic_cap;  // dynamic smem: word offset of the in-smem sort area and its capacity (0 = disabled)
 };
 
 __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_constant__ NmsParams p) {
@@ -54,16 +55,40 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     int* keep_r = p.keep_r + off;
 
     HD_PHASE(0);
-    for (int i = tid; i < n; i += NMS_NT) {
-        uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + i] : (uint32_t)i;
-        k0[i] = ((uint64_t)(~hd_orderable(p.scores[off + i])) << 32) | tb;
-        v0[i] = (uint32_t)i;
+    const uint32_t* order;
+    if (n <= p.bitonic_cap) {
+        // segment fits in shared memory: bitonic sort of (key, slot) right there
+        unsigned long long* skey = reinterpret_cast<unsigned long long*>(removed + p.sort_off);
+        uint32_t* sval = reinterpret_cast<uint32_t*>(skey + p.bitonic_cap);
+        const int N = hd_bitonic_padded(n);
+        for (int i = tid; i < N; i += NMS_NT) {
+            if (i < n) {
+                const uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + i] : (uint32_t)i;
+                skey[i] = ((uint64_t)(~hd_orderable(p.scores[off + i])) << 32) | tb;
+                sval[i] = (uint32_t)i;
+            } else {
+                skey[i] = ~0ull;
+                sval[i] = 0u;
+            }
+        }
+        __syncthreads();
+        HD_PHASE(2);
+        if (N == 2048) hd_cta_bitonic_reg<2, true>(skey, sval);
+        else if (N == 4096) hd_cta_bitonic_reg<4, true>(skey, sval);
+        else hd_cta_bitonic_reg<8, true>(skey, sval);
+        order = sval;
+    } else {
+        for (int i = tid; i < n; i += NMS_NT) {
+            uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + i] : (uint32_t)i;
+            k0[i] = ((uint64_t)(~hd_orderable(p.scores[off + i])) << 32) | tb;
+            v0[i] = (uint32_t)i;
+        }
+        __syncthreads();
+        HD_PHASE(2);
+        const int res = hd_cta_radix_sort<NMS_NT>(k0, v0, k1, v1, n, ssm);
+        order = res ? v1 : v0;
     }
-    __syncthreads();
-    HD_PHASE(2);
-    const int res = hd_cta_radix_sort<NMS_NT>(k0, v0, k1, v1, n, ssm);
     HD_PHASE(3);
-    const uint32_t* order = res ? v1 : v0;
 
     const int n_use = (p.max_nms > 0) ? min(n, p.max_nms) : n;
     const int max_det = (p.max_det > 0) ? p.max_det : n_use;
@@ -211,7 +236,10 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
     p.sbox = (float4*)(w0 + offs[4]); p.scls = (int*)(w0 + offs[5]); p.keep_r = (int*)(w0 + offs[6]); p.gitem = (float4*)(w0 + offs[7]);
     size_t words = ((size_t)(cap + 31) / 32 + 4 + 1) & ~(size_t)1;   // 8-byte aligned end
     HD_CHECK_ARG(words * 4 <= 64 * 1024, "cap=%d too large for the shared-memory removed bitmap", cap);
-    size_t smem = words * 4;
+    // shared-memory sort area for segments of up to 8192 candidates: (u64 key, u32 slot)
+    p.sort_off = (int)words;
+    p.bitonic_cap = 8192;
+    size_t smem = words * 4 + (size_t)p.bitonic_cap * 12;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         HD_CUDA_CALL(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 186 * 1024));
