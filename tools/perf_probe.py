@@ -106,6 +106,8 @@ def cfg3():
     out = torch.empty((B, 208, 208, 256), device="cuda")
     t = timeit(lambda: _lib.check(_lib.lib().hd_nchw_to_nhwc(_lib.ptr(feats[0]), _lib.ptr(out), B, 256, 208, 208, _lib.stream())), iters=5)
     report("cfg3 nchw->nhwc level0", t, 2 * feats[0].numel() * 4)
+    t = timeit(lambda: (pr(obj, dlt), roi.multilevel_roi_align(nhwc, rois, 7, scales, 2, False)), iters=5)
+    report("cfg3 RPN + multilevel RoIAlign (NHWC in), per batch", t, rpn_bytes + fbytes + obytes, B)
     try:
         import torchvision
         small = rois[:4000]
