@@ -6,6 +6,7 @@
 #include "hd_nms_core.cuh"
 
 #define RPN_NT 1024
+#define RPN_U 8   // keys in flight per thread in the latency-bound scans over the N proposals of an image
 
 struct RpnParams {
     const float* obj[HD_MAX_LEVELS];
@@ -130,12 +131,12 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     auto scan_hist = [&](int sh, unsigned long long prefix, unsigned long long himask) {
         if (tid < 256) s_hist[tid] = 0;
         __syncthreads();
-        for (int i0 = 0; i0 < p.N; i0 += 4 * RPN_NT) {
-            uint32_t kk[4];
+        for (int i0 = 0; i0 < p.N; i0 += RPN_U * RPN_NT) {
+            uint32_t kk[RPN_U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int i = i0 + u * RPN_NT + tid; kk[u] = (i < p.N) ? keys[i] : 0u; }
+            for (int u = 0; u < RPN_U; ++u) { const int i = i0 + u * RPN_NT + tid; kk[u] = (i < p.N) ? keys[i] : 0u; }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < RPN_U; ++u) {
                 const int i = i0 + u * RPN_NT + tid;
                 int dg = 256 + lane;
                 if (kk[u] != 0u) {
@@ -199,12 +200,12 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
         __syncthreads();
         {
             const unsigned long long prefix = s_prefix;
-            for (int i0 = 0; i0 < p.N; i0 += 4 * RPN_NT) {
-                uint32_t kk[4];
+            for (int i0 = 0; i0 < p.N; i0 += RPN_U * RPN_NT) {
+                uint32_t kk[RPN_U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int i = i0 + u * RPN_NT + tid; kk[u] = (i < p.N) ? keys[i] : 0u; }
+                for (int u = 0; u < RPN_U; ++u) { const int i = i0 + u * RPN_NT + tid; kk[u] = (i < p.N) ? keys[i] : 0u; }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < RPN_U; ++u) {
                     const int i = i0 + u * RPN_NT + tid;
                     const unsigned long long comp = rpn_composite(kk[u], i);
                     const bool hit = kk[u] != 0u && ((comp ^ prefix) >> 48) == 0ull;
@@ -251,13 +252,13 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     __shared__ int s_base;
     if (tid == 0) s_base = 0;
     __syncthreads();
-    for (int i0 = 0; i0 < p.N; i0 += 4 * RPN_NT) {
-        const int ib = i0 + 4 * tid;            // four consecutive proposals per thread
-        uint32_t kk[4];
-        bool sel[4];
+    for (int i0 = 0; i0 < p.N; i0 += RPN_U * RPN_NT) {
+        const int ib = i0 + RPN_U * tid;        // RPN_U consecutive proposals per thread
+        uint32_t kk[RPN_U];
+        bool sel[RPN_U];
         int c = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < RPN_U; ++u) {
             const int i = ib + u;
             kk[u] = (i < p.N) ? keys[i] : 0u;
             sel[u] = kk[u] != 0u && rpn_composite(kk[u], i) >= T;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
         int tot = 0;
         if (tid == RPN_NT - 1) tot = pre + c;   // last thread knows the new running total
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < RPN_U; ++u) {
             if (sel[u]) {
                 if (pre < p.cap) { kk0[pre] = ~kk[u]; v0[pre] = (uint32_t)(ib + u); }
                 ++pre;
@@ -422,7 +423,9 @@ extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores,
     size_t words = ((size_t)(cap + 31) / 32 + 4 + 1) & ~(size_t)1;
     HD_CHECK_ARG(words * 4 <= 56 * 1024, "n_pre too large for the shared-memory bitmap");
     p.sort_off = (int)words;
-    p.bitonic_cap = 8192;   // larger selections (e.g. 12 000) sort faster with the 32-bit stable radix passes
+    // selections of up to 8192 proposals sort in shared memory; larger ones (e.g. 12 000) use the 32-bit stable radix
+    // passes and keep the shared memory for L1 (the pruned NMS streams its records through it)
+    p.bitonic_cap = (cap <= 8192) ? 8192 : 0;
     size_t smem = words * 4 + (size_t)p.bitonic_cap * 8;
     static bool attr_set = false;
     if (!attr_set) {

@@ -95,3 +95,28 @@ def test_box_iou_matches_torchvision():
     # same fp32 op order; division correctly rounded on both sides
     assert torch.allclose(got, ref, rtol=1e-6, atol=1e-7)
     assert ops.box_iou(b1[:0].cuda(), b2.cuda()).shape == (0, 1301)
+
+
+@pytest.mark.parametrize("thr", [0.05, 0.3, 0.5, 0.5005, 0.7, 0.95])
+@pytest.mark.parametrize("n", [1500, 9000])
+def test_grid_pruned_path_with_adversarial_boxes(n, thr):
+    """n > 768 takes the spatially pruned pass (n <= 8192 also the shared-memory bitonic sort): its pruning argument must
+    hold for every threshold and its 'improper box' rule for NaN / inf / inverted / zero-area / huge boxes."""
+    g = torch.Generator().manual_seed(n + int(thr * 1000))
+    b, s = _boxes(n, n + 1)
+    k = 24
+    idx = torch.randperm(n, generator=g)[: 8 * k]
+    b[idx[0 * k:1 * k], 0] = float("nan")
+    b[idx[1 * k:2 * k], 2] = float("inf")
+    b[idx[2 * k:3 * k]] = b[idx[2 * k:3 * k]][:, [2, 3, 0, 1]]                    # inverted
+    b[idx[3 * k:4 * k], 2] = b[idx[3 * k:4 * k], 0]                               # zero width
+    b[idx[4 * k:5 * k]] = torch.tensor([-1e6, -1e6, 1e6, 1e6])                    # huge: covers every cell
+    b[idx[5 * k:6 * k]] = b[idx[0]].nan_to_num(0.0)                               # exact duplicates
+    b[idx[6 * k:7 * k], :2] -= 3e4                                                # far outliers stretch the extent
+    b[idx[7 * k:8 * k], 2:] = b[idx[7 * k:8 * k], :2] + 1e-3                      # tiny boxes
+    s[idx[:k]] = s[idx[k:2 * k]]                                                  # score ties
+    ref = torchvision.ops.nms(b, s, thr)
+    got = _run(b, s, thr)
+    assert torch.equal(got, ref)
+    c = torch.randint(0, 7, (n,), generator=g)
+    assert torch.equal(_run(b, s, thr, c.int(), 1), torchvision.ops.boxes._batched_nms_vanilla(b, s, c, thr))
