@@ -165,3 +165,29 @@ def test_tta_map_back_inverts_the_view_transform():
     view[:, [1, 3]] = det[:, [1, 3]] * r
     b, s, l = oracle.tta.map_back(view, r, True, W, 640.0, 640.0)
     assert torch.allclose(b * 640, det[:, :4], atol=1e-3) and s.item() == pytest.approx(0.9) and l.item() == 3.0
+
+
+def test_plain_c_restatement_is_pinned_to_torchvision():
+    """oracle/c/hd_oracle.c (gcc, -ffp-contract=off) against the torchvision CPU ops and the golden fixtures."""
+    from oracle import cref
+    b, s = T("nms_boxes"), T("nms_scores")
+    for thr in (0.3, 0.5, 0.7):
+        assert np.array_equal(cref.nms(b.numpy(), s.numpy(), thr), G[f"nms_keep_{thr}"])
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 50, 700):
+        c = torch.rand((n, 2), generator=g) * 200
+        w = torch.rand((n, 2), generator=g) * 60 + 1
+        bb = torch.cat((c - w / 2, c + w / 2), 1)
+        sc = (torch.rand((n,), generator=g) * 16).round() / 16
+        if n > 10:
+            sc[3] = float("nan"); bb[5, 0] = float("nan"); bb[7] = bb[7][[2, 3, 0, 1]]
+        for thr in (0.2, 0.5, 0.6):
+            assert np.array_equal(cref.nms(bb.numpy(), sc.numpy(), thr), torchvision.ops.nms(bb, sc, thr).numpy())
+        assert np.array_equal(cref.nms(bb.numpy(), sc.numpy(), 0.5, max_keep=3), torchvision.ops.nms(bb, sc, 0.5).numpy()[:3])
+    assert np.allclose(cref.box_iou(b[:40].numpy(), b[40:90].numpy()), G["box_iou_40x50"], rtol=1e-6, atol=1e-7)
+    x, rois = T("roi_x"), T("roi_rois")
+    for sr in (2, 0):
+        for al in (False, True):
+            got = cref.roi_align(x.numpy(), rois.numpy(), 7, 0.125, sr, al)
+            assert np.allclose(got, G[f"roi_align_sr{sr}_al{int(al)}"], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(cref.roi_pool(x.numpy(), rois.numpy(), 7, 0.125), G["roi_pool"])
