@@ -153,18 +153,47 @@ def main():
     heads_cpu, _ = synth.yolo_heads(B, IMG, NC, G, 1235 + rank)
     heads = [h.to(dev) for h in heads_cpu]
     pp = yolo.YoloPostprocessor(conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=(args.mode == "dense"), device=dev)
-    gather = hd_dist.DetectionGather(B, MAX_DET, dev) if world > 1 else None
+    # multi-GPU: the NMS kernels store every kept row into every rank's gather buffer (symmetric memory, posted NVLink
+    # stores) -- the all-gather is fused into the kernel epilogue; a cross-GPU barrier per step runs on a side stream.
+    # Fallback if symmetric memory is unavailable: pack + NCCL all_gather_into_tensor on a side stream.
+    gather, peer, gather_mode = None, None, "none"
+    if world > 1:
+        try:
+            peer = hd_dist.PeerDetectionBuffers(B, MAX_DET, dev)
+            gather_mode = "fused: NMS kernels write into every peer's gather buffer over NVLink (symmetric memory) + per-step device barrier"
+        except Exception as e:  # noqa: BLE001
+            peer = None
+            gather = hd_dist.DetectionGather(B, MAX_DET, dev)
+            gather_mode = f"NCCL all_gather of padded detections on a side stream (symmetric memory unavailable: {type(e).__name__})"
 
     # the step is ONE C-ABI call (decode+filter kernel, small-image NMS kernel, large-image pass), captured once in a CUDA graph
-    replay, det, cnt, _ = pp.graph(heads)
+    if peer is not None:
+        replays = [pp.graph(heads, peer=peer, slot=s_)[0:3] for s_ in (0, 1)]
+        side = torch.cuda.Stream(dev)
+        ev_step = torch.cuda.Event()
+    else:
+        replays = [pp.graph(heads)[0:3]]
 
-    def step():
+    def run_step(k):
+        replay, det, cnt = replays[k % len(replays)]
         replay()
-        if gather is not None:
-            gather(det, cnt)
+        if peer is not None:
+            ev_step.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev_step)
+                peer.barrier()                # all ranks' stores of this step have landed; overlaps the next replay
+        elif gather is not None:
+            gather(det, cnt)                  # side stream: overlaps the next replay
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    def join():
+        if peer is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        elif gather is not None:
+            gather.finish()
+
+    for k in range(max(args.warmup, 3)):
+        run_step(k)
+    join()
     torch.cuda.synchronize()
     # ---------------- timed region: K steps, device-resident inputs (2.19 GB/rank >> 126 MB L2)
     K = args.steps
@@ -176,13 +205,18 @@ def main():
     torch.cuda.synchronize()
     sampler.start()
     for k in range(K):
+        replay, det, cnt = replays[k % len(replays)]
         ev[k][0].record()
         replay()
         ev[k][1].record()
-        if gather is not None:
-            gather(det, cnt)               # side stream: overlaps the next replay
-    if gather is not None:
-        gather.finish()                    # every all-gather completes inside the timed region
+        if peer is not None:
+            ev_step.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev_step)
+                peer.barrier()
+        elif gather is not None:
+            gather(det, cnt)
+    join()                                    # every gather completes inside the timed region
     ev_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -206,10 +240,12 @@ def main():
     pp_copy = yolo.YoloPostprocessor(conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=False, device=dev)
     pp_zc = yolo.YoloPostprocessor(conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=False, device=dev)
 
+    e2e_gather = hd_dist.DetectionGather(B, MAX_DET, dev) if world > 1 else None
+
     def finish(det, cnt):
-        if gather is not None:
-            gather(det, cnt)
-            gather.finish()
+        if e2e_gather is not None:
+            e2e_gather(det, cnt)
+            e2e_gather.finish()
         det_h.copy_(det, non_blocking=True)
         cnt_h.copy_(cnt, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -288,7 +324,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "conf_thres": CONF, "iou_thres": IOU, "max_det": MAX_DET,
                        "read_mode": args.mode, "l2": "inputs (2.19 GB/rank) larger than the 126 MB L2", "launch": "CUDA graph replay of one hd_yolo_postprocess call",
-                       "parallelism": f"image-sharded x{world}" + (" + NCCL all_gather of padded detections" if world > 1 else "")},
+                       "parallelism": f"image-sharded x{world}", "gather": gather_mode},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "path": e2e_path},
             "gpu_launches": 3 * K,

@@ -30,6 +30,13 @@ class RpnLevel(C.Structure):
                 ("stride", C.c_float), ("anchor_base", C.c_float * (4 * HD_MAX_ANCHORS))]
 
 
+HD_MAX_REPLICAS = 16
+
+
+class Replicas(C.Structure):
+    _fields_ = [("n", C.c_int32), ("det", C.c_void_p * HD_MAX_REPLICAS), ("count", C.c_void_p * HD_MAX_REPLICAS)]
+
+
 class RoiLevel(C.Structure):
     _fields_ = [("data", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("spatial_scale", C.c_float)]
 
@@ -48,6 +55,8 @@ SIGNATURES = {
     "hd_yolo_filter_pred": (_i, [_vp, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "hd_sort_nms_workspace_size": (_sz, [_i, _i]),
     "hd_sort_nms_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hd_sort_nms_batched_replicated": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _f, _i, _i, _vp, _vp, _vp, C.POINTER(Replicas), _vp, _sz, _vp]),
+    "hd_yolo_postprocess_replicated": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _d, _d, _i, _i, _f, _i, _i, _vp, _vp, _vp, C.POINTER(Replicas), _vp, _sz, _vp]),
     "hd_box_iou": (_i, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "hd_rpn_num_anchors": (_i, [C.POINTER(RpnLevel), _i, _i]),
     "hd_rpn_decode": (_i, [C.POINTER(RpnLevel), _i, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),

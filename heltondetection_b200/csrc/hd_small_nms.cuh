@@ -9,6 +9,12 @@
 #define HD_SMALL_N 512
 #define HD_SMALL_NT 256
 
+struct HdRep {   // device copy of hd_replicas
+    int n;
+    float* det[HD_MAX_REPLICAS];
+    int* cnt[HD_MAX_REPLICAS];
+};
+
 struct HdNmsTail {
     float thr;  // hd_thr_floor(iou)
     int class_mode;
@@ -17,6 +23,7 @@ struct HdNmsTail {
     float* out_det;
     long long* out_idx;
     int* out_count;
+    HdRep rep;
 };
 
 struct HdSmallSmem {
@@ -39,6 +46,7 @@ __device__ __forceinline__ bool hd_small_nms_image(HdSmallSmem& sm, const HdNmsT
     if (n > HD_SMALL_N) return false;
     if (n <= 0) {
         if (tid == 0) q.out_count[b] = 0;
+        if (tid < q.rep.n) q.rep.cnt[tid][b] = 0;
         return true;
     }
     const size_t off = (size_t)b * cap;
@@ -80,14 +88,19 @@ __device__ __forceinline__ bool hd_small_nms_image(HdSmallSmem& sm, const HdNmsT
         const int slot = sm.order[sm.keep[k]];
         if (q.out_det) {
             const float4 bx = sm.raw_box[slot];
-            float* o = q.out_det + ((size_t)b * q.max_det + k) * 6;
-            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-            o[4] = sm.score[slot];
-            o[5] = (float)sm.cls[slot];
+            const float sc = sm.score[slot], cf = (float)sm.cls[slot];
+            const size_t ro = ((size_t)b * q.max_det + k) * 6;
+            float* o = q.out_det + ro;
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = sc; o[5] = cf;
+            for (int r = 0; r < q.rep.n; ++r) {   // posted stores into the peers' gather buffers
+                float* pr = q.rep.det[r] + ro;
+                pr[0] = bx.x; pr[1] = bx.y; pr[2] = bx.z; pr[3] = bx.w; pr[4] = sc; pr[5] = cf;
+            }
         }
         if (q.out_idx) q.out_idx[(size_t)b * q.max_det + k] = (long long)sm.tie[slot];
     }
     if (tid == 0) q.out_count[b] = kc;
+    if (tid < q.rep.n) q.rep.cnt[tid][b] = kc;
     __syncthreads();
     return true;
 }

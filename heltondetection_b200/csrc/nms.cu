@@ -31,6 +31,7 @@ struct NmsParams {
     uint64_t* k0; uint64_t* k1; uint32_t* v0; uint32_t* v1;
     float4* sbox; int* scls; int* keep_r; float4* gitem;
     int sort_off, bitonic_cap;  // dynamic smem: word offset of the in-smem sort area and its capacity (0 = disabled)
+    HdRep rep;
 };
 
 __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_constant__ NmsParams p) {
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     if (p.min_n >= 0 && n <= p.min_n) return;
     if (n <= 0) {
         if (tid == 0) p.out_count[b] = 0;
+        if (tid < p.rep.n) p.rep.cnt[tid][b] = 0;
         return;
     }
     const size_t off = (size_t)b * p.cap;
@@ -121,14 +123,19 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
         const uint32_t slot = order[r];
         if (p.out_det) {
             const float4 bx = p.boxes[off + slot];
-            float* o = p.out_det + ((size_t)b * p.max_det + q) * 6;
-            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
-            o[4] = p.scores[off + slot];
-            o[5] = p.cls ? (float)p.cls[off + slot] : 0.0f;
+            const float sc = p.scores[off + slot], cf = p.cls ? (float)p.cls[off + slot] : 0.0f;
+            const size_t ro = ((size_t)b * p.max_det + q) * 6;
+            float* o = p.out_det + ro;
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = sc; o[5] = cf;
+            for (int r = 0; r < p.rep.n; ++r) {   // posted stores into the peers' gather buffers
+                float* pr = p.rep.det[r] + ro;
+                pr[0] = bx.x; pr[1] = bx.y; pr[2] = bx.z; pr[3] = bx.w; pr[4] = sc; pr[5] = cf;
+            }
         }
         if (p.out_idx) p.out_idx[(size_t)b * p.max_det + q] = p.tiebreak ? (long long)p.tiebreak[off + slot] : (long long)slot;
     }
     if (tid == 0) p.out_count[b] = kc;
+    if (tid < p.rep.n) p.rep.cnt[tid][b] = kc;
 }
 
 // small-image variant: 256 threads, everything in shared memory, several images per SM at once
@@ -192,20 +199,32 @@ extern "C" HD_API size_t hd_sort_nms_workspace_size(int B, int cap) {
 int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
                             const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
                             float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
-                            int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream, int min_n);
+                            int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream, int min_n,
+                            const hd_replicas* replicas);
+
+extern "C" HD_API int hd_sort_nms_batched_replicated(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
+                                                     const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
+                                                     float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
+                                                     int32_t* out_count, const hd_replicas* replicas, void* workspace,
+                                                     size_t workspace_bytes, void* stream) {
+    return hd_sort_nms_batched_min(boxes, scores, cls, tiebreak, counts, n_fixed, B, cap, iou_thres, class_mode, offset_scale, max_nms,
+                                   max_det, out_det, out_idx, out_count, workspace, workspace_bytes, stream, -1, replicas);
+}
 
 extern "C" HD_API int hd_sort_nms_batched(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
                                           const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
                                           float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
                                           int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
     return hd_sort_nms_batched_min(boxes, scores, cls, tiebreak, counts, n_fixed, B, cap, iou_thres, class_mode, offset_scale, max_nms,
-                                   max_det, out_det, out_idx, out_count, workspace, workspace_bytes, stream, -1);
+                                   max_det, out_det, out_idx, out_count, workspace, workspace_bytes, stream, -1, nullptr);
 }
 
 int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
                             const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
                             float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
-                            int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream, int min_n) {
+                            int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream, int min_n,
+                            const hd_replicas* replicas) {
+    HD_CHECK_ARG(replicas == nullptr || (replicas->n >= 0 && replicas->n <= HD_MAX_REPLICAS), "replicas->n out of [0,%d]", HD_MAX_REPLICAS);
     HD_CHECK_ARG(B >= 0 && cap >= 0, "bad shape B=%d cap=%d", B, cap);
     if (B == 0) return HD_OK;
     HD_CHECK_ARG(out_count != nullptr, "out_count is NULL");
@@ -228,6 +247,14 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
     NmsParams p;
     p.boxes = (const float4*)boxes; p.scores = scores; p.cls = (class_mode == HD_NMS_AGNOSTIC) ? cls : cls; p.tiebreak = tiebreak;
     p.counts = counts; p.n_fixed = n_fixed; p.B = B; p.cap = cap; p.min_n = min_n;
+    p.rep.n = 0;
+    if (replicas) {
+        p.rep.n = replicas->n;
+        for (int r = 0; r < replicas->n; ++r) {
+            HD_CHECK_ARG(replicas->det[r] && replicas->count[r], "replica %d has a NULL pointer", r);
+            p.rep.det[r] = replicas->det[r]; p.rep.cnt[r] = replicas->count[r];
+        }
+    }
     p.thr = hd_thr_floor(iou_thres);
     p.class_mode = class_mode; p.offset_scale = offset_scale; p.max_nms = max_nms; p.max_det = max_det;
     p.out_det = out_det; p.out_idx = (long long*)out_idx; p.out_count = out_count;
@@ -251,6 +278,7 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
         HdNmsTail q;
         q.thr = p.thr; q.class_mode = class_mode; q.offset_scale = offset_scale; q.max_nms = max_nms; q.max_det = max_det;
         q.out_det = out_det; q.out_idx = (long long*)out_idx; q.out_count = out_count;
+        q.rep = p.rep;
         small_nms_kernel<<<B, HD_SMALL_NT, 0, st>>>(p, q);
         HD_CUDA_LAUNCH_CHECK("small_nms_kernel");
         p.min_n = HD_SMALL_N;

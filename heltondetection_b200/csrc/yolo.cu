@@ -440,6 +440,14 @@ extern "C" HD_API size_t hd_yolo_postprocess_workspace_size(int B, int total_anc
 extern "C" HD_API int hd_yolo_postprocess(const hd_yolo_level* levels, int n_levels, int B, int A, int nc, double conf_thres, double iou_thres,
                                           int flags, int class_mode, float offset_scale, int max_nms, int max_det, float* out_det,
                                           int64_t* out_idx, int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    return hd_yolo_postprocess_replicated(levels, n_levels, B, A, nc, conf_thres, iou_thres, flags, class_mode, offset_scale, max_nms,
+                                          max_det, out_det, out_idx, out_count, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" HD_API int hd_yolo_postprocess_replicated(const hd_yolo_level* levels, int n_levels, int B, int A, int nc, double conf_thres,
+                                                     double iou_thres, int flags, int class_mode, float offset_scale, int max_nms,
+                                                     int max_det, float* out_det, int64_t* out_idx, int32_t* out_count,
+                                                     const hd_replicas* replicas, void* workspace, size_t workspace_bytes, void* stream) {
     HD_CHECK_ARG(levels != nullptr && n_levels >= 1 && n_levels <= HD_MAX_LEVELS, "n_levels must be in [1,%d], got %d", HD_MAX_LEVELS, n_levels);
     if (B == 0) return HD_OK;
     long long cap_ll = 0;
@@ -458,6 +466,7 @@ extern "C" HD_API int hd_yolo_postprocess(const hd_yolo_level* levels, int n_lev
     int32_t* cand_count = (int32_t*)(w0 + offs[4]);
     int rc = hd_yolo_decode_filter(levels, n_levels, B, A, nc, conf_thres, flags, cand_box, cand_score, cand_cls, cand_anchor, cand_count, cap, stream);
     if (rc) return rc;
-    return hd_sort_nms_batched(cand_box, cand_score, cand_cls, cand_anchor, cand_count, 0, B, cap, iou_thres, class_mode, offset_scale, max_nms,
-                               max_det, out_det, out_idx, out_count, (void*)(w0 + offs[5]), hd_sort_nms_workspace_size(B, cap), stream);
+    return hd_sort_nms_batched_replicated(cand_box, cand_score, cand_cls, cand_anchor, cand_count, 0, B, cap, iou_thres, class_mode,
+                                          offset_scale, max_nms, max_det, out_det, out_idx, out_count, replicas, (void*)(w0 + offs[5]),
+                                          hd_sort_nms_workspace_size(B, cap), stream);
 }

@@ -89,3 +89,54 @@ def gather_ragged(det, count, n_images, group=None):
     dist.all_gather(outs, rec, group=group)
     full = torch.cat([o[: s.stop - s.start] for o, s in zip(outs, sizes)], 0)
     return unpack_records(full, md)
+
+
+class PeerDetectionBuffers:
+    """Gather buffers in symmetric (peer-mapped) memory: det [slots, world*B, max_det, 6] + count [slots, world*B] on
+    every rank.  The NMS kernels of rank r write image b of their shard to row r*B+b of EVERY rank's buffer, so after a
+    step (and a cross-GPU barrier) each rank holds the gathered detections without pack kernels or an NCCL collective.
+    `slots` buffers alternate between steps so a consumer can still read step k while step k+1 is being written."""
+
+    def __init__(self, B, max_det, device, group=None, slots=2):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.B, self.max_det, self.slots = B, max_det, slots
+        if self.world - 1 > _lib.HD_MAX_REPLICAS:
+            raise RuntimeError("too many peers for hd_replicas")
+        n = self.world * B
+        self.det = symm.empty((slots, n, max_det, 6), dtype=torch.float32, device=device)
+        self.count = symm.empty((slots, n), dtype=torch.int32, device=device)
+        self.det.zero_()
+        self.count.zero_()
+        self.h_det = symm.rendezvous(self.det, self.group.group_name)
+        self.h_cnt = symm.rendezvous(self.count, self.group.group_name)
+        self._rep = []
+        for s in range(slots):
+            r = _lib.Replicas()
+            k = 0
+            for p in range(self.world):
+                if p == self.rank:
+                    continue
+                r.det[k] = self.h_det.buffer_ptrs[p] + ((s * n + self.rank * B) * max_det * 6) * 4
+                r.count[k] = self.h_cnt.buffer_ptrs[p] + (s * n + self.rank * B) * 4
+                k += 1
+            r.n = k
+            self._rep.append(r)
+
+    def local(self, slot):
+        """this rank's slice of its own gather buffer: (det [B,max_det,6], count [B])"""
+        lo = self.rank * self.B
+        return self.det[slot, lo:lo + self.B], self.count[slot, lo:lo + self.B]
+
+    def replicas(self, slot):
+        return self._rep[slot]
+
+    def gathered(self, slot):
+        """(det [world*B,max_det,6], count [world*B]) -- complete once every rank's step has finished (see barrier())"""
+        return self.det[slot], self.count[slot]
+
+    def barrier(self):
+        """cross-GPU barrier on the current stream: afterwards the stores of all ranks' previous kernels have landed"""
+        self.h_det.barrier()

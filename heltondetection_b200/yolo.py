@@ -113,7 +113,7 @@ class YoloPostprocessor:
             return keep[0].device
         return torch.device("cuda", torch.cuda.current_device())
 
-    def _one_call(self, arr, keep, B, A, nc, total):
+    def _one_call(self, arr, keep, B, A, nc, total, peer=None, slot=0):
         dev = self._out_device(keep)
         key = (B, total, dev)
         if self._fkey != key:
@@ -124,14 +124,19 @@ class YoloPostprocessor:
             self.f_idx = torch.zeros((B, self.max_det), dtype=torch.int64, device=dev)
             self.f_count = torch.zeros((B,), dtype=torch.int32, device=dev)
             self._fkey = key
+        det, count, rep = self.f_det, self.f_count, None
+        if peer is not None:   # outputs go to this rank's slice of the gather buffer and, replicated, to every peer's
+            det, count, rep = peer.local(slot)[0], peer.local(slot)[1], peer.replicas(slot)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().hd_yolo_postprocess(
+            _lib.check(_lib.lib().hd_yolo_postprocess_replicated(
                 arr, len(keep), B, A, nc, self.conf_thres, self.iou_thres, self.flags, self.class_mode, self.max_wh, self.max_nms,
-                self.max_det, _lib.ptr(self.f_det), _lib.ptr(self.f_idx), _lib.ptr(self.f_count), _lib.ptr(self.f_ws), self.f_ws_bytes,
+                self.max_det, _lib.ptr(det), _lib.ptr(self.f_idx), _lib.ptr(count), rep, _lib.ptr(self.f_ws), self.f_ws_bytes,
                 _lib.stream()))
-        return self.f_det, self.f_count, self.f_idx
+        return det, count, self.f_idx
 
-    def __call__(self, outputs):
+    def __call__(self, outputs, peer=None, slot=0):
+        """peer: a dist.PeerDetectionBuffers -- the NMS kernels then store every kept row into this rank's slice of the
+        gather buffer of EVERY rank (posted NVLink stores), i.e. the all-gather is fused into the kernel epilogue."""
         # the level table only depends on the pointers/shapes: rebuild it when they change
         sig = tuple((x.data_ptr(), tuple(x.shape), x.dtype, x.is_contiguous()) for x in outputs)
         if getattr(self, "_sig", None) != sig:
@@ -139,7 +144,9 @@ class YoloPostprocessor:
             self._sig = sig
         arr, keep, B, A, nc, total = self._lv
         if self.one_call:
-            return self._one_call(arr, keep, B, A, nc, total)
+            return self._one_call(arr, keep, B, A, nc, total, peer, slot)
+        if peer is not None:
+            raise RuntimeError("replicated (peer) outputs need the one-call path")
         buf = self.buffers(B, total, self._out_device(keep))
         _lib.check(_lib.lib().hd_yolo_decode_filter(
             arr, len(keep), B, A, nc, self.conf_thres, self.flags, _lib.ptr(buf.box), _lib.ptr(buf.score),
@@ -147,15 +154,15 @@ class YoloPostprocessor:
         _run_nms(buf, self.iou_thres, self.class_mode, self.max_wh, self.max_nms)
         return buf.det, buf.out_count, buf.idx
 
-    def graph(self, outputs, warmup=3):
+    def graph(self, outputs, warmup=3, peer=None, slot=0):
         """Capture one post-process of `outputs` (fixed buffers) into a CUDA graph; returns (replay, det, count, idx).
         replay() re-runs the captured kernels on whatever the input buffers hold -- no per-call host work."""
         for _ in range(warmup):
-            self(outputs)
+            self(outputs, peer, slot)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            det, count, idx = self(outputs)
+            det, count, idx = self(outputs, peer, slot)
         return g.replay, det, count, idx
 
     def candidates(self, outputs):

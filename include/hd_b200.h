@@ -116,6 +116,28 @@ HD_API int hd_sort_nms_batched(const float* boxes, const float* scores, const in
                         float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
                         int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Replicated outputs (multi-GPU): besides out_det/out_count, every kept row and every count is also stored to
+ * `n` more buffers -- typically the slices of the gather buffers of the peer GPUs, mapped into this process
+ * (CUDA IPC / symmetric memory) -- so the all-gather of the padded detections happens in the NMS
+ * kernel's epilogue as posted NVLink stores instead of a separate pack + NCCL collective.  det[i] addresses a
+ * [B, max_det, 6] block, count[i] a [B] block, at the place this rank's images occupy in replica i. */
+#define HD_MAX_REPLICAS 16
+typedef struct {
+    int32_t n;
+    float* det[HD_MAX_REPLICAS];
+    int32_t* count[HD_MAX_REPLICAS];
+} hd_replicas; /* host struct */
+HD_API int hd_sort_nms_batched_replicated(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
+                                          const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
+                                          float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,
+                                          int32_t* out_count, const hd_replicas* replicas /*host, nullable*/, void* workspace,
+                                          size_t workspace_bytes, void* stream);
+HD_API int hd_yolo_postprocess_replicated(const hd_yolo_level* levels /*host*/, int n_levels, int B, int A, int nc,
+                                          double conf_thres, double iou_thres, int flags, int class_mode, float offset_scale,
+                                          int max_nms, int max_det, float* out_det, int64_t* out_idx, int32_t* out_count,
+                                          const hd_replicas* replicas /*host, nullable*/, void* workspace,
+                                          size_t workspace_bytes, void* stream);
+
 /* box_iou (boxes.py:308-370): iou[N,M] = inter / (area1 + area2 - inter), fp32, no eps. */
 HD_API int hd_box_iou(const float* boxes1, int64_t N, const float* boxes2, int64_t M, float* iou, void* stream);
 
