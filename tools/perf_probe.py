@@ -173,8 +173,50 @@ def zerocopy():
     report("H2D copy + sparse postprocess", t, nbytes, B)
 
 
+def cpu():
+    """The reference's CPU path (oracle = torch CPU + torchvision CPU ops + numpy WBF) on bounded samples of every config."""
+    import oracle
+    import numpy as np
+    torch.set_num_threads(os.cpu_count() or 1)
+    nt = torch.get_num_threads()
+
+    def best(fn, reps=3):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    def line(name, t, n_img):
+        print(f"CPU[{nt} threads] {name:58s} {t * 1e3:9.1f} ms for {n_img} img -> {n_img / t:9.1f} img/s", flush=True)
+
+    h, _ = synth.yolo_heads(16, 640, 80, 20, 1235)
+    line("cfg2 decode_box + non_max_suppression (conf .25)", best(lambda: oracle.yolo.non_max_suppression(oracle.yolo.decode_box(h), 0.25, 0.45)), 16)
+    line("cfg1 same, batch 1", best(lambda: oracle.yolo.non_max_suppression(oracle.yolo.decode_box([x[:1] for x in h]), 0.25, 0.45)), 1)
+    h4, _ = synth.yolo_heads(2, 1280, 10, 300, 1238, dense=True)
+    line("cfg4 1280^2 nc=10 dense, conf .001 iou .6", best(lambda: oracle.yolo.non_max_suppression(oracle.yolo.decode_box(h4), 0.001, 0.6)), 2)
+    obj, dlt, bases, _ = synth.rpn_heads(2, 832, G=20, seed=1237)
+    props = oracle.rpn.rpn_proposals(obj, dlt, bases, (4, 8, 16, 32), (832, 832), n_pre_nms=12000, n_post_nms=2000, min_size=16)
+    line("cfg3 RPN decode + top-12000 + nms(0.7) + top-2000", best(lambda: oracle.rpn.rpn_proposals(obj, dlt, bases, (4, 8, 16, 32), (832, 832), n_pre_nms=12000, n_post_nms=2000, min_size=16), 2), 2)
+    feats = synth.fpn_features(1, 832, 256, 1237)
+    r = torch.cat((torch.zeros(len(props[0][0]), 1), props[0][0]), 1)
+    line("cfg3 multi-level RoIAlign 2000x256x7x7 (sr=2)", best(lambda: oracle.roi.multilevel_roi_align(feats, r, 7, [1 / 4, 1 / 8, 1 / 16, 1 / 32], 2, False), 2), 1)
+    line("cfg3 multi-level RoIPool 2000x256x7x7", best(lambda: oracle.roi.multilevel_roi_align(feats, r, 7, [1 / 4, 1 / 8, 1 / 16, 1 / 32], 2, False, op="pool"), 2), 1)
+    views, _ = synth.tta_heads(2, 640, 80, G=20, seed=1239)
+
+    def tta():
+        for b in range(2):
+            bl, sl, ll = [], [], []
+            for (hh, rr, ff, ss) in views:
+                d = oracle.yolo.non_max_suppression(oracle.yolo.decode_box([x[b:b + 1] for x in hh]), 0.25, 0.45)[0]
+                bb, sc, lb = oracle.tta.map_back(d, rr, ff, float(ss), 640.0, 640.0)
+                bl.append(bb.numpy()); sl.append(sc.numpy()); ll.append(lb.numpy())
+            oracle.wbf.weighted_boxes_fusion(bl, sl, ll, None, 0.55, 0.001)
+    line("cfg5 TTA x6 (decode+NMS) + map-back + WBF", best(tta, 2), 2)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg4", "cfg5", "zerocopy"]
+    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg4", "cfg5", "zerocopy", "cpu"]
     torch.cuda.set_device(0)
     for w in which:
         print(f"==== {w}", flush=True)
