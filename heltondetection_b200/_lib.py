@@ -62,6 +62,9 @@ SIGNATURES = {
     "hd_rpn_decode": (_i, [C.POINTER(RpnLevel), _i, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "hd_rpn_select_nms_workspace_size": (_sz, [_i, _i, _i]),
     "hd_rpn_select_nms": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hd_rpn_set_mode": (_i, [_i]),
+    "hd_rpn_cluster_capacity": (_i, [_i]),
+    "hd_rpn_set_cluster_size": (_i, [_i]),
     "hd_rpn_proposals_workspace_size": (_sz, [_i, _i, _i]),
     "hd_rpn_proposals": (_i, [C.POINTER(RpnLevel), _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hd_wbf_workspace_size": (_sz, [_i, _i, _i, _i]),

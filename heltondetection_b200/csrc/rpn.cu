@@ -4,6 +4,8 @@
 // models/detection/rpn.py:231-297, _utils.py:183-224).
 #include "hd_sort.cuh"
 #include "hd_nms_core.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 #define RPN_NT 1024
 #define RPN_U 8   // keys in flight per thread in the latency-bound scans over the N proposals of an image
@@ -101,6 +103,7 @@ struct RpnSelParams {
     int cap;           // per-image workspace stride (>= min(n_pre, N))
     uint64_t* k0; uint64_t* k1; uint32_t* v0; uint32_t* v1; float4* sbox; int* keep_r; float4* gitem;
     int sort_off, bitonic_cap;  // dynamic smem: word offset and capacity (keys) of the in-smem sort area
+    const int* only;            // nullable: run only the images whose flag is set (fallback pass behind the cluster kernel)
 };
 
 __device__ __forceinline__ uint64_t rpn_composite(uint32_t key, int idx) { return ((uint64_t)key << 32) | (uint32_t)(~(uint32_t)idx); }
@@ -116,6 +119,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.x;
+    if (p.only && p.only[b] == 0) return;
     const uint32_t* __restrict__ keys = p.keys + (size_t)b * p.N;
     const size_t off = (size_t)b * p.cap;
     uint64_t* k0 = p.k0 + off; uint64_t* k1 = p.k1 + off;
@@ -333,6 +337,566 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     HD_PHASE(6);
 }
 
+// ------------------------------------------------------------------------------------------------
+// select + sort + NMS spread over a thread-block CLUSTER: 8 CTAs (8 SMs) per image instead of one.
+//   S. radix select of the k-th largest 32-bit score key: every CTA histograms its 1/8 slice of the keys (held in
+//      shared memory after one global read), the 8 histograms are summed through distributed shared memory (DSMEM);
+//      ties on the threshold key go to the lowest indices (stable-sort rule) by giving each CTA a quota of them.
+//   C. ordered compaction of the selected set (index order kept) as unique composites (~key << 32 | index).
+//   M. each CTA bitonic-sorts an even 1/8 slice of the composites in registers/shared memory; the final rank of an
+//      element is the sum of its lower bounds in the 8 sorted slices (binary searches in a shared-memory copy).
+//   N. greedy NMS as a DAG problem: the spatial hash of hd_nms_core.cuh is built cooperatively (per-CTA bucket
+//      counts combined over DSMEM), every CTA then lists, for its boxes j, the higher-ranked boxes i with
+//      IoU(i,j) > thr (<= RPNC_ADJ of them, else the image is flagged for the single-CTA kernel), and CTA 0
+//      resolves  kept[j] = !any(kept[i], i in adj[j])  1024 ranks at a time by Jacobi iteration to the unique
+//      fixed point (= the greedy answer), stopping at n_post keeps.
+// Bit-identical outputs to rpn_select_nms_kernel (same selection rule, same IoU predicate).
+// ------------------------------------------------------------------------------------------------
+#define RPNC_MAXCL 8       // CTAs per image: 1, 2, 4 or 8 (the portable cluster maximum), chosen per launch
+#define RPNC_MAXN 16384    // n_pre limit: the merge step holds all composites in shared memory (128 KB)
+#define RPNC_ADJ 64        // suppressor candidates stored per box
+#define RPNC_LOG2T 12
+#define RPNC_T (1 << RPNC_LOG2T)
+#define RPNC_NCLS 64
+
+// size class of a (positive) area: its binary exponent, clamped; monotone in the area
+__device__ __forceinline__ int rpnc_class(float area) { return min(max((__float_as_int(area) >> 23) - 127 + 16, 0), RPNC_NCLS - 1); }
+// 1 / cell size of class c: cell = 2^((c-16)/2) = the side of the smallest square box of the class
+__device__ __forceinline__ float rpnc_inv_cell(int c) { return exp2f(-0.5f * (float)(c - 16)); }
+__device__ __forceinline__ uint32_t rpnc_hash(int gx, int gy, int c) {
+    return ((((uint32_t)gx * 0x9E3779B1u) ^ ((uint32_t)gy * 0x85EBCA77u) ^ ((uint32_t)c * 0x27D4EB2Fu)) * 0xC2B2AE3Du) >> (32 - RPNC_LOG2T);
+}
+
+struct RpnClParams {
+    RpnSelParams s;
+    uint64_t* comp;      // [B,cap] compacted composites (index order)
+    uint64_t* sorted;    // [B,cap] 8 sorted slices
+    uint32_t* order;     // [B,cap] rank -> proposal index
+    float4* gbox;        // [B,cap] boxes bucket by bucket
+    int* grank;          // [B,cap] their ranks
+    int* adj_cnt;        // [B,cap]
+    unsigned short* adj; // [B,cap,RPNC_ADJ]
+    int* fallback;       // [B] set when an adjacency list overflows
+    int per;             // keys per CTA slice
+    int key_cache;       // 1: the slice is held in shared memory
+    int cen_off, irk_off, acnt_off, queue_off, queue_cap;   // dynamic shared memory layout of the adjacency phase (bytes..., entries)
+};
+
+__global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_cluster_kernel(const __grid_constant__ RpnClParams q) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ int s_hist[2][256];
+    __shared__ int s_tot[256];
+    __shared__ int s_wsum[RPN_NT / 32];
+    __shared__ int s_cnt[2];
+    __shared__ float s_cinv[RPNC_NCLS], s_cgx[RPNC_NCLS], s_cgy[RPNC_NCLS];
+    __shared__ uint32_t s_kept[RPNC_MAXN / 32 + 64];   // resolve state of CTA 0: bitmap over ranks
+    __shared__ int s_done;
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_need, s_base[2], s_total;
+
+    cg::cluster_group cluster = cg::this_cluster();
+    const RpnSelParams& p = q.s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int crank = (int)cluster.block_rank();
+    const int CL = (int)cluster.num_blocks();
+    const int b = blockIdx.x / CL;
+    const size_t off = (size_t)b * p.cap;
+    const uint32_t* __restrict__ gkeys = p.keys + (size_t)b * p.N;
+    const int lo = min(crank * q.per, p.N), cntl = min(p.N, lo + q.per) - lo;   // this CTA's slice of the keys
+    uint32_t* kcache = reinterpret_cast<uint32_t*>(dsm);
+    if (q.key_cache) {
+        for (int i = tid; i < cntl; i += RPN_NT) kcache[i] = gkeys[lo + i];
+        __syncthreads();
+    }
+    auto KEY = [&](int il) -> uint32_t { return q.key_cache ? kcache[il] : gkeys[lo + il]; };
+
+    HD_PHASE(0);
+    // ---- S: radix select on the 32-bit key, one byte per pass, histograms summed over the cluster
+    auto scan_hist = [&](int pass, int sh, uint32_t prefix, uint32_t himask) {
+        int* h = s_hist[pass & 1];
+        if (tid < 256) h[tid] = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < cntl; i0 += RPN_NT) {
+            const int il = i0 + tid;
+            const uint32_t key = (il < cntl) ? KEY(il) : 0u;
+            int dg = 256 + lane;
+            if (key != 0u && ((key ^ prefix) & himask) == 0u) dg = (int)((key >> sh) & 255u);
+            const unsigned act = __ballot_sync(HD_FULL, dg < 256);
+            if (act) {
+                const int d0 = __shfl_sync(HD_FULL, dg, __ffs(act) - 1);
+                const unsigned same = __ballot_sync(HD_FULL, dg == d0);
+                if (dg == d0) { if ((same & hd_lanemask_lt()) == 0u) atomicAdd(&h[d0], __popc(same)); }
+                else if (dg < 256) atomicAdd(&h[dg], 1);
+            }
+        }
+        __syncthreads();
+        cluster.sync();
+        if (tid < 256) {
+            int t = 0;
+            for (int c = 0; c < CL; ++c) t += cluster.map_shared_rank(h, c)[tid];
+            s_tot[tid] = t;
+        }
+        __syncthreads();
+    };
+    scan_hist(0, 24, 0u, 0u);
+    if (tid == 0) {
+        int v = 0;
+        for (int d = 0; d < 256; ++d) v += s_tot[d];
+        s_total = v;
+    }
+    __syncthreads();
+    const int valid = s_total;
+    const int k = min((p.n_pre > 0) ? min(p.n_pre, valid) : valid, p.cap);
+    if (k == 0) {
+        if (crank == 0) {
+            for (int r = tid; r < p.n_post; r += RPN_NT) {
+                float* o = p.out_rois + ((size_t)b * p.n_post + r) * 5;
+                o[0] = (float)b; o[1] = o[2] = o[3] = o[4] = 0.0f;
+                if (p.out_scores) p.out_scores[(size_t)b * p.n_post + r] = 0.0f;
+                if (p.out_idx) p.out_idx[(size_t)b * p.n_post + r] = -1;
+            }
+            if (tid == 0) p.out_count[b] = 0;
+        }
+        cluster.sync();   // nobody leaves while its histogram may still be read
+        return;
+    }
+    uint32_t Tkey = 0u;   // selected: key > Tkey, plus the `need` lowest-index elements with key == Tkey
+    int need = 0;
+    if (k < valid) {
+        if (tid == 0) { s_need = k; s_prefix = 0u; }
+        __syncthreads();
+        for (int byte = 3; byte >= 0; --byte) {
+            const int sh = byte * 8;
+            if (byte < 3) scan_hist(3 - byte, sh, s_prefix, ~0u << (sh + 8));
+            if (tid == 0) {
+                int nd = s_need, d = 255;
+                for (; d > 0; --d) {
+                    if (s_tot[d] >= nd) break;
+                    nd -= s_tot[d];
+                }
+                s_need = nd;
+                s_prefix |= ((uint32_t)d << sh);
+            }
+            __syncthreads();
+        }
+        Tkey = s_prefix;
+        need = s_need;
+    }
+    HD_PHASE(1);
+    // ---- C: ordered compaction.  Per-CTA counts -> every CTA derives its output base and its quota of threshold ties
+    {
+        int cg_ = 0, ce = 0;
+        for (int il = tid; il < cntl; il += RPN_NT) {
+            const uint32_t key = KEY(il);
+            cg_ += (key > Tkey);
+            ce += (key == Tkey && key != 0u);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { cg_ += __shfl_xor_sync(HD_FULL, cg_, d); ce += __shfl_xor_sync(HD_FULL, ce, d); }
+        if (lane == 0) { s_wsum[wid] = cg_; s_hist[0][wid] = ce; }   // (the select histograms are dead by now)
+        __syncthreads();
+        if (tid == 0) {
+            int g = 0, e = 0;
+            for (int w = 0; w < RPN_NT / 32; ++w) { g += s_wsum[w]; e += s_hist[0][w]; }
+            s_cnt[0] = g; s_cnt[1] = e;
+        }
+    }
+    cluster.sync();
+    int out_base = 0, quota = 0;
+    {
+        int eq_before = 0;
+        for (int c = 0; c < CL; ++c) {
+            const int* rc = cluster.map_shared_rank(s_cnt, c);
+            const int g = rc[0], e = rc[1];
+            const int qc = min(max(need - eq_before, 0), e);
+            if (c < crank) out_base += g + qc;
+            if (c == crank) quota = qc;
+            eq_before += e;
+        }
+    }
+    uint64_t* comp = q.comp + off;
+    if (tid == 0) { s_base[0] = 0; s_base[1] = 0; }
+    __syncthreads();
+    for (int i0 = 0; i0 < cntl; i0 += RPN_U * RPN_NT) {
+        const int ib = i0 + RPN_U * tid;   // RPN_U consecutive keys per thread
+        uint32_t kk[RPN_U];
+        int cgt = 0, ceq = 0;
+#pragma unroll
+        for (int u = 0; u < RPN_U; ++u) {
+            kk[u] = (ib + u < cntl) ? KEY(ib + u) : 0u;
+            cgt += (kk[u] > Tkey);
+            ceq += (kk[u] == Tkey && kk[u] != 0u);
+        }
+        const int mine = cgt | (ceq << 16);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        int pre = incl - mine;
+        for (int w = 0; w < wid; ++w) pre += s_wsum[w];
+        int gb = s_base[0] + (pre & 0xffff), eb = s_base[1] + (pre >> 16);
+        const int tot = pre + mine;
+#pragma unroll
+        for (int u = 0; u < RPN_U; ++u) {
+            const bool gt = kk[u] > Tkey, eq = (kk[u] == Tkey && kk[u] != 0u);
+            if (gt || (eq && eb < quota)) {
+                const int pos = out_base + gb + min(eb, quota);
+                if (pos < p.cap) comp[pos] = ((unsigned long long)(~kk[u]) << 32) | (uint32_t)(lo + ib + u);
+            }
+            gb += gt; eb += eq;
+        }
+        __syncthreads();
+        if (tid == RPN_NT - 1) { s_base[0] += tot & 0xffff; s_base[1] += tot >> 16; }
+        __syncthreads();
+    }
+    cluster.sync();
+    HD_PHASE(2);
+    // ---- M: slice sort + merge ranks
+    const int n = k;
+    const int m = (n + CL - 1) / CL;                           // <= 8192 (host check)
+    const int slo = min(crank * m, n), slen = min(n, slo + m) - slo;
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(dsm);
+    const int Np = hd_bitonic_padded(m);
+    for (int i = tid; i < Np; i += RPN_NT) skey[i] = (i < slen) ? comp[slo + i] : ~0ull;
+    __syncthreads();
+    if (Np == 2048) hd_cta_bitonic_reg<2, false>(skey, nullptr);
+    else if (Np == 4096) hd_cta_bitonic_reg<4, false>(skey, nullptr);
+    else hd_cta_bitonic_reg<8, false>(skey, nullptr);
+    uint64_t* sorted = q.sorted + off;
+    for (int i = tid; i < slen; i += RPN_NT) sorted[slo + i] = skey[i];
+    cluster.sync();
+    for (int i = tid; i < n; i += RPN_NT) skey[i] = sorted[i];
+    __syncthreads();
+    uint32_t* order = q.order + off;
+    float4* sbox = p.sbox + off;
+    const float4* __restrict__ boxes = p.boxes + (size_t)b * p.N;
+    for (int i = tid; i < slen; i += RPN_NT) {
+        const unsigned long long v = skey[slo + i];
+        int rank = i;                                          // lower bound in the own slice
+        for (int c = 0; c < CL; ++c) {
+            if (c == crank) continue;
+            int a = min(c * m, n), z = min(n, a + m);          // lower bound of v in slice c
+            const int a0 = a;
+            while (a < z) { const int mid = (a + z) >> 1; if (skey[mid] < v) a = mid + 1; else z = mid; }
+            rank += a - a0;
+        }
+        const uint32_t idx = (uint32_t)v;
+        order[rank] = idx;
+        sbox[rank] = boxes[idx];
+    }
+    cluster.sync();
+    HD_PHASE(3);
+    // ---- N: greedy NMS in rank batches.  Only the ranks up to the n_post-th keep matter, so the first batch covers the
+    // top max(2 n_post, 128 CL) ranks and the second (rarely needed) the rest.  Per batch [lo_r, hi_r):
+    //   N1  size-stratified spatial hash over the ranks < hi_r, built cooperatively: a proper box of area a belongs to
+    //       class c = exponent(a) and is hashed by (centre / 2^(c/2), c) -- cells scale with the boxes they hold, so a
+    //       query touches a handful of cells whatever the box size;
+    //   N2  adjacency lists of the ranks in [lo_r, hi_r), an even share per CTA;
+    //   N3  CTA 0 resolves them 1024 ranks at a time and tells the cluster whether it is done.
+    // Class tables (max width/height per class -> growth of the query window) come from a reduction over all n boxes
+    // that every CTA runs itself (max is order independent -> identical in all CTAs).
+    int* s_cw = s_hist[0];   // [RPNC_NCLS] max width per class (float bits), the select histograms are dead
+    int* s_ch = s_hist[1];
+    for (int i = tid; i < RPNC_NCLS; i += RPN_NT) { s_cw[i] = 0; s_ch[i] = 0; }
+    if (tid == 0) s_total = 0;
+    for (int i = tid; i < (n + 31) / 32 + 33; i += RPN_NT) s_kept[i] = 0u;
+    __syncthreads();
+    {
+        float cmax = 0.f;
+        for (int r = tid; r < n; r += RPN_NT) {
+            const float4 bx = sbox[r];
+            if (hd_box_proper(bx)) {
+                const int c = rpnc_class(hd_area(bx));
+                atomicMax(&s_cw[c], __float_as_int(bx.z - bx.x));   // positive floats order like their bit patterns
+                atomicMax(&s_ch[c], __float_as_int(bx.w - bx.y));
+                cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(bx.x), fabsf(bx.y)), fmaxf(fabsf(bx.z), fabsf(bx.w))));
+            }
+        }
+        atomicMax(&s_total, __float_as_int(cmax));
+    }
+    __syncthreads();
+    const float slack = 5.0e-7f * __int_as_float(s_total);
+    const float grow = fmaxf(0.0f, 0.5f - (p.thr - 1.0e-3f));
+    const float tq = p.thr - 1.0e-3f;
+    if (tid < RPNC_NCLS) {   // per-class query tables (inverse cell size, window growth); 0 marks an empty class
+        const float wc = __int_as_float(s_cw[tid]), hc = __int_as_float(s_ch[tid]);
+        s_cinv[tid] = (wc > 0.0f) ? rpnc_inv_cell(tid) : 0.0f;
+        s_cgx[tid] = grow * wc + slack; s_cgy[tid] = grow * hc + slack;
+    }
+    int* start = reinterpret_cast<int*>(dsm);                                  // [T+1] bucket starts (cluster-wide)
+    int* hist = reinterpret_cast<int*>(dsm + q.queue_off);                     // [T] per-CTA counts, then scatter cursors (dead before the queue is used)
+    float2* cen = reinterpret_cast<float2*>(dsm + q.cen_off);                  // [items] centres, bucket by bucket
+    unsigned short* irk = reinterpret_cast<unsigned short*>(dsm + q.irk_off);  // [items] their ranks
+    int* acnt = reinterpret_cast<int*>(dsm + q.acnt_off);                      // [RPN_NT] list lengths of the round's boxes
+    uint32_t* queue = reinterpret_cast<uint32_t*>(dsm + q.queue_off);
+    int* grank = q.grank + off;
+    float4* gbox = q.gbox + off;
+    unsigned short* adj = q.adj + off * RPNC_ADJ;
+    int* adj_cnt = q.adj_cnt + off;
+    int* keep_r = p.keep_r + off;
+    // per-warp queue segments and counters (a single CTA-wide counter would serialise ~10^4 shared-memory atomics per round)
+    const int segcap = q.queue_cap / (RPN_NT / 32);
+    uint32_t* myq = queue + wid * segcap;
+    int* s_qn = s_wsum;            // [32] entries queued by each warp
+    int* s_qpre = s_tot;           // [33] their exclusive prefix
+    // cells of class c under the query window of box bq: origin (x1,y1), nx columns; returns the cell count
+    auto window = [&](const float4 bq, int c, int& x1, int& y1, int& nx, float& lx, float& hx, float& ly, float& hy) -> int {
+        const float inv = s_cinv[c];
+        if (inv == 0.0f) return 0;
+        lx = bq.x - s_cgx[c]; hx = bq.z + s_cgx[c]; ly = bq.y - s_cgy[c]; hy = bq.w + s_cgy[c];
+        x1 = hd_cell(lx, inv); y1 = hd_cell(ly, inv);
+        const long long dx = (long long)hd_cell(hx, inv) - x1 + 1, dy = (long long)hd_cell(hy, inv) - y1 + 1;
+        if (dx * dy > 1024) { q.fallback[b] = 1; return 0; }   // low thresholds / degenerate geometry: single-CTA kernel
+        nx = (int)dx;
+        return (int)(dx * dy);
+    };
+    // exact test of box j (rank jr, round slot bl) against the higher-ranked box i (rank ir)
+    auto exact = [&](int bl, int jr, const float4 bq, int ir, const float4 bi) {
+        const float aq = hd_area(bq), ai = hd_area(bi);
+        const float amin = tq * aq, amax = (tq > 0.0f) ? aq / tq : 3.0e38f;
+        if (ai < amin || ai > amax) return;
+        const float cx = 0.5f * (bi.x + bi.z), cy = 0.5f * (bi.y + bi.w);
+        const float gx = grow * (bi.z - bi.x) + slack, gy = grow * (bi.w - bi.y) + slack;
+        if (cx < bq.x - gx || cx > bq.z + gx || cy < bq.y - gy || cy > bq.w + gy) return;
+        if (hd_iou_gt(bi, ai, bq, aq, p.thr)) {
+            const int slot = atomicAdd(&acnt[bl], 1);
+            if (slot < RPNC_ADJ) adj[(size_t)jr * RPNC_ADJ + slot] = (unsigned short)ir;
+        }
+    };
+    int kc = 0;
+    const int first = max(2 * p.n_post, 128 * CL);
+    for (int lo_r = 0, hi_r = min(n, first);; lo_r = hi_r, hi_r = n) {
+        HD_PHASE(3);
+        // ---- N1
+        for (int i = tid; i < RPNC_T; i += RPN_NT) hist[i] = 0;
+        __syncthreads();
+        const int mg = (hi_r + CL - 1) / CL, glo = min(crank * mg, hi_r), glen = min(hi_r, glo + mg) - glo;
+        for (int i = tid; i < glen; i += RPN_NT) {
+            const float4 bx = sbox[glo + i];
+            if (hd_box_proper(bx)) {
+                const int c = rpnc_class(hd_area(bx));
+                const float inv = rpnc_inv_cell(c);
+                atomicAdd(&hist[rpnc_hash(hd_cell(0.5f * (bx.x + bx.z), inv), hd_cell(0.5f * (bx.y + bx.w), inv), c)], 1);
+            }
+        }
+        __syncthreads();
+        cluster.sync();
+        {
+            constexpr int PER = RPNC_T / RPN_NT;   // consecutive buckets per thread
+            static_assert(PER == 4, "one int4 of buckets per thread");
+            int tot[PER], myoff[PER];
+            int loc = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { tot[j] = 0; myoff[j] = 0; }
+            for (int c = 0; c < CL; ++c) {
+                const int4 v = reinterpret_cast<const int4*>(cluster.map_shared_rank(hist, c))[tid];
+                tot[0] += v.x; tot[1] += v.y; tot[2] += v.z; tot[3] += v.w;
+                if (c < crank) { myoff[0] += v.x; myoff[1] += v.y; myoff[2] += v.z; myoff[3] += v.w; }
+            }
+#pragma unroll
+            for (int j = 0; j < PER; ++j) loc += tot[j];
+            int incl = loc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
+            if (lane == 31) s_wsum[wid] = incl;
+            cluster.sync();   // every CTA has read every histogram: they may now be overwritten with cursors
+            int pre = incl - loc;
+            for (int w = 0; w < wid; ++w) pre += s_wsum[w];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int h = tid * PER + j;
+                start[h] = pre; hist[h] = pre + myoff[j]; pre += tot[j];
+            }
+            if (tid == RPN_NT - 1) start[RPNC_T] = pre;
+        }
+        __syncthreads();
+        for (int i = tid; i < glen; i += RPN_NT) {
+            const float4 bx = sbox[glo + i];
+            if (hd_box_proper(bx)) {
+                const int c = rpnc_class(hd_area(bx));
+                const float inv = rpnc_inv_cell(c);
+                const int pos = atomicAdd(&hist[rpnc_hash(hd_cell(0.5f * (bx.x + bx.z), inv), hd_cell(0.5f * (bx.y + bx.w), inv), c)], 1);
+                gbox[pos] = bx; grank[pos] = glo + i;
+            }
+        }
+        cluster.sync();
+        HD_PHASE(4);
+        // ---- N2: box j looks for the higher-ranked boxes i with iou(i,j) > thr:
+        //   iou > t  =>  centre_i inside box_j grown by max(0, .5 - t) * (w_i, h_i),  and  area_i in [t * area_j, area_j / t],
+        // i.e. the 3 (t = 0.7) size classes around j's own, a handful of cells each.  Phase A: a lane owns one box of the
+        // round; the (box, cell) pairs of the warp's 32 boxes are dealt out to the lanes (prefix sums + a shuffle binary
+        // search), so every lane visits one cell per step whatever the box sizes; item centres and ranks sit in shared
+        // memory bucket by bucket; survivors of the centre and rank tests go to per-warp queues.  Phase B drains the
+        // queues with all threads: exact test on the full boxes (balanced, several loads in flight), hits appended to
+        // j's list through a shared-memory counter.
+        const int nitem = start[RPNC_T];
+        for (int i = tid; i < nitem; i += RPN_NT) {
+            const float4 bx = gbox[i];
+            cen[i] = make_float2(0.5f * (bx.x + bx.z), 0.5f * (bx.y + bx.w));
+            irk[i] = (unsigned short)grank[i];
+        }
+        const int ma = (hi_r - lo_r + CL - 1) / CL, slo = min(lo_r + crank * ma, hi_r), slen = min(hi_r, slo + ma) - slo;
+        for (int b0 = 0; b0 < slen; b0 += RPN_NT) {
+            const int nb = min(RPN_NT, slen - b0);
+            if (tid < RPN_NT / 32) s_qn[tid] = 0;
+            acnt[tid] = 0;
+            __syncthreads();
+            const int jr = slo + b0 + tid;
+            float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid < nb) bq = sbox[jr];
+            int ncell = 0;
+            if (tid < nb && jr > 0 && hd_box_proper(bq)) {
+                const float aq = hd_area(bq);
+                const int c0 = rpnc_class(tq * aq), c1 = rpnc_class((tq > 0.0f) ? aq / tq : 3.0e38f);
+                for (int c = c0; c <= c1; ++c) { int x1, y1, nx; float lx, hx, ly, hy; ncell += window(bq, c, x1, y1, nx, lx, hx, ly, hy); }
+            }
+            int incl = ncell;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
+            const int pre = incl - ncell, total = __shfl_sync(HD_FULL, incl, 31);
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                int src = 0;                                       // largest lane whose prefix is <= t
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) { const int v = __shfl_sync(HD_FULL, pre, src + d); if (v <= t) src += d; }
+                int local = t - __shfl_sync(HD_FULL, pre, src);
+                float4 bs;
+                bs.x = __shfl_sync(HD_FULL, bq.x, src); bs.y = __shfl_sync(HD_FULL, bq.y, src);
+                bs.z = __shfl_sync(HD_FULL, bq.z, src); bs.w = __shfl_sync(HD_FULL, bq.w, src);
+                if (t >= total) continue;
+                const int sbl = (wid << 5) + src, sjr = slo + b0 + sbl;
+                const float aq = hd_area(bs);
+                const int c1 = rpnc_class((tq > 0.0f) ? aq / tq : 3.0e38f);
+                int c = rpnc_class(tq * aq), x1 = 0, y1 = 0, nx = 1;
+                float lx = 0.f, hx = 0.f, ly = 0.f, hy = 0.f;
+                for (; c <= c1; ++c) {
+                    const int nc2 = window(bs, c, x1, y1, nx, lx, hx, ly, hy);
+                    if (local < nc2) break;
+                    local -= nc2;
+                }
+                if (c > c1) continue;                              // (cannot happen: the counts are recomputed identically)
+                const int gy = local / nx, gx = local - gy * nx;
+                const uint32_t hb = rpnc_hash(x1 + gx, y1 + gy, c);
+                const int s1 = start[hb + 1];
+                for (int kk = start[hb]; kk < s1; ++kk) {
+                    const float2 ce = cen[kk];
+                    if (ce.x < lx || ce.x > hx || ce.y < ly || ce.y > hy) continue;   // also rejects most hash collisions
+                    const int ir = irk[kk];
+                    if (ir >= sjr) continue;                                           // only higher-ranked boxes suppress
+                    const int slot = atomicAdd(&s_qn[wid], 1);
+                    if (slot < segcap) myq[slot] = ((uint32_t)sbl << 16) | (uint32_t)kk;
+                    else exact(sbl, sjr, bs, ir, gbox[kk]);
+                }
+            }
+            __syncthreads();
+            if (tid < 32) {
+                const int c = min(s_qn[tid], segcap);
+                int in2 = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, in2, d); if (lane >= d) in2 += y; }
+                s_qpre[tid] = in2 - c;
+                if (tid == 31) s_qpre[32] = in2;
+            }
+            __syncthreads();
+            const int nq = s_qpre[32];
+            for (int e0 = 0; e0 < nq; e0 += 2 * RPN_NT) {
+                int bl[2], ir[2]; float4 bb[2], bi[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int e = e0 + u * RPN_NT + tid;
+                    bl[u] = -1;
+                    if (e < nq) {
+                        int w = 0;                           // segment holding entry e
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) if (s_qpre[w + d] <= e) w += d;
+                        const uint32_t en = queue[w * segcap + (e - s_qpre[w])];
+                        bl[u] = (int)(en >> 16);
+                        const int pos = (int)(en & 0xffffu);
+                        ir[u] = irk[pos];
+                        bb[u] = sbox[slo + b0 + bl[u]]; bi[u] = gbox[pos];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) if (bl[u] >= 0) exact(bl[u], slo + b0 + bl[u], bb[u], ir[u], bi[u]);
+            }
+            __syncthreads();
+            if (tid < nb) {
+                const int c = acnt[tid];
+                adj_cnt[slo + b0 + tid] = min(c, RPNC_ADJ);
+                if (c > RPNC_ADJ) q.fallback[b] = 1;
+            }
+            __syncthreads();
+        }
+        cluster.sync();
+        HD_PHASE(5);
+        // ---- N3: CTA 0 resolves  kept[j] = !any(kept[i], i in adj[j])  1024 ranks at a time (Jacobi iteration to the
+        // unique fixed point = the greedy answer) and pushes "done" into every CTA of the cluster
+        if (crank == 0) {
+            int done = (hi_r >= n) ? 1 : 0;
+            if (*(volatile int*)&q.fallback[b]) done = 2;   // the single-CTA kernel redoes this image
+            for (int base = lo_r; done != 2 && base < hi_r && kc < p.n_post; base += RPN_NT) {
+                const int j = base + tid;
+                const bool in = j < hi_r;
+                const int cnt = in ? adj_cnt[j] : 0;
+                const unsigned short* lst = adj + (size_t)j * RPNC_ADJ;
+                const int wi = (base >> 5) + wid;
+                {
+                    const unsigned w0 = __ballot_sync(HD_FULL, in);
+                    if (lane == 0) s_kept[wi] = w0;
+                }
+                __syncthreads();
+                for (;;) {
+                    bool nk = in;
+                    for (int e = 0; e < cnt; ++e) {
+                        const int i = lst[e];
+                        if ((s_kept[i >> 5] >> (i & 31)) & 1u) { nk = false; break; }
+                    }
+                    const unsigned w1 = __ballot_sync(HD_FULL, nk);
+                    const bool ch = (w1 != s_kept[wi]);
+                    __syncthreads();
+                    if (lane == 0) s_kept[wi] = w1;
+                    if (!__syncthreads_or(ch)) break;
+                }
+                const unsigned wv = s_kept[wi];
+                if (lane == 0) s_wsum[wid] = __popc(wv);
+                __syncthreads();
+                int pre = kc, tot2 = kc;
+                for (int w = 0; w < RPN_NT / 32; ++w) { if (w < wid) pre += s_wsum[w]; tot2 += s_wsum[w]; }
+                if ((wv >> lane) & 1u) {
+                    const int pos = pre + __popc(wv & hd_lanemask_lt());
+                    if (pos < p.n_post) keep_r[pos] = j;
+                }
+                kc = min(tot2, p.n_post);
+                __syncthreads();
+            }
+            if (kc >= p.n_post && done == 0) done = 1;
+            if (tid < CL) *cluster.map_shared_rank(&s_done, tid) = done;
+        }
+        cluster.sync();
+        if (s_done) break;
+    }
+    if (crank != 0 || s_done == 2) return;
+    HD_PHASE(6);
+    for (int r = tid; r < p.n_post; r += RPN_NT) {
+        float* o = p.out_rois + ((size_t)b * p.n_post + r) * 5;
+        o[0] = (float)b;
+        if (r < kc) {
+            const int rr = keep_r[r];
+            const float4 bx = sbox[rr];
+            o[1] = bx.x; o[2] = bx.y; o[3] = bx.z; o[4] = bx.w;
+            if (p.out_scores) p.out_scores[(size_t)b * p.n_post + r] = p.scores[(size_t)b * p.N + order[rr]];
+            if (p.out_idx) p.out_idx[(size_t)b * p.n_post + r] = (long long)order[rr];
+        } else {
+            o[1] = o[2] = o[3] = o[4] = 0.0f;
+            if (p.out_scores) p.out_scores[(size_t)b * p.n_post + r] = 0.0f;
+            if (p.out_idx) p.out_idx[(size_t)b * p.n_post + r] = -1;
+        }
+    }
+    if (tid == 0) p.out_count[b] = kc;
+    HD_PHASE(7);
+}
+
 // ------------------------------------------------------------------------------------------------ host
 static int rpn_fill(RpnParams& p, const hd_rpn_level* levels, int n_levels, int B, int A, int flags, float img_h, float img_w,
                     float min_size, float clamp_dwh) {
@@ -381,6 +945,8 @@ extern "C" HD_API int hd_rpn_decode(const hd_rpn_level* levels, int n_levels, in
     return HD_OK;
 }
 
+#define RPN_WS_PARTS 11
+static bool rpn_cluster_ok(int cap) { return cap <= RPNC_MAXN; }
 static void rpn_ws_layout(int B, int cap, size_t* offs, size_t* total) {
     size_t n = (size_t)B * cap, o = 0;
     offs[0] = o; o = hd_align_up(o + n * 8, 256);
@@ -390,12 +956,39 @@ static void rpn_ws_layout(int B, int cap, size_t* offs, size_t* total) {
     offs[4] = o; o = hd_align_up(o + n * 16, 256);
     offs[5] = o; o = hd_align_up(o + n * 4, 256);
     offs[6] = o; o = hd_align_up(o + n * 16, 256);
+    // cluster kernel only: bucket ranks, adjacency counts + lists, per-image fallback flags
+    const size_t nc = rpn_cluster_ok(cap) ? n : 0;
+    offs[7] = o; o = hd_align_up(o + nc * 4, 256);
+    offs[8] = o; o = hd_align_up(o + nc * 4, 256);
+    offs[9] = o; o = hd_align_up(o + nc * RPNC_ADJ * 2, 256);
+    offs[10] = o; o = hd_align_up(o + (size_t)B * 4, 256);
     *total = o;
 }
+static int rpn_cluster_capacity(int CL) {
+    // how many CL-CTA clusters of the stage-2 kernel the device holds at once (1 CTA per SM: 1024 threads x 64 registers)
+    static int cached[RPNC_MAXCL + 1] = {0};
+    if (cached[CL]) return cached[CL];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(RPN_NT); cfg.dynamicSmemBytes = 200 * 1024;
+    cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int nc = 0;
+    cudaFuncSetAttribute(rpn_select_nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (cudaOccupancyMaxActiveClusters(&nc, rpn_select_nms_cluster_kernel, &cfg) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = HD_NUM_SMS / CL; }
+    return cached[CL] = nc;
+}
+extern "C" HD_API int hd_rpn_cluster_capacity(int cluster_size) {
+    if (cluster_size != 1 && cluster_size != 2 && cluster_size != 4 && cluster_size != 8) return -1;
+    return rpn_cluster_capacity(cluster_size);
+}
+static int g_rpn_cluster = 0;   // 0: chosen per launch
+extern "C" HD_API int hd_rpn_set_cluster_size(int cl) { int old = g_rpn_cluster; g_rpn_cluster = (cl == 1 || cl == 2 || cl == 4 || cl == 8) ? cl : 0; return old; }
+static int g_rpn_mode = 0;   // 0 auto, 1 single CTA per image, 2 cluster (when eligible)
+extern "C" HD_API int hd_rpn_set_mode(int mode) { int old = g_rpn_mode; g_rpn_mode = mode; return old; }
 static int rpn_cap(int N, int n_pre) { return (n_pre > 0 && n_pre < N) ? n_pre : N; }
 
 extern "C" HD_API size_t hd_rpn_select_nms_workspace_size(int B, int N, int n_pre) {
-    size_t offs[7], total;
+    size_t offs[RPN_WS_PARTS], total;
     rpn_ws_layout(B < 0 ? 0 : B, rpn_cap(N < 0 ? 0 : N, n_pre), offs, &total);
     return total + 256;
 }
@@ -409,12 +1002,13 @@ extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores,
     HD_CHECK_ARG(out_rois && out_count, "null output");
     HD_CHECK_ARG(N == 0 || (boxes && scores && keys), "null input");
     const int cap = rpn_cap(N, n_pre) > 0 ? rpn_cap(N, n_pre) : 1;
-    size_t offs[7], total;
+    size_t offs[RPN_WS_PARTS], total;
     rpn_ws_layout(B, cap, offs, &total);
     uintptr_t w0 = hd_align_up((uintptr_t)workspace, 256);
     if (!workspace || w0 + total > (uintptr_t)workspace + workspace_bytes)
         HD_FAIL(HD_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", total + 256, workspace_bytes);
     RpnSelParams p;
+    p.only = nullptr;
     p.boxes = (const float4*)boxes; p.scores = scores; p.keys = keys; p.B = B; p.N = N; p.n_pre = n_pre; p.n_post = n_post;
     p.thr = hd_thr_floor(nms_iou);
     p.out_rois = out_rois; p.out_scores = out_scores; p.out_idx = (long long*)out_idx; p.out_count = out_count; p.cap = cap;
@@ -430,7 +1024,52 @@ extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores,
     static bool attr_set = false;
     if (!attr_set) {
         HD_CUDA_CALL(cudaFuncSetAttribute(rpn_select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 186 * 1024));
+        HD_CUDA_CALL(cudaFuncSetAttribute(rpn_select_nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
+    }
+    if (g_rpn_mode != 1 && rpn_cluster_ok(cap) && N > 0) {
+        // CL SMs per image; an image whose adjacency lists overflow is redone by the single-CTA kernel below.
+        // CL minimises waves * (serial + parallel / CL) with phase times measured on B200 (profiles/r1_results.md).
+        int CL = g_rpn_cluster;
+        if (!CL) {
+            double best = 1e30;
+            for (int c = RPNC_MAXCL; c >= 1; c >>= 1) {
+                if ((cap + c - 1) / c > 8192) continue;
+                const int capn = rpn_cluster_capacity(c);
+                const double t = (double)((B + capn - 1) / capn) * (60.0 + 800.0 / c);
+                if (t < best) { best = t; CL = c; }
+            }
+        }
+        while ((cap + CL - 1) / CL > 8192) CL <<= 1;
+        RpnClParams q;
+        q.s = p;
+        q.comp = p.k0; q.sorted = p.k1; q.order = p.v1; q.gbox = p.gitem;
+        q.grank = (int*)(w0 + offs[7]); q.adj_cnt = (int*)(w0 + offs[8]); q.adj = (unsigned short*)(w0 + offs[9]);
+        q.fallback = (int*)(w0 + offs[10]);
+        q.per = (int)(((size_t)(N + CL - 1) / CL + 3) & ~(size_t)3);
+        const size_t budget = 200 * 1024;
+        q.key_cache = ((size_t)q.per * 4 <= budget) ? 1 : 0;
+        const int mslice = (cap + CL - 1) / CL;
+        const size_t np = mslice <= 2048 ? 2048 : (mslice <= 4096 ? 4096 : 8192);
+        size_t sm_c = np * 8;                                           // slice sort
+        if (sm_c < (size_t)cap * 8) sm_c = (size_t)cap * 8;             // merge: all composites
+        if (q.key_cache && sm_c < (size_t)q.per * 4) sm_c = (size_t)q.per * 4;
+        q.cen_off = (int)hd_align_up(((size_t)RPNC_T + 1) * 4, 16);
+        q.irk_off = (int)hd_align_up((size_t)q.cen_off + (size_t)cap * 8, 16);
+        q.acnt_off = (int)hd_align_up((size_t)q.irk_off + (size_t)cap * 2, 16);
+        q.queue_off = (int)hd_align_up((size_t)q.acnt_off + (size_t)RPN_NT * 4, 16);
+        size_t want = (size_t)q.queue_off + 64 * 1024;                  // adjacency: buckets + centres + candidate queue
+        if (want > budget) want = budget;
+        if (want < (size_t)q.queue_off + (size_t)RPNC_T * 4) want = (size_t)q.queue_off + (size_t)RPNC_T * 4;
+        if (sm_c < want) sm_c = want;
+        q.queue_cap = (int)((sm_c - q.queue_off) / 4);
+        HD_CUDA_CALL(cudaMemsetAsync(q.fallback, 0, (size_t)B * 4, (cudaStream_t)stream));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * CL)); cfg.blockDim = dim3(RPN_NT); cfg.dynamicSmemBytes = sm_c; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        HD_CUDA_CALL(cudaLaunchKernelEx(&cfg, rpn_select_nms_cluster_kernel, q));
+        p.only = q.fallback;
     }
     rpn_select_nms_kernel<<<B, RPN_NT, smem, (cudaStream_t)stream>>>(p);
     HD_CUDA_LAUNCH_CHECK("rpn_select_nms_kernel");

@@ -21,6 +21,11 @@ def generate_anchor_base(base_size, ratios=(0.5, 1.0, 2.0), scales=(8.0,)):
     return out
 
 
+def set_mode(mode):
+    """stage-2 kernel choice: 0 auto, 1 one CTA per image, 2 cluster of 8 CTAs per image; returns the previous mode."""
+    return _lib.lib().hd_rpn_set_mode(int(mode))
+
+
 def _levels(objectness, deltas, anchor_bases, strides, softmax):
     n = len(deltas)
     if not (len(objectness) == n == len(anchor_bases) == len(strides)):

@@ -206,6 +206,14 @@ HD_API size_t hd_rpn_select_nms_workspace_size(int B, int N, int n_pre);
 HD_API int hd_rpn_select_nms(const float* boxes, const float* scores, const uint32_t* keys, int B, int N, int n_pre, int n_post,
                              double nms_iou, float* out_rois, float* out_scores, int64_t* out_idx, int32_t* out_count,
                              void* workspace, size_t workspace_bytes, void* stream);
+/* Stage 2 runs as one thread-block CLUSTER (8 SMs) per image when n_pre <= 16384, else as one CTA per image; both
+ * give bit-identical outputs.  hd_rpn_set_mode: 0 = automatic (default), 1 = force one CTA per image,
+ * 2 = cluster whenever eligible.  Returns the previous mode (process-wide; developer / test aid). */
+HD_API int hd_rpn_set_mode(int mode);
+/* number of clusters (of the given size) of the stage-2 kernel the current device holds at once (developer aid; -1 on error) */
+HD_API int hd_rpn_cluster_capacity(int cluster_size /* 1, 2, 4 or 8 */);
+/* force the cluster size of stage 2 (1, 2, 4, 8; 0 = chosen per launch from batch size and device capacity); returns the previous value */
+HD_API int hd_rpn_set_cluster_size(int cluster_size);
 /* both stages */
 HD_API size_t hd_rpn_proposals_workspace_size(int B, int N, int n_pre);
 HD_API int hd_rpn_proposals(const hd_rpn_level* levels /*host*/, int n_levels, int B, int A, int flags, float img_h, float img_w,

@@ -115,3 +115,67 @@ def test_proposal_creator_lineage_signature(cfg):
     # same fp32 scores in, decode by elementwise torch ops on the GPU (exp differs by ulps): compare sets
     want, got = set(ref_idx.tolist()), set(idx.cpu().tolist())
     assert len(want & got) / len(want) >= 0.99
+
+
+def _ref_select_nms(bx, sc, valid, n_pre, n_post, thr):
+    keep = torch.where(valid)[0]
+    order = torch.sort(sc[keep], descending=True, stable=True)[1]
+    if n_pre > 0:
+        order = order[:n_pre]
+    sel = keep[order]
+    k = torchvision.ops.nms(bx[sel], sc[sel], thr)[:n_post]
+    return sel[k]
+
+
+def _adversarial(seed, N, kind):
+    g = torch.Generator().manual_seed(seed)
+    xy = torch.rand(N, 2, generator=g) * 700
+    wh = torch.rand(N, 2, generator=g) * 120 + 8
+    bx = torch.cat((xy, xy + wh), 1)
+    sc = torch.rand(N, generator=g)
+    valid = torch.rand(N, generator=g) > 0.1
+    if kind == "ties":          # few distinct scores: the top-k cut and the sort fall inside big tie groups
+        sc = (sc * 7).floor() / 7
+    elif kind == "clusters":    # > RPNC_ADJ near-identical boxes per object: adjacency overflow -> single-CTA redo
+        c = torch.randint(0, 12, (N,), generator=g)
+        base = torch.rand(12, 4, generator=g) * 300
+        base[:, 2:] = base[:, :2] + 150 + base[:, 2:] * 0.2
+        bx = base[c] + torch.randn(N, 4, generator=g) * 1.5
+    elif kind == "degenerate":  # NaN / inverted / zero-area boxes can neither suppress nor be suppressed
+        bx[::7, 2] = bx[::7, 0]
+        bx[3::11, 3] = bx[3::11, 1] - 5
+        bx[5::13, 0] = float("nan")
+        sc[::97] = sc[1]
+    elif kind == "all_equal":
+        sc[:] = 0.5
+    return bx.contiguous(), sc.contiguous(), valid
+
+
+@pytest.mark.parametrize("kind", ["plain", "ties", "clusters", "degenerate", "all_equal"])
+@pytest.mark.parametrize("N,n_pre,n_post", [(20000, 6000, 1000), (5000, 0, 5000), (40000, 16384, 2000), (777, 300, 100)])
+def test_cluster_and_single_cta_kernels_bit_exact(kind, N, n_pre, n_post):
+    """explicit arrays through hd_rpn_select_nms: cluster kernel (mode 2) == single-CTA kernel (mode 1) == stable sort + torchvision nms"""
+    from heltondetection_b200 import rpn
+    B = 3
+    data = [_adversarial(100 + 7 * b + N, N, kind) for b in range(B)]
+    bx = torch.stack([d[0] for d in data]).cuda(); sc = torch.stack([d[1] for d in data]).cuda(); va = torch.stack([d[2] for d in data]).cuda()
+    from heltondetection_b200 import _lib
+    outs = {}
+    for mode, cl in ((1, 0), (2, 8), (2, 4), (2, 2), (2, 1)):
+        old = rpn.set_mode(mode)
+        _lib.lib().hd_rpn_set_cluster_size(cl)
+        try:
+            rois, osc, idx, cnt = rpn.select_nms(bx, sc, va, n_pre, n_post, 0.7)
+            outs[(mode, cl)] = (rois.cpu(), osc.cpu(), idx.cpu(), cnt.cpu())
+        finally:
+            rpn.set_mode(old)
+            _lib.lib().hd_rpn_set_cluster_size(0)
+    for key in outs:
+        for a, c in zip(outs[(1, 0)], outs[key]):
+            assert torch.equal(a, c) or (torch.isnan(a) == torch.isnan(c)).all() and torch.equal(torch.nan_to_num(a), torch.nan_to_num(c)), key
+    outs[2] = outs[(2, 8)]
+    for b in range(B):
+        ref = _ref_select_nms(data[b][0], data[b][1], data[b][2], n_pre, n_post, 0.7)
+        n = int(outs[2][3][b])
+        assert n == ref.numel()
+        assert torch.equal(outs[2][2][b, :n], ref)
