@@ -468,14 +468,23 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_cluster_kernel(const
         for (int byte = 3; byte >= 0; --byte) {
             const int sh = byte * 8;
             if (byte < 3) scan_hist(3 - byte, sh, s_prefix, ~0u << (sh + 8));
-            if (tid == 0) {
-                int nd = s_need, d = 255;
-                for (; d > 0; --d) {
-                    if (s_tot[d] >= nd) break;
-                    nd -= s_tot[d];
-                }
-                s_need = nd;
-                s_prefix |= ((uint32_t)d << sh);
+            // digit holding the s_need-th largest key: suffix sums of the 256 totals (8 warps), then the one thread whose
+            // suffix crosses s_need publishes the digit
+            int suf = 0, mine = 0;
+            if (tid < 256) {
+                mine = s_tot[tid];
+                suf = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_down_sync(HD_FULL, suf, d); if (lane + d < 32) suf += y; }
+                if (lane == 0) s_wsum[wid] = suf;
+            }
+            __syncthreads();
+            const int nd = s_need;
+            __syncthreads();
+            if (tid < 256) {
+                for (int w = wid + 1; w < 8; ++w) suf += s_wsum[w];      // suf = sum of totals of digits >= tid
+                const int above = suf - mine;                            // digits > tid
+                if (suf >= nd && above < nd) { s_need = nd - above; s_prefix |= ((uint32_t)tid << sh); }
             }
             __syncthreads();
         }
@@ -736,17 +745,20 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_cluster_kernel(const
             cen[i] = make_float2(0.5f * (bx.x + bx.z), 0.5f * (bx.y + bx.w));
             irk[i] = (unsigned short)grank[i];
         }
-        const int ma = (hi_r - lo_r + CL - 1) / CL, slo = min(lo_r + crank * ma, hi_r), slen = min(hi_r, slo + ma) - slo;
+        // consecutive ranks go to different CTAs and different warps: the top ranks are the dense object clusters, whose
+        // long buckets would otherwise all land in the first warps.  Round slot `bl` of this CTA <-> rank slot_rank(bl).
+        const int slen = (hi_r - lo_r + CL - 1) / CL;              // slots per CTA (the last ones may be empty)
         for (int b0 = 0; b0 < slen; b0 += RPN_NT) {
-            const int nb = min(RPN_NT, slen - b0);
+            auto slot_rank = [&](int bl) { return lo_r + (b0 + ((bl & 31) << 5) + (bl >> 5)) * CL + crank; };
             if (tid < RPN_NT / 32) s_qn[tid] = 0;
             acnt[tid] = 0;
             __syncthreads();
-            const int jr = slo + b0 + tid;
+            const int jr = slot_rank(tid);
+            const bool has = jr < hi_r;
             float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tid < nb) bq = sbox[jr];
+            if (has) bq = sbox[jr];
             int ncell = 0;
-            if (tid < nb && jr > 0 && hd_box_proper(bq)) {
+            if (has && jr > 0 && hd_box_proper(bq)) {
                 const float aq = hd_area(bq);
                 const int c0 = rpnc_class(tq * aq), c1 = rpnc_class((tq > 0.0f) ? aq / tq : 3.0e38f);
                 for (int c = c0; c <= c1; ++c) { int x1, y1, nx; float lx, hx, ly, hy; ncell += window(bq, c, x1, y1, nx, lx, hx, ly, hy); }
@@ -765,7 +777,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_cluster_kernel(const
                 bs.x = __shfl_sync(HD_FULL, bq.x, src); bs.y = __shfl_sync(HD_FULL, bq.y, src);
                 bs.z = __shfl_sync(HD_FULL, bq.z, src); bs.w = __shfl_sync(HD_FULL, bq.w, src);
                 if (t >= total) continue;
-                const int sbl = (wid << 5) + src, sjr = slo + b0 + sbl;
+                const int sbl = (wid << 5) + src, sjr = slot_rank(sbl);
                 const float aq = hd_area(bs);
                 const int c1 = rpnc_class((tq > 0.0f) ? aq / tq : 3.0e38f);
                 int c = rpnc_class(tq * aq), x1 = 0, y1 = 0, nx = 1;
@@ -814,16 +826,16 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_cluster_kernel(const
                         bl[u] = (int)(en >> 16);
                         const int pos = (int)(en & 0xffffu);
                         ir[u] = irk[pos];
-                        bb[u] = sbox[slo + b0 + bl[u]]; bi[u] = gbox[pos];
+                        bb[u] = sbox[slot_rank(bl[u])]; bi[u] = gbox[pos];
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) if (bl[u] >= 0) exact(bl[u], slo + b0 + bl[u], bb[u], ir[u], bi[u]);
+                for (int u = 0; u < 2; ++u) if (bl[u] >= 0) exact(bl[u], slot_rank(bl[u]), bb[u], ir[u], bi[u]);
             }
             __syncthreads();
-            if (tid < nb) {
+            if (has) {
                 const int c = acnt[tid];
-                adj_cnt[slo + b0 + tid] = min(c, RPNC_ADJ);
+                adj_cnt[jr] = min(c, RPNC_ADJ);
                 if (c > RPNC_ADJ) q.fallback[b] = 1;
             }
             __syncthreads();
@@ -1036,7 +1048,7 @@ extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores,
             for (int c = RPNC_MAXCL; c >= 1; c >>= 1) {
                 if ((cap + c - 1) / c > 8192) continue;
                 const int capn = rpn_cluster_capacity(c);
-                const double t = (double)((B + capn - 1) / capn) * (60.0 + 800.0 / c);
+                const double t = (double)((B + capn - 1) / capn) * (90.0 + 480.0 / c);
                 if (t < best) { best = t; CL = c; }
             }
         }
