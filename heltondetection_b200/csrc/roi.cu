@@ -371,6 +371,285 @@ __global__ void __launch_bounds__(256, EFIX == 4 ? 4 : 3) roi_align_nhwc_quad_ke
     tile_store(p.out + (size_t)k * p.C * nb, tile, p.C * nb, use_tma != 0);
 }
 
+// ------------------------------------------------------------------------------------------------ RoIAlign NHWC, staged rows
+// Persistent, warp-specialised variant for sampling_ratio <= 2 (the detection-head configuration): one CTA per SM walks
+// its RoIs; a PRODUCER warp derives each RoI's geometry (the separable tables, the distinct feature rows they touch and
+// the x range) and streams exactly those row segments -- span * C contiguous floats in NHWC -- into a shared-memory
+// ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx); 8 CONSUMER warps (warp = output column pw, lane =
+// channel quads) compute the bins from shared memory and assemble the [C,PH,PW] tile, which leaves with one TMA bulk
+// store.  The gather kernel above re-reads every cell ~2.5x through L1/L2 (overlapping bilinear footprints of
+// neighbouring samples and bins); here every needed cell crosses L2->SM once, and the loads of RoI i+1 are in flight
+// while RoI i is computed.  RoIs whose x range exceeds RR_SPAN cells (sparse sampling: no reuse to win) are computed by
+// the same consumers straight from global memory.  Same arithmetic as the gather kernels (identical tables and order).
+// STATUS: opt-in (hd_roi_set_mode(2)).  Measured on B200 (cfg3, 32 000 RoIs): 3.0 ms vs 1.2 ms for the gather kernel; streaming the
+// rows alone (no compute, no store) already takes 1.0 ms.  With a 50 KB output tile only ~10 row slots (130 KB) fit beside it,
+// of which a bin-row pins 3-4, so too few bytes are in flight per SM to cover the L2 latency, and 8 consumer warps cannot hide
+// the shared-memory latency of the bin arithmetic.  Kept because it is bit-identical, tested, and the starting point for a
+// tensor-map variant with channel-sliced tiles (several small CTAs per SM).
+#define RR_NCW 8                      // consumer warps
+#define RR_THREADS ((RR_NCW + 1) * 32)
+#define RR_MAXSLOTS 16
+#define RR_SPAN 16                    // widest staged x range (cells)
+#define RR_MAXP 8                     // PH, PW <= 8
+#define RR_NG 4                       // geometry records in flight
+
+struct RrGeom {
+    AxisEntry ytab[RR_MAXP * 4], xtab[RR_MAXP * 4];   // off = raw cell index
+    int ycnt[RR_MAXP], xcnt[RR_MAXP];
+    int yrow[RR_MAXP * 4];        // row sequence index of every y entry
+    int rows[RR_MAXP * 4];        // distinct rows in load order
+    int first_row[RR_MAXP + 1];   // lowest row index still needed from bin-row ph on
+    int last_row[RR_MAXP];        // highest row index bin-row ph needs (-1: none)
+    int nrows, xmin, span, staged, lvl, bidx;
+    float count;
+};
+
+__device__ __forceinline__ void rr_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rr_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void rr_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rr_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void rr_bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// one output bin of one channel quad: NY x NX separable taps (rows already resolved to pointers)
+template <int NX, bool STAGED>
+__device__ __forceinline__ float4 rr_bin(const float4* const* rowp, const float* wy, int ny, const int* xo, const float* wx, int q) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        if (a < ny) {
+            const float4* row = rowp[a] + q;
+            float4 v[NX];
+#pragma unroll
+            for (int b = 0; b < NX; ++b) v[b] = STAGED ? row[xo[b]] : __ldg(row + xo[b]);
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int b = 0; b < NX; ++b) { r.x = fmaf(wx[b], v[b].x, r.x); r.y = fmaf(wx[b], v[b].y, r.y); r.z = fmaf(wx[b], v[b].z, r.z); r.w = fmaf(wx[b], v[b].w, r.w); }
+            acc.x = fmaf(wy[a], r.x, acc.x); acc.y = fmaf(wy[a], r.y, acc.y); acc.z = fmaf(wy[a], r.z, acc.z); acc.w = fmaf(wy[a], r.w, acc.w);
+        }
+    }
+    return acc;
+}
+
+struct RrSmem {
+    RrGeom geom[RR_NG];
+    unsigned long long full[RR_MAXSLOTS], empty[RR_MAXSLOTS], gfull[RR_NG], gempty[RR_NG];
+};
+
+__global__ void __launch_bounds__(RR_THREADS, 1) roi_align_ring_kernel(const __grid_constant__ RoiParams p, int n_slots, int slot_bytes, int ring_off, int meta_off, int dbg) {
+    extern __shared__ __align__(128) unsigned char smem_b[];
+    float* tile = reinterpret_cast<float*>(smem_b);                       // [C][PH*PW]
+    unsigned char* ring = smem_b + ring_off;
+    RrSmem& sm = *reinterpret_cast<RrSmem*>(smem_b + meta_off);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nb = p.PH * p.PW, nq = p.C >> 2;
+    if (tid == 0) {
+        for (int s = 0; s < n_slots; ++s) { rr_mbar_init(&sm.full[s], 1); rr_mbar_init(&sm.empty[s], RR_NCW); }
+        for (int g = 0; g < RR_NG; ++g) { rr_mbar_init(&sm.gfull[g], 1); rr_mbar_init(&sm.gempty[g], RR_NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long k0 = blockIdx.x, kstep = gridDim.x;
+    // ring position of the next staged row: slot index and use count of that slot; producer and consumers advance identically
+    int rslot = 0; unsigned ruse = 0;
+    auto advance = [&](int rows) { rslot += rows; while (rslot >= n_slots) { rslot -= n_slots; ++ruse; } };
+    if (wid == RR_NCW) {
+        // ================================================================ producer warp
+        int it = 0;
+        for (long long k = k0; k < p.K; k += kstep, ++it) {
+            RrGeom& G = sm.geom[it % RR_NG];
+            rr_mbar_wait(&sm.gempty[it % RR_NG], ((it / RR_NG) & 1) ^ 1);
+            const float* roi = p.rois + k * 5;
+            const int lvl = p.level_ids ? p.level_ids[k] : 0;
+            const int H = p.H[lvl], W = p.W[lvl];
+            const float sc = p.scale[lvl];
+            const float off = p.aligned ? 0.5f : 0.0f;
+            const float sw = __fsub_rn(__fmul_rn(roi[1], sc), off), sh = __fsub_rn(__fmul_rn(roi[2], sc), off);
+            const float ew = __fsub_rn(__fmul_rn(roi[3], sc), off), eh = __fsub_rn(__fmul_rn(roi[4], sc), off);
+            float rw = __fsub_rn(ew, sw), rh = __fsub_rn(eh, sh);
+            if (!p.aligned) { rw = fmaxf(rw, 1.0f); rh = fmaxf(rh, 1.0f); }
+            const float bh = __fdiv_rn(rh, (float)p.PH), bw = __fdiv_rn(rw, (float)p.PW);
+            const int g = p.sampling_ratio;   // 1 or 2 (host check)
+            if (lane < p.PH) build_axis(G.ytab, G.ycnt, lane, 4, sh, bh, g, H, 1, 4);
+            else if (lane >= 16 && lane < 16 + p.PW) build_axis(G.xtab, G.xcnt, lane - 16, 4, sw, bw, g, W, 1, 4);
+            __syncwarp();
+            // lane e = (ph, a) owns one y entry.  The distinct rows, ascending, are the load order (sample positions grow with
+            // ph, so a row is new only if it is above every earlier one): row index = number of distinct smaller rows.
+            const int eph = lane >> 2, ea = lane & 3;
+            const bool yvalid = eph < p.PH && ea < G.ycnt[eph];
+            const int ycell = yvalid ? G.ytab[lane].off : 0x7fffffff - lane;     // distinct sentinels
+            const unsigned peers = __match_any_sync(HD_FULL, ycell);
+            const bool leader = yvalid && (peers & hd_lanemask_lt()) == 0u;
+            int idx = 0;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) {
+                const int yl = __shfl_sync(HD_FULL, ycell, l);
+                const int ll = __shfl_sync(HD_FULL, (int)leader, l);
+                idx += (ll && yl < ycell) ? 1 : 0;
+            }
+            const int nrows = __popc(__ballot_sync(HD_FULL, leader));
+            if (yvalid) G.yrow[lane] = idx;
+            if (leader) G.rows[idx] = ycell;
+            // x range
+            const bool xvalid = eph < p.PW && ea < G.xcnt[eph];
+            int xmin = xvalid ? G.xtab[lane].off : 0x7fffffff, xmax = xvalid ? G.xtab[lane].off : -1;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { xmin = min(xmin, __shfl_xor_sync(HD_FULL, xmin, d)); xmax = max(xmax, __shfl_xor_sync(HD_FULL, xmax, d)); }
+            const int span = (xmax >= 0) ? xmax - xmin + 1 : 0;
+            if (xmax < 0) xmin = 0;
+            const int staged = (nrows > 0 && span >= 1 && span <= RR_SPAN && bh >= 0.0f && bw >= 0.0f && !(dbg & 8)) ? 1 : 0;   // (inverted RoIs walk the rows downwards)
+            __syncwarp();
+            if (lane < p.PH) {   // per bin-row: highest row needed, and lowest row any bin-row >= ph still needs
+                const int c = G.ycnt[lane];
+                G.last_row[lane] = c > 0 ? G.yrow[lane * 4 + c - 1] : -1;
+                int fr = nrows;
+                for (int ph = p.PH - 1; ph >= lane; --ph) if (G.ycnt[ph] > 0) fr = G.yrow[ph * 4];
+                G.first_row[lane] = fr;
+            }
+            if (lane == 0) {
+                G.first_row[p.PH] = nrows;
+                G.nrows = nrows; G.xmin = xmin; G.span = span; G.staged = staged; G.lvl = lvl; G.bidx = (int)roi[0];
+                G.count = (float)max(g * g, 1);
+            }
+            __syncwarp();
+            if (lane == 0) rr_mbar_arrive(&sm.gfull[it % RR_NG]);
+            if (staged) {
+                const float* f = p.data[lvl] + (size_t)(int)roi[0] * H * W * p.C;
+                const unsigned bytes = (unsigned)span * (unsigned)p.C * 4u;
+                // lane r issues row r, one wave of n_slots rows at a time: inside a wave every lane waits on a different
+                // slot, so the 1-bit phase parity of the empty barriers cannot alias (a waiter is never two phases ahead)
+                for (int base = 0; base < nrows; base += n_slots) {
+                    if (lane >= base && lane < min(nrows, base + n_slots)) {
+                        int slot = rslot + lane; unsigned use = ruse;
+                        while (slot >= n_slots) { slot -= n_slots; ++use; }
+                        rr_mbar_wait(&sm.empty[slot], (use & 1u) ^ 1u);
+                        rr_mbar_expect_tx(&sm.full[slot], bytes);
+                        rr_bulk_load(ring + (size_t)slot * slot_bytes, f + ((size_t)G.rows[lane] * W + xmin) * p.C, bytes, &sm.full[slot]);
+                    }
+                    __syncwarp();
+                }
+                advance(nrows);
+            }
+        }
+    } else {
+        // ================================================================ consumer warps
+        const int rot = lane >> 3;
+        int it = 0;
+        for (long long k = k0; k < p.K; k += kstep, ++it) {
+            const RrGeom& G = sm.geom[it % RR_NG];
+            rr_mbar_wait(&sm.gfull[it % RR_NG], (it / RR_NG) & 1);
+            const int lvl = G.lvl, W = p.W[lvl], H = p.H[lvl];
+            const float* __restrict__ f = p.data[lvl] + (size_t)G.bidx * H * W * p.C;
+            const float count = G.count;
+            const int icount = (int)count;
+            const bool pow2 = (icount & (icount - 1)) == 0;
+            const float inv = 1.0f / count;
+            const bool staged = G.staged != 0;
+            const int xmin = G.xmin, nrows = G.nrows;
+            // the previous tile must have left shared memory before it is overwritten
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(RR_NCW * 32) : "memory");
+            int waited = 0, released = 0;
+            for (int ph = 0; ph < p.PH; ++ph) {
+                const int ny = G.ycnt[ph];
+                const float4* rowp[4]; float wy[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    wy[a] = G.ytab[ph * 4 + a].w;
+                    if (staged) {
+                        int slot = rslot + ((a < ny) ? G.yrow[ph * 4 + a] : 0);
+                        while (slot >= n_slots) slot -= n_slots;
+                        rowp[a] = reinterpret_cast<const float4*>(ring + (size_t)slot * slot_bytes);
+                    } else {
+                        rowp[a] = reinterpret_cast<const float4*>(f + (size_t)G.ytab[ph * 4 + a].off * W * p.C);
+                    }
+                }
+                if (staged) {
+                    const int need = G.last_row[ph];
+                    for (; waited <= need; ++waited) {
+                        int slot = rslot + waited; unsigned use = ruse;
+                        while (slot >= n_slots) { slot -= n_slots; ++use; }
+                        rr_mbar_wait(&sm.full[slot], use & 1u);
+                    }
+                }
+                for (int pw = wid; pw < p.PW && !(dbg & 2); pw += RR_NCW) {
+                    const int nx = G.xcnt[pw];
+                    int xo[4]; float wx[4];
+#pragma unroll
+                    for (int bq = 0; bq < 4; ++bq) {
+                        const int xc = G.xtab[pw * 4 + bq].off;
+                        xo[bq] = (staged ? (xc - xmin) : xc) * nq;        // float4 units
+                        wx[bq] = G.xtab[pw * 4 + bq].w;
+                    }
+                    const int bin = ph * p.PW + pw;
+                    for (int q = lane; q < nq; q += 32) {
+                        float4 acc;
+                        if (staged) {
+                            if (nx == 2) acc = rr_bin<2, true>(rowp, wy, ny, xo, wx, q);
+                            else if (nx == 3) acc = rr_bin<3, true>(rowp, wy, ny, xo, wx, q);
+                            else if (nx == 4) acc = rr_bin<4, true>(rowp, wy, ny, xo, wx, q);
+                            else if (nx == 1) acc = rr_bin<1, true>(rowp, wy, ny, xo, wx, q);
+                            else acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        } else {
+                            if (nx == 2) acc = rr_bin<2, false>(rowp, wy, ny, xo, wx, q);
+                            else if (nx == 3) acc = rr_bin<3, false>(rowp, wy, ny, xo, wx, q);
+                            else if (nx == 4) acc = rr_bin<4, false>(rowp, wy, ny, xo, wx, q);
+                            else if (nx == 1) acc = rr_bin<1, false>(rowp, wy, ny, xo, wx, q);
+                            else acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        if (pow2) { acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
+                        else { acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count); acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count); }
+                        // lane-rotated store order (rot = lane/8): at every step the 32 lanes hit 32 different banks
+                        float* t = tile + (size_t)(4 * q) * nb + bin;
+                        const float a0 = (rot & 1) ? acc.y : acc.x, a1 = (rot & 1) ? acc.z : acc.y, a2 = (rot & 1) ? acc.w : acc.z, a3 = (rot & 1) ? acc.x : acc.w;
+                        const float b0 = (rot & 2) ? a2 : a0, b1 = (rot & 2) ? a3 : a1, b2 = (rot & 2) ? a0 : a2, b3 = (rot & 2) ? a1 : a3;  // b_s = acc[(s+rot)&3]
+                        t[((0 + rot) & 3) * nb] = b0; t[((1 + rot) & 3) * nb] = b1; t[((2 + rot) & 3) * nb] = b2; t[((3 + rot) & 3) * nb] = b3;
+                    }
+                }
+                if (staged) {   // rows no later bin-row needs go back to the producer
+                    __syncwarp();
+                    const int upto = G.first_row[ph + 1];
+                    if (lane == 0)
+                        for (int r = released; r < upto; ++r) {
+                            int slot = rslot + r;
+                            while (slot >= n_slots) slot -= n_slots;
+                            rr_mbar_arrive(&sm.empty[slot]);
+                        }
+                    released = max(released, upto);
+                }
+            }
+            if (staged) advance(nrows);
+            __syncwarp();
+            if (lane == 0) rr_mbar_arrive(&sm.gempty[it % RR_NG]);
+            // tile complete -> one bulk store
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(RR_NCW * 32) : "memory");
+            if (tid == 0 && !(dbg & 1)) {
+                unsigned saddr = (unsigned)__cvta_generic_to_shared(tile);
+                float* gdst = p.out + (size_t)k * p.C * nb;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(p.C * nb * 4) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ RoIPool NHWC
 __global__ void __launch_bounds__(256) roi_pool_nhwc_kernel(const __grid_constant__ RoiParams p, int use_tma) {
     extern __shared__ __align__(128) float smem_f[];
@@ -618,6 +897,12 @@ static int fill_roi(RoiParams& p, const hd_roi_level* levels, int n_levels, int 
     return HD_OK;
 }
 
+// 0 auto (= gather kernels: the staged-row kernel measured 2.5x slower on B200, see profiles/r1_results.md), 1 gather kernels
+// only, 2 staged-row kernel whenever eligible; bits 4.. are debug switches of the staged-row kernel (1: no tile store,
+// 2: no compute, 8: nothing staged)
+static int g_roi_mode = 0;
+extern "C" HD_API int hd_roi_set_mode(int mode) { int old = g_roi_mode; g_roi_mode = mode; return old; }
+
 static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st) {
     if (p.K == 0) return HD_OK;
     HD_CHECK_ARG(p.rois && p.out, "rois/out is NULL");
@@ -649,6 +934,23 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
         for (int l = 0; l < p.n_levels; ++l) quad = quad && (((uintptr_t)p.data[l] & 15) == 0);
         int nq = p.C / 4, QT = 8;               // threads per bin group: power of two >= channel quads, in [8,256]
         while (QT < nq && QT < 256) QT <<= 1;
+        if (!pool && quad && (g_roi_mode & 15) != 1 && p.sampling_ratio >= 1 && p.sampling_ratio <= 2 && p.PH <= RR_MAXP && p.PW <= RR_MAXP &&
+            (g_roi_mode & 15) == 2) {
+            // staged-row persistent kernel: tile | ring of row slots | geometry records + mbarriers
+            const size_t tile_b = hd_align_up(tile, 128), slot_b = hd_align_up((size_t)RR_SPAN * p.C * 4, 128), meta_b = hd_align_up(sizeof(RrSmem), 128);
+            const size_t budget = 227 * 1024;
+            int n_slots = tile_b + meta_b < budget ? (int)((budget - tile_b - meta_b) / slot_b) : 0;
+            if (n_slots > RR_MAXSLOTS) n_slots = RR_MAXSLOTS;
+            if (n_slots >= 6 && use_tma) {
+                static bool ring_attr = false;
+                if (!ring_attr) { HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); ring_attr = true; }
+                const size_t smem_ring = tile_b + (size_t)n_slots * slot_b + meta_b;
+                const unsigned grid = (unsigned)(p.K < HD_NUM_SMS ? p.K : HD_NUM_SMS);
+                roi_align_ring_kernel<<<grid, RR_THREADS, smem_ring, st>>>(p, n_slots, (int)slot_b, (int)tile_b, (int)(tile_b + (size_t)n_slots * slot_b), g_roi_mode >> 4);
+                HD_CUDA_LAUNCH_CHECK("roi_align_ring_kernel");
+                return HD_OK;
+            }
+        }
         if (pool && quad) roi_pool_nhwc_quad_kernel<<<(unsigned)p.K, 256, smem, st>>>(p, use_tma, QT);
         else if (pool) roi_pool_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
         else if (quad && tab < ROI_TAB && p.sampling_ratio <= 2) roi_align_nhwc_quad_kernel<4><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);

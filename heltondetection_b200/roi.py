@@ -9,6 +9,11 @@ from torch import nn
 from . import _lib
 
 
+def set_mode(mode):
+    """RoIAlign kernel choice: 0 auto, 1 gather kernels only, 2 staged-row (TMA ring) kernel whenever eligible; returns the previous mode."""
+    return _lib.lib().hd_roi_set_mode(int(mode))
+
+
 def _pair(v):
     return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
 

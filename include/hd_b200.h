@@ -165,6 +165,10 @@ HD_API int hd_roi_align(const hd_roi_level* levels /*host*/, int n_levels, int l
 HD_API int hd_roi_pool(const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, const float* rois,
                        const int32_t* level_ids, int64_t K, int pooled_h, int pooled_w, float* out, int32_t* argmax,
                        void* stream);
+/* RoIAlign kernel choice (process-wide; developer / test aid): 0 = automatic (the gather kernels), 1 = gather kernels only,
+ * 2 = experimental staged-row (TMA ring) kernel whenever eligible (NHWC, C % 4 == 0, sampling_ratio 1 or 2, output <= 8x8;
+ * bit-identical results, currently slower).  Returns the previous mode. */
+HD_API int hd_roi_set_mode(int mode);
 /* [B,C,H,W] -> [B,H,W,C] layout pass used in front of the NHWC kernels. */
 HD_API int hd_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, void* stream);
 /* Level of each RoI.  rois: rows of roi_stride floats with the xyxy box at box_offset.

@@ -102,3 +102,47 @@ def test_multilevel_matches_oracle(op):
     ref1, _ = oracle.roi.multilevel_roi_align(feats[:1], rois, 7, scales[:1], 2, False, op=op)
     got1, _ = ops.multilevel_roi_align([feats[0].cuda()], rois.cuda(), 7, scales[:1], 2, False, op=op)
     assert close(got1, ref1)
+
+
+@pytest.mark.parametrize("C,K,sr,aligned,out", [(256, 700, 2, False, 7), (256, 700, 2, True, 7), (64, 400, 1, False, 7), (8, 350, 2, True, (5, 8)),
+                                               (512, 320, 2, False, 7), (48, 60, 2, False, 7)])
+def test_staged_row_kernel_equals_gather_kernel_and_torchvision(C, K, sr, aligned, out):
+    """the TMA row-ring kernel (mode 2) runs the same arithmetic as the gather kernels (mode 1): identical bits;
+    both within 1e-5 of torchvision.  RoIs include out-of-map, zero-size, inverted and wide (> 16 cells: direct path) boxes."""
+    from heltondetection_b200 import ops, roi
+    x, rois = _data(B=2, C=C, H=60, W=52, K=K, img=416, seed=3 + C)
+    rois[5, 1:] = torch.tensor([4.0, 8.0, 400.0, 380.0])      # spans the whole map: > 16 cells wide
+    rois[6, 1:] = torch.tensor([100.0, 8.0, 140.0, 410.0])    # tall and narrow
+    rois[7, 1:] = torch.tensor([8.0, 100.0, 410.0, 130.0])    # wide and flat
+    ref = torchvision.ops.roi_align(x, rois, out, 0.125, sr, aligned)
+    xcl = x.cuda().contiguous(memory_format=torch.channels_last)
+    res = {}
+    for mode in (1, 2):
+        old = roi.set_mode(mode)
+        try:
+            res[mode] = ops.roi_align(xcl, rois.cuda(), out, 0.125, sr, aligned).cpu()
+        finally:
+            roi.set_mode(old)
+    assert torch.equal(res[1], res[2])
+    assert close(res[2], ref)
+
+
+def test_staged_row_kernel_multilevel_large():
+    import oracle
+    from heltondetection_b200 import ops, roi, synth
+    feats = synth.fpn_features(2, 416, 64, seed=6)
+    rois = synth.random_rois(2, 1500, 416, 11, min_side=6.0)
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    ref, rl = oracle.roi.multilevel_roi_align(feats, rois, 7, scales, 2, False)
+    cl = [f.cuda().contiguous(memory_format=torch.channels_last) for f in feats]
+    res = {}
+    for mode in (1, 2):
+        old = roi.set_mode(mode)
+        try:
+            got, gl = ops.multilevel_roi_align(cl, rois.cuda(), 7, scales, 2, False)
+            res[mode] = got.cpu()
+        finally:
+            roi.set_mode(old)
+    assert torch.equal(gl.cpu(), rl)
+    assert torch.equal(res[1], res[2])
+    assert close(res[2], ref)

@@ -1,0 +1,14 @@
+import sys, os, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from heltondetection_b200 import synth, rpn, roi
+B, img = 4, 832
+obj, dlt, bases, _ = synth.rpn_heads(B, img, G=20, seed=1237)
+feats = [f.cuda().contiguous(memory_format=torch.channels_last) for f in synth.fpn_features(B, img, 256, 1237)]
+obj, dlt = [o.cuda() for o in obj], [d.cuda() for d in dlt]
+pr = rpn.RpnProposals(bases, (4, 8, 16, 32), (img, img), n_pre_nms=12000, n_post_nms=2000, min_size=16)
+rois, cnt, sc, idx = pr(obj, dlt)
+roi.set_mode(2)
+for _ in range(3):
+    out, lv = roi.multilevel_roi_align(feats, rois, 7, [1 / 4, 1 / 8, 1 / 16, 1 / 32], 2, False)
+torch.cuda.synchronize()
+print("ok", out.shape)
