@@ -17,6 +17,8 @@ FLAG_DENSE_READ = 2
 NMS_AGNOSTIC, NMS_CLASS_EXACT, NMS_CLASS_OFFSET = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 RPN_SOFTMAX, RPN_CLAMP_DWH = 1, 2
+ROIHEAD_MUL_STD, ROIHEAD_CLAMP_DWH, ROIHEAD_LABEL_MINUS1 = 16, 32, 64
+BOX_XYWH = 1
 WBF_AVG, WBF_MAX = 0, 1
 
 
@@ -67,6 +69,10 @@ SIGNATURES = {
     "hd_rpn_set_cluster_size": (_i, [_i]),
     "hd_rpn_proposals_workspace_size": (_sz, [_i, _i, _i]),
     "hd_rpn_proposals": (_i, [C.POINTER(RpnLevel), _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hd_roi_head_decode_filter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(C.c_float), _i, _f, _f, _f, _d, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "hd_roi_head_postprocess_workspace_size": (_sz, [_i, _i, _i]),
+    "hd_roi_head_postprocess": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(C.c_float), _i, _f, _f, _f, _d, _f, _d, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hd_scale_detections": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "hd_wbf_workspace_size": (_sz, [_i, _i, _i, _i]),
     "hd_wbf": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_double), _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hd_tta_map_back": (_i, [_vp, _vp, _i, _i, _f, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

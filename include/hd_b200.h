@@ -180,6 +180,40 @@ HD_API int hd_roi_level_map(const float* rois, int roi_stride, int box_offset, i
                             void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * RoI-head output post-process -- the FasterRCNN final stage (README.md:8).  Replaces
+ * torchvision RoIHeads.postprocess_detections (models/detection/roi_heads.py:668-723) with BoxCoder.decode_single
+ * (_utils.py:183-224), and the lineage DecodeBox (bubbliiiing frcnn) as a flag variant.
+ *   cls_logits [B*R, n_class] (class 0 = background), box_deltas [B*R, n_class*4], rois [B*R, 5] = (b,x1,y1,x2,y2)
+ *   with the R rows of image b contiguous (the hd_rpn_proposals layout); roi_count[b] (nullable) = valid rows.
+ * Per (roi, class c >= 1): score = softmax(logits)[c]; box = decode(roi, deltas[c] / weights)  [weights 10,10,5,5]
+ * -> clip to the image -> keep score > score_thresh and w,h >= min_size (pass -INFINITY to skip the size test)
+ * -> candidate (box, score, label c, id = r*(n_class-1) + c-1).  hd_roi_head_postprocess then runs the class-aware
+ * NMS (suppress only equal labels, = batched_nms) and writes the first max_det keeps by score:
+ *   out_det [B, max_det, 6] = (x1,y1,x2,y2,score,label), out_idx [B, max_det] = candidate id, out_count [B].
+ * ------------------------------------------------------------------------------------------- */
+#define HD_ROIHEAD_MUL_STD 16      /* weights are multipliers (std 0.1,0.1,0.2,0.2: lineage) instead of divisors (10,10,5,5) */
+#define HD_ROIHEAD_CLAMP_DWH 32    /* clamp dw,dh to clamp_dwh before exp (torchvision bbox_xform_clip = log(1000/16)) */
+#define HD_ROIHEAD_LABEL_MINUS1 64 /* labels c-1 (lineage) instead of c (torchvision) */
+HD_API int hd_roi_head_decode_filter(const float* cls_logits, const float* box_deltas, const float* rois, const int32_t* roi_count,
+                                     int B, int R, int n_class, const float* weights /*host[4]*/, int flags, float clamp_dwh,
+                                     float img_h, float img_w, double score_thresh, float min_size, float* cand_box,
+                                     float* cand_score, int32_t* cand_cls, int32_t* cand_id, int32_t* cand_count, int cap,
+                                     void* stream);
+HD_API size_t hd_roi_head_postprocess_workspace_size(int B, int R, int n_class);
+HD_API int hd_roi_head_postprocess(const float* cls_logits, const float* box_deltas, const float* rois, const int32_t* roi_count,
+                                   int B, int R, int n_class, const float* weights /*host[4]*/, int flags, float clamp_dwh,
+                                   float img_h, float img_w, double score_thresh, float min_size, double nms_iou, int max_det,
+                                   float* out_det, int64_t* out_idx, int32_t* out_count, void* workspace, size_t workspace_bytes,
+                                   void* stream);
+
+/* Output formats: letterbox inverse + clip of padded detections [B, max_det, 6] (ultralytics
+ * scale_coords / clip_coords) and optionally the COCO result-json box (x, y, w, h).  meta [B,5] (device) =
+ * (pad_x, pad_y, gain, w0, h0) per image; rows >= count[b] (count nullable) are zeroed.  out may alias det. */
+#define HD_BOX_XYWH 1
+HD_API int hd_scale_detections(const float* det, const int32_t* count, int B, int max_det, const float* meta, int flags, float* out,
+                               void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * RPN proposal creation (README.md:8,63-65; lineage ProposalCreator / loc2bbox, SURVEY.md A.3;
  * cross-check torchvision models/detection/rpn.py:231-297, _utils.py:183-224).
  * Per level: objectness [B, A, H, W] (sigmoid) or [B, 2A, H, W] (HD_RPN_SOFTMAX, channel a*2+{bg,fg}),

@@ -21,4 +21,4 @@ Third-party arithmetic on the path:
   * ZFTurbo ``ensemble-boxes`` ``weighted_boxes_fusion`` (not installed, version
     unknown): restated from its published algorithm in ``oracle/wbf.py``.
 """
-from . import boxes, yolo, rpn, roi, wbf, tta  # noqa: F401
+from . import boxes, yolo, rpn, roi, wbf, tta, roi_head  # noqa: F401

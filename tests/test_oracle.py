@@ -191,3 +191,24 @@ def test_plain_c_restatement_is_pinned_to_torchvision():
             got = cref.roi_align(x.numpy(), rois.numpy(), 7, 0.125, sr, al)
             assert np.allclose(got, G[f"roi_align_sr{sr}_al{int(al)}"], rtol=1e-6, atol=1e-6)
     assert np.array_equal(cref.roi_pool(x.numpy(), rois.numpy(), 7, 0.125), G["roi_pool"])
+
+
+def test_roi_head_restatement_equals_torchvision_method():
+    """oracle.roi_head.postprocess_detections (restatement with variant switches) == the unmodified torchvision
+    RoIHeads.postprocess_detections on the default variant (roi_heads.py:668-723)."""
+    import oracle
+    g = torch.Generator().manual_seed(0)
+    R, C = 300, 21
+    lg = torch.randn(2 * R, C, generator=g) * 3
+    rg = torch.randn(2 * R, C * 4, generator=g) * 0.5
+    xy = torch.rand(2 * R, 2, generator=g) * 300
+    pr = torch.cat((xy, xy + torch.rand(2 * R, 2, generator=g) * 150 + 4), 1)
+    props, shapes = [pr[:R], pr[R:]], [(400, 420), (380, 450)]
+    a = oracle.roi_head.postprocess_detections_tv(lg, rg, props, shapes)
+    b = oracle.roi_head.postprocess_detections(lg, rg, props, shapes)
+    for x, y in zip(a, b):
+        for u, v in zip(x, y):
+            assert torch.equal(u, v)
+    # letterbox inverse known answer: 640x640 letterbox of a 480x640 image has gain 1 and 80 px of vertical padding
+    box = torch.tensor([[10.0, 90.0, 630.0, 700.0]])
+    assert oracle.roi_head.scale_coords((640, 640), box, (480, 640)).tolist() == [[10.0, 10.0, 630.0, 480.0]]
