@@ -73,3 +73,19 @@ def test_wbf():
     ll = [G[f"wbf_l{v}"] for v in range(3)]
     b, s, l = wbf.weighted_boxes_fusion(bl, sl, ll, None, 0.55, 0.1, "avg")
     assert np.array_equal(l, G["wbf_labels"]) and np.array_equal(b, G["wbf_boxes"]) and np.array_equal(s, G["wbf_scores"])
+
+
+def test_roi_head_against_torchvision_method_fixture():
+    """golden_v2.npz: outputs of torchvision RoIHeads.postprocess_detections (CPU) + scale_coords"""
+    from heltondetection_b200 import roi_head
+    G2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v2.npz"))
+    lg, rg, pr = (torch.from_numpy(G2[k]).cuda() for k in ("rh_logits", "rh_deltas", "rh_props"))
+    b, s, l = roi_head.postprocess_detections(lg, rg, [pr[:120], pr[120:]], [(256, 320)] * 2, 0.05, 0.5, 50)
+    for i in range(2):
+        assert np.array_equal(l[i].cpu().numpy(), G2[f"rh_labels{i}"])
+        assert boxes_close(b[i], torch.from_numpy(G2[f"rh_boxes{i}"]))
+        assert close(s[i], torch.from_numpy(G2[f"rh_scores{i}"]), scale=1e-3)
+        k = b[i].shape[0]
+        det = torch.zeros((1, k, 6), device="cuda"); det[0, :, :4] = torch.from_numpy(G2[f"rh_boxes{i}"]).cuda()
+        sc = roi_head.scale_coords((256, 320), det, [(480, 640)])
+        assert np.array_equal(sc[0, :, :4].cpu().numpy(), G2[f"rh_scaled{i}"])

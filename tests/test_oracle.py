@@ -212,3 +212,15 @@ def test_roi_head_restatement_equals_torchvision_method():
     # letterbox inverse known answer: 640x640 letterbox of a 480x640 image has gain 1 and 80 px of vertical padding
     box = torch.tensor([[10.0, 90.0, 630.0, 700.0]])
     assert oracle.roi_head.scale_coords((640, 640), box, (480, 640)).tolist() == [[10.0, 10.0, 630.0, 480.0]]
+
+
+def test_roi_head_oracle_against_committed_fixture():
+    import os
+    import numpy as np
+    import oracle
+    G2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v2.npz"))
+    lg, rg, pr = (torch.from_numpy(G2[k]) for k in ("rh_logits", "rh_deltas", "rh_props"))
+    b, s, l = oracle.roi_head.postprocess_detections(lg, rg, [pr[:120], pr[120:]], [(256, 320)] * 2, 0.05, 0.5, 50)
+    for i in range(2):
+        assert np.array_equal(b[i].numpy(), G2[f"rh_boxes{i}"]) and np.array_equal(l[i].numpy(), G2[f"rh_labels{i}"])
+        assert np.array_equal(oracle.roi_head.scale_coords((256, 320), b[i], (480, 640)).numpy(), G2[f"rh_scaled{i}"])

@@ -122,6 +122,25 @@ def cfg3():
         print("   torchvision cuda comparison skipped:", e)
 
 
+def roihead():
+    """FasterRCNN final stage on the cfg3 proposals: 16 x 2000 RoIs x 81 classes -> softmax/decode/filter -> class-aware NMS -> top 100"""
+    from heltondetection_b200 import roi_head
+    B, R, Cn = 16, 2000, 81
+    g = torch.Generator().manual_seed(1240)
+    lg = (torch.randn(B * R, Cn, generator=g) * 3).cuda()
+    rg = (torch.randn(B * R, Cn * 4, generator=g) * 0.5).cuda()
+    xy = torch.rand(B * R, 2, generator=g) * 700
+    rois = torch.cat((torch.arange(B).repeat_interleave(R)[:, None].float(), xy, xy + torch.rand(B * R, 2, generator=g) * 120 + 8), 1).cuda()
+    pp = roi_head.RoIHeadPostprocessor((832, 832), 0.05, 0.5, 100)
+    nbytes = lg.numel() * 4 + rg.numel() * 4 + rois.numel() * 4
+    t = timeit(lambda: pp(lg, rg, rois, None, B=B), iters=10)
+    det, idx, cnt = pp(lg, rg, rois, None, B=B)
+    report("roi-head post-process 16x2000x81 (decode+filter+NMS+top100)", t, nbytes, B)
+    print("    detections/img:", cnt.tolist()[:8])
+    t = timeit(lambda: roi_head.scale_coords((832, 832), det, [(1080, 1920)] * B, cnt, xywh=True), iters=10)
+    report("scale_coords + COCO boxes 16x100", t, None)
+
+
 def cfg5():
     B, img, nc = 64, 640, 80
     views, _ = synth.tta_heads(B, img, nc, G=20, seed=1239)
@@ -216,7 +235,7 @@ def cpu():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg4", "cfg5", "zerocopy", "cpu"]
+    which = sys.argv[1:] or ["cfg2", "cfg3", "roihead", "cfg4", "cfg5", "zerocopy", "cpu"]
     torch.cuda.set_device(0)
     for w in which:
         print(f"==== {w}", flush=True)
