@@ -1,9 +1,33 @@
 // YOLOv5 head kernels: dense decode (a1), fused decode+filter+compaction (a1+a2), filter on decoded pred (a2).
 // Reference feature: README.md:9; semantics SURVEY.md A.1/A.2 (ultralytics / bubbliiiing lineage, README.md:158-162).
 #include "hd_common.cuh"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+// head element types: fp32 (default) or, with HD_FLAG_IN_F16 / HD_FLAG_IN_BF16, 16-bit heads that are widened to fp32 on
+// load (exact) -- half the HBM bytes of the dominant read; all arithmetic stays fp32
+struct HdF16 { unsigned short v; };
+struct HdBF16 { unsigned short v; };
+__device__ __forceinline__ float hd_widen(float x) { return x; }
+__device__ __forceinline__ float hd_widen(HdF16 x) { return __half2float(__ushort_as_half(x.v)); }
+__device__ __forceinline__ float hd_widen(HdBF16 x) { return __uint_as_float((unsigned)x.v << 16); }
+template <typename T> __device__ __forceinline__ float hd_load1(const T* q) { return hd_widen(*q); }
+template <> __device__ __forceinline__ float hd_load1<float>(const float* q) { return hd_ldg_stream(q); }
+// four consecutive elements with one streaming load (128-bit for fp32, 64-bit for the 16-bit types)
+template <typename T> __device__ __forceinline__ void hd_load4(const T* q, float* v) {
+    unsigned lo, hi;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(q));
+    T e;
+    e.v = (unsigned short)(lo & 0xffffu); v[0] = hd_widen(e); e.v = (unsigned short)(lo >> 16); v[1] = hd_widen(e);
+    e.v = (unsigned short)(hi & 0xffffu); v[2] = hd_widen(e); e.v = (unsigned short)(hi >> 16); v[3] = hd_widen(e);
+}
+template <> __device__ __forceinline__ void hd_load4<float>(const float* q, float* v) {
+    const float4 w = hd_ldg_stream4(q);
+    v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+}
 
 struct YoloParams {
-    const float* data[HD_MAX_LEVELS];
+    const void* data[HD_MAX_LEVELS];
     int HW[HD_MAX_LEVELS];
     int W[HD_MAX_LEVELS];
     float stride[HD_MAX_LEVELS];
@@ -31,7 +55,7 @@ struct YoloParams {
 //     an exact rescan;
 //   - survivors are compacted with one atomicAdd per warp.
 // ------------------------------------------------------------------------------------------------
-template <bool VEC>
+template <bool VEC, typename T>
 __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long long item, const int lane,
                                                  float4* __restrict__ cand_box, float* __restrict__ cand_score,
                                                  int* __restrict__ cand_cls, int* __restrict__ cand_anchor,
@@ -48,7 +72,7 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
     const int t = r - a * tiles_l;
     const int HW = p.HW[l];
     const int cell0 = t * 128 + lane * 4;
-    const float* __restrict__ base = p.data[l] + ((size_t)(b * p.A + a) * p.no) * HW + cell0;
+    const T* __restrict__ base = reinterpret_cast<const T*>(p.data[l]) + ((size_t)(b * p.A + a) * p.no) * HW + cell0;
 
     float o[4], bx[4][4], m[4], L[4];
     int j[4];
@@ -58,16 +82,13 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
 
     bool need = true;  // lane fetches the non-objectness planes (narrowed below in sparse mode)
     auto load4 = [&](int plane, float* v) {
-        const float* q = base + (size_t)plane * HW;
+        const T* q = base + (size_t)plane * HW;
         if (VEC) {
-            if (valid[0] && need) {
-                float4 w = hd_ldg_stream4(q);
-                v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
-            }
+            if (valid[0] && need) hd_load4<T>(q, v);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (valid[k] && need) v[k] = hd_ldg_stream(q + k);
+                if (valid[k] && need) v[k] = hd_load1<T>(q + k);
         }
     };
 
@@ -133,9 +154,9 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
             if (ok) {
                 if (L[k] > -INFINITY && __fmul_rn(hd_sigmoid(L[k]), po) == cf) {
                     // an earlier class ties after rounding: torch.max returns the first maximal product
-                    const float* q = base + k;
+                    const T* q = base + k;
                     for (int cc = 0; cc < j[k]; ++cc) {
-                        float lg = __ldg(q + (size_t)(5 + cc) * HW);
+                        float lg = hd_load1<T>(q + (size_t)(5 + cc) * HW);
                         if (__fmul_rn(hd_sigmoid(lg), po) == cf) { j[k] = cc; break; }
                     }
                 }
@@ -184,7 +205,7 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
     }
 }
 
-template <bool VEC>
+template <bool VEC, typename T = float>
 __global__ void __launch_bounds__(256, 4) yolo_decode_filter_kernel(const __grid_constant__ YoloParams p,
                                                                  float4* __restrict__ cand_box,
                                                                  float* __restrict__ cand_score,
@@ -193,7 +214,7 @@ __global__ void __launch_bounds__(256, 4) yolo_decode_filter_kernel(const __grid
                                                                  int* __restrict__ cand_count) {
     const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.total_items) return;
-    yolo_decode_item<VEC>(p, item, threadIdx.x & 31, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
+    yolo_decode_item<VEC, T>(p, item, threadIdx.x & 31, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -220,7 +241,7 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const __grid_constant_
     const int HW = p.HW[l], W = p.W[l];
     const int cell = t * 32 + lane;
     const bool valid = cell < HW;
-    const float* __restrict__ base = p.data[l] + ((size_t)(b * p.A + a) * p.no) * HW + cell;
+    const float* __restrict__ base = reinterpret_cast<const float*>(p.data[l]) + ((size_t)(b * p.A + a) * p.no) * HW + cell;
     const float s = p.stride[l];
     const int gi = cell / W, gj = cell - gi * W;
     for (int c0 = 0; c0 < p.no; c0 += 8) {  // eight independent plane loads in flight per lane
@@ -366,15 +387,18 @@ extern "C" HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels, int n_l
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0) return HD_OK;
     HD_CUDA_CALL(cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)B, st));
+    const int dt = (flags & HD_FLAG_IN_F16) ? 1 : ((flags & HD_FLAG_IN_BF16) ? 2 : 0);
+    HD_CHECK_ARG(!((flags & HD_FLAG_IN_F16) && (flags & HD_FLAG_IN_BF16)), "HD_FLAG_IN_F16 and HD_FLAG_IN_BF16 are exclusive");
     bool vec = true;
-    for (int l = 0; l < n_levels; ++l) vec = vec && (p.HW[l] % 4 == 0) && (((uintptr_t)p.data[l] & 15) == 0);
+    for (int l = 0; l < n_levels; ++l) vec = vec && (p.HW[l] % 4 == 0) && (((uintptr_t)p.data[l] & (dt ? 7 : 15)) == 0);
     const int warps = 8;
     long long blocks = (p.total_items + warps - 1) / warps;
     HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
-    if (vec)
-        yolo_decode_filter_kernel<true><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count);
-    else
-        yolo_decode_filter_kernel<false><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count);
+#define HD_YOLO_LAUNCH(V, T) yolo_decode_filter_kernel<V, T><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count)
+    if (dt == 0) { if (vec) HD_YOLO_LAUNCH(true, float); else HD_YOLO_LAUNCH(false, float); }
+    else if (dt == 1) { if (vec) HD_YOLO_LAUNCH(true, HdF16); else HD_YOLO_LAUNCH(false, HdF16); }
+    else { if (vec) HD_YOLO_LAUNCH(true, HdBF16); else HD_YOLO_LAUNCH(false, HdBF16); }
+#undef HD_YOLO_LAUNCH
     HD_CUDA_LAUNCH_CHECK("yolo_decode_filter_kernel");
     return HD_OK;
 }

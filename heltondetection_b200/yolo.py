@@ -20,7 +20,14 @@ def _is_pinned_host(x):
     return (not x.is_cuda) and x.is_pinned()
 
 
-def _levels(outputs, anchors, strides, host_ok=False):
+_HALF_FLAGS = {torch.float16: 4, torch.bfloat16: 8}   # HD_FLAG_IN_F16 / HD_FLAG_IN_BF16
+
+
+def _dtype_flag(keep):
+    return _HALF_FLAGS.get(keep[0].dtype, 0)
+
+
+def _levels(outputs, anchors, strides, host_ok=False, half_ok=False):
     if len(outputs) != len(anchors) or len(outputs) != len(strides):
         raise RuntimeError("outputs, anchors and strides must have one entry per level")
     A = len(anchors[0])
@@ -36,7 +43,10 @@ def _levels(outputs, anchors, strides, host_ok=False):
             _lib.require_cuda(x)
         if x.dim() != 4 or x.shape[0] != B or x.shape[1] != Ctot or len(anc) != A:
             raise RuntimeError(f"level {l}: expected [B={B}, {Ctot}, H, W], got {tuple(x.shape)}")
-        x = _lib.f32c(x)
+        if half_ok and x.dtype in _HALF_FLAGS and x.dtype == outputs[0].dtype:
+            x = x if x.is_contiguous() else x.contiguous()   # 16-bit heads are widened to fp32 inside the kernel
+        else:
+            x = _lib.f32c(x)
         keep.append(x)
         arr[l].data = x.data_ptr()
         arr[l].H, arr[l].W, arr[l].stride = x.shape[2], x.shape[3], float(s)
@@ -82,7 +92,9 @@ class YoloPostprocessor:
     """Raw-head post-process: decode+filter+compaction kernel, then per-image sort+NMS kernels.
 
     __call__(outputs) -> (det [B,max_det,6] = x1,y1,x2,y2,conf,cls ; count [B] int32 ; idx [B,max_det] anchor ids)
-    all on the device, padded, with no host synchronisation (CUDA-graph capturable)."""
+    all on the device, padded, with no host synchronisation (CUDA-graph capturable).  `outputs` may be fp32, or fp16 /
+    bf16 heads (an autocast model): the kernel widens them to fp32 on load and computes in fp32, i.e. the result equals
+    the fp32 path run on ``outputs.float()``, at half the HBM traffic."""
 
     def __init__(self, anchors=DEFAULT_ANCHORS, strides=DEFAULT_STRIDES, conf_thres=0.25, iou_thres=0.45,
                  agnostic=False, max_det=300, max_nms=30000, max_wh=7680.0, class_mode="offset", ge=False,
@@ -129,7 +141,7 @@ class YoloPostprocessor:
             det, count, rep = peer.local(slot)[0], peer.local(slot)[1], peer.replicas(slot)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().hd_yolo_postprocess_replicated(
-                arr, len(keep), B, A, nc, self.conf_thres, self.iou_thres, self.flags, self.class_mode, self.max_wh, self.max_nms,
+                arr, len(keep), B, A, nc, self.conf_thres, self.iou_thres, self.flags | self._dflag, self.class_mode, self.max_wh, self.max_nms,
                 self.max_det, _lib.ptr(det), _lib.ptr(self.f_idx), _lib.ptr(count), rep, _lib.ptr(self.f_ws), self.f_ws_bytes,
                 _lib.stream()))
         return det, count, self.f_idx
@@ -140,16 +152,17 @@ class YoloPostprocessor:
         # the level table only depends on the pointers/shapes: rebuild it when they change
         sig = tuple((x.data_ptr(), tuple(x.shape), x.dtype, x.is_contiguous()) for x in outputs)
         if getattr(self, "_sig", None) != sig:
-            self._lv = _levels(outputs, self.anchors, self.strides, host_ok=True)
+            self._lv = _levels(outputs, self.anchors, self.strides, host_ok=True, half_ok=True)
             self._sig = sig
         arr, keep, B, A, nc, total = self._lv
+        self._dflag = _dtype_flag(keep)
         if self.one_call:
             return self._one_call(arr, keep, B, A, nc, total, peer, slot)
         if peer is not None:
             raise RuntimeError("replicated (peer) outputs need the one-call path")
         buf = self.buffers(B, total, self._out_device(keep))
         _lib.check(_lib.lib().hd_yolo_decode_filter(
-            arr, len(keep), B, A, nc, self.conf_thres, self.flags, _lib.ptr(buf.box), _lib.ptr(buf.score),
+            arr, len(keep), B, A, nc, self.conf_thres, self.flags | self._dflag, _lib.ptr(buf.box), _lib.ptr(buf.score),
             _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))
         _run_nms(buf, self.iou_thres, self.class_mode, self.max_wh, self.max_nms)
         return buf.det, buf.out_count, buf.idx
@@ -167,10 +180,10 @@ class YoloPostprocessor:
 
     def candidates(self, outputs):
         """decode+filter only -> per image (cand [n,6], anchor idx [n]) sorted by anchor index (test helper)."""
-        arr, keep, B, A, nc, total = _levels(outputs, self.anchors, self.strides)
+        arr, keep, B, A, nc, total = _levels(outputs, self.anchors, self.strides, half_ok=True)
         buf = self.buffers(B, total, keep[0].device)
         _lib.check(_lib.lib().hd_yolo_decode_filter(
-            arr, len(keep), B, A, nc, self.conf_thres, self.flags, _lib.ptr(buf.box), _lib.ptr(buf.score),
+            arr, len(keep), B, A, nc, self.conf_thres, self.flags | _dtype_flag(keep), _lib.ptr(buf.box), _lib.ptr(buf.score),
             _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))
         return _collect_candidates(buf)
 

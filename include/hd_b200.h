@@ -47,6 +47,8 @@ extern "C" {
 /* flags */
 #define HD_FLAG_CONF_GE 1     /* keep conf >= thr (bubbliiiing) instead of conf > thr (ultralytics) */
 #define HD_FLAG_DENSE_READ 2  /* stream every head element (no objectness-tile skip) */
+#define HD_FLAG_IN_F16 4      /* hd_yolo_decode_filter / hd_yolo_postprocess*: levels[].data points to IEEE half heads */
+#define HD_FLAG_IN_BF16 8     /* ... to bfloat16 heads.  Elements are widened to fp32 on load (exact); all arithmetic is fp32 */
 
 /* class handling of the batched NMS */
 #define HD_NMS_AGNOSTIC 0

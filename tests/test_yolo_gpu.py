@@ -135,3 +135,32 @@ def test_zero_copy_pinned_host_inputs(cfg1):
         assert torch.equal(ref[0][i, :n], got[0][i, :n])
     with pytest.raises(RuntimeError, match="CUDA-only"):
         yolo.YoloPostprocessor()(cfg1)          # pageable host memory is refused
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("dense", [False, True])
+def test_half_precision_heads_equal_the_fp32_path_on_widened_inputs(dtype, dense):
+    """8f-4: 16-bit heads are widened to fp32 on load (exact), so the result must be bit-identical to the fp32
+    kernels run on heads.to(dtype).float() -- and through that equal to the oracle on the same widened inputs."""
+    import oracle
+    from heltondetection_b200 import synth, yolo
+    heads, _ = synth.yolo_heads(3, 320, 20, 12, 99)
+    h16 = [h.to(dtype).cuda() for h in heads]
+    h32 = [h.float() for h in h16]
+    pp = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=dense)
+    d16, c16, i16 = [t.clone() for t in pp(h16)]
+    d32, c32, i32 = [t.clone() for t in pp(h32)]
+    assert torch.equal(c16, c32)
+    for b in range(3):
+        n = int(c16[b])
+        assert torch.equal(d16[b, :n], d32[b, :n]) and torch.equal(i16[b, :n], i32[b, :n])
+    ref, ridx = oracle.yolo.non_max_suppression(oracle.yolo.decode_box([h.cpu() for h in h32]), 0.25, 0.45, return_index=True)
+    for b in range(3):
+        n = int(c16[b])
+        assert torch.equal(i16[b, :n].cpu(), ridx[b])
+    # odd spatial size -> scalar (non-vectorised) loads
+    odd = [torch.randn(2, 3 * 8, 13, 11).to(dtype).cuda(), torch.randn(2, 3 * 8, 7, 5).to(dtype).cuda(), torch.randn(2, 3 * 8, 3, 3).to(dtype).cuda()]
+    a = yolo.YoloPostprocessor(conf_thres=0.3, dense_read=dense).candidates(odd)
+    bq = yolo.YoloPostprocessor(conf_thres=0.3, dense_read=dense).candidates([o.float() for o in odd])
+    for (ca, ia), (cb, ib) in zip(a, bq):
+        assert torch.equal(ca, cb) and torch.equal(ia, ib)

@@ -71,6 +71,20 @@ def cfg2():
     yolo_cfg("cfg2", 256, 640, 80, 20, 1235, 0.25, 0.45, False)
 
 
+def cfg2_half():
+    """8f-4: the same cfg2 batch with fp16 / bf16 heads (widened to fp32 in the kernel): half the bytes"""
+    heads_cpu, _ = synth.yolo_heads(256, 640, 80, 20, 1235)
+    for dt in (torch.float16, torch.bfloat16):
+        heads = [h.to(dt).cuda() for h in heads_cpu]
+        nbytes = sum(h.numel() * 2 for h in heads)
+        for mode in (True, False):
+            pp = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=mode)
+            rp, det, cnt, idx = pp.graph(heads)
+            t = timeit(rp, iters=50)
+            report(f"cfg2 {str(dt)[6:]} heads, full postprocess, graph ({'dense' if mode else 'sparse'})", t, nbytes, 256)
+        del heads
+
+
 def cfg4():
     yolo_cfg("cfg4", 64, 1280, 10, 300, 1238, 0.001, 0.6, True)
 
@@ -235,7 +249,7 @@ def cpu():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg2", "cfg3", "roihead", "cfg4", "cfg5", "zerocopy", "cpu"]
+    which = sys.argv[1:] or ["cfg2", "cfg2_half", "cfg3", "roihead", "cfg4", "cfg5", "zerocopy", "cpu"]
     torch.cuda.set_device(0)
     for w in which:
         print(f"==== {w}", flush=True)
