@@ -25,6 +25,21 @@ template <> __device__ __forceinline__ void hd_load4<float>(const float* q, floa
     const float4 w = hd_ldg_stream4(q);
     v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
 }
+// the same four elements kept packed until they are consumed: 16-bit heads then hold twice the planes in flight per register
+template <typename T> struct HdRaw4 { unsigned lo, hi; };
+template <> struct HdRaw4<float> { float4 w; };
+template <typename T> __device__ __forceinline__ HdRaw4<T> hd_load_raw4(const T* q) {
+    HdRaw4<T> r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.lo), "=r"(r.hi) : "l"(q));
+    return r;
+}
+template <> __device__ __forceinline__ HdRaw4<float> hd_load_raw4<float>(const float* q) { HdRaw4<float> r; r.w = hd_ldg_stream4(q); return r; }
+template <typename T> __device__ __forceinline__ void hd_unpack4(const HdRaw4<T>& r, float* v) {
+    T e;
+    e.v = (unsigned short)(r.lo & 0xffffu); v[0] = hd_widen(e); e.v = (unsigned short)(r.lo >> 16); v[1] = hd_widen(e);
+    e.v = (unsigned short)(r.hi & 0xffffu); v[2] = hd_widen(e); e.v = (unsigned short)(r.hi >> 16); v[3] = hd_widen(e);
+}
+template <> __device__ __forceinline__ void hd_unpack4<float>(const HdRaw4<float>& r, float* v) { v[0] = r.w.x; v[1] = r.w.y; v[2] = r.w.z; v[3] = r.w.w; }
 
 struct YoloParams {
     const void* data[HD_MAX_LEVELS];
@@ -121,18 +136,36 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
             m[k] = g ? v[k] : m[k];
         }
     };
-    constexpr int U = 8;
     int c = 0;
-    for (; c + U <= p.nc; c += U) {
-        float v[U][4];
+    if (VEC) {
+        // U independent plane loads in flight per lane (same bytes in flight for 32-bit and 16-bit heads)
+        constexpr int U = (sizeof(T) == 4) ? 8 : 16;
+        const bool ld = valid[0] && need;
+        for (; c + U <= p.nc; c += U) {
+            HdRaw4<T> raw[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
+            for (int u = 0; u < U; ++u)
+                if (ld) raw[u] = hd_load_raw4<T>(base + (size_t)(5 + c + u) * HW);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[u][k] = -INFINITY;
-            load4(5 + c + u, v[u]);
+            for (int u = 0; u < U; ++u) {
+                float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (ld) hd_unpack4<T>(raw[u], v);
+                upd(v, c + u);
+            }
         }
+    } else {
+        constexpr int U = 8;
+        for (; c + U <= p.nc; c += U) {
+            float v[U][4];
 #pragma unroll
-        for (int u = 0; u < U; ++u) upd(v[u], c + u);
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[u][k] = -INFINITY;
+                load4(5 + c + u, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) upd(v[u], c + u);
+        }
     }
     for (; c < p.nc; ++c) {
         float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
