@@ -73,6 +73,8 @@ SIGNATURES = {
     "hd_roi_head_postprocess_workspace_size": (_sz, [_i, _i, _i]),
     "hd_roi_head_postprocess": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(C.c_float), _i, _f, _f, _f, _d, _f, _d, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hd_scale_detections": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    "hd_match_workspace_size": (_sz, [_i, _i, _i]),
+    "hd_match": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _d, _d, _i, _vp, _vp, _vp, _sz, _vp]),
     "hd_wbf_workspace_size": (_sz, [_i, _i, _i, _i]),
     "hd_wbf": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_double), _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hd_tta_map_back": (_i, [_vp, _vp, _i, _i, _f, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -216,6 +216,20 @@ HD_API int hd_scale_detections(const float* det, const int32_t* count, int B, in
                                void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * IoU-based label assignment (training-side user of box_iou): torchvision det_utils.Matcher
+ * (models/detection/_utils.py:318-400) over box_iou (boxes.py:308-370) without materialising the [G,N] matrix.
+ *   gt_boxes [B, Gmax, 4] with gt_count[b] (nullable: all Gmax) valid rows; pred_boxes [N,4] shared by all images
+ *   (anchors; pred_per_image = 0) or [B,N,4] (proposals; pred_per_image = 1).
+ *   matches [B,N] int64: index of the best GT (first on ties), -1 if its IoU < low, -2 if low <= IoU < high; with
+ *   allow_low_quality every prediction that attains some GT's best IoU keeps its arg-max match.
+ *   matched_iou [B,N] (nullable): the best IoU.  Boxes are expected proper (x2 >= x1, y2 >= y1).
+ * ------------------------------------------------------------------------------------------- */
+HD_API size_t hd_match_workspace_size(int B, int Gmax, int N);
+HD_API int hd_match(const float* gt_boxes, const int32_t* gt_count, int B, int Gmax, const float* pred_boxes, int pred_per_image, int N,
+                    double high_threshold, double low_threshold, int allow_low_quality, int64_t* matches, float* matched_iou,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * RPN proposal creation (README.md:8,63-65; lineage ProposalCreator / loc2bbox, SURVEY.md A.3;
  * cross-check torchvision models/detection/rpn.py:231-297, _utils.py:183-224).
  * Per level: objectness [B, A, H, W] (sigmoid) or [B, 2A, H, W] (HD_RPN_SOFTMAX, channel a*2+{bg,fg}),
