@@ -81,6 +81,7 @@ SIGNATURES = {
     "hd_roi_align": (_i, [C.POINTER(RoiLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "hd_roi_pool": (_i, [C.POINTER(RoiLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "hd_roi_set_mode": (_i, [_i]),
+    "hd_roi_align_backward": (_i, [_vp, _vp, _vp, _i64, C.POINTER(RoiLevel), _i, _i, _i, _i, _i, _i, _i, _vp]),
     "hd_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "hd_roi_level_map": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp]),
 }

@@ -94,9 +94,47 @@ def _run(features, scales, rois, level_ids, output_size, sampling_ratio, aligned
     return (out, argmax) if return_argmax else out
 
 
+def roi_align_backward(grad, rois, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width, sampling_ratio, aligned,
+                       channels_last=True):
+    """torch.ops.torchvision._roi_align_backward schema -> grad_input [B,C,H,W] (channels_last memory by default: the layout whose
+    kernel adds a channel quad with one 128-bit reduction)."""
+    _lib.require_cuda(grad, rois)
+    grad, rois = _lib.f32c(grad), _lib.f32c(rois.to(torch.float32))
+    if channels_last:   # NHWC storage viewed as [B,C,H,W] (= torch.channels_last)
+        gi = torch.zeros((batch_size, height, width, channels), dtype=torch.float32, device=grad.device).permute(0, 3, 1, 2)
+    else:
+        gi = torch.zeros((batch_size, channels, height, width), dtype=torch.float32, device=grad.device)
+    K = rois.shape[0]
+    if K == 0:
+        return gi
+    arr = _levels_struct([gi], [spatial_scale])
+    arr[0].H, arr[0].W = height, width
+    lay = _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW
+    _lib.check(_lib.lib().hd_roi_align_backward(_lib.ptr(grad), _lib.ptr(rois), None, K, arr, 1, lay, channels, int(pooled_height), int(pooled_width),
+                                                int(sampling_ratio), int(bool(aligned)), _lib.stream()))
+    return gi
+
+
+class _RoIAlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, rois, output_size, spatial_scale, sampling_ratio, aligned, layout):
+        ctx.save_for_backward(rois)
+        ctx.args = (tuple(input.shape), _pair(output_size), float(spatial_scale), int(sampling_ratio), bool(aligned), _is_channels_last(input))
+        return _run([input], [spatial_scale], rois, None, output_size, sampling_ratio, aligned, False, layout)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (rois,) = ctx.saved_tensors
+        (B, C, H, W), (PH, PW), scale, sr, al, cl = ctx.args
+        gi = roi_align_backward(grad, rois, scale, PH, PW, B, C, H, W, sr, al, channels_last=cl)
+        return gi, None, None, None, None, None, None
+
+
 def roi_align(input, boxes, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, layout="auto"):
-    """torchvision.ops.roi_align (roi_align.py:204-260)."""
+    """torchvision.ops.roi_align (roi_align.py:204-260); differentiable w.r.t. `input` (RoIAlign backward kernels)."""
     rois = _check_rois(boxes)
+    if input.requires_grad and torch.is_grad_enabled():
+        return _RoIAlignFn.apply(input, rois, output_size, spatial_scale, sampling_ratio, aligned, layout)
     return _run([input], [spatial_scale], rois, None, output_size, sampling_ratio, aligned, False, layout)
 
 

@@ -167,6 +167,14 @@ HD_API int hd_roi_align(const hd_roi_level* levels /*host*/, int n_levels, int l
 HD_API int hd_roi_pool(const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, const float* rois,
                        const int32_t* level_ids, int64_t K, int pooled_h, int pooled_w, float* out, int32_t* argmax,
                        void* stream);
+/* RoIAlign backward (torchvision _roi_align_backward): grad_out [K,C,PH,PW] is scattered into the gradient
+ * buffers levels[l].data (written through, although the struct declares them const; same shapes/layout as the forward
+ * inputs), which the caller has zero-filled: grad_in[b,c,y,x] += grad_out[k,c,ph,pw] * w_corner / count per sample.
+ * NHWC with C % 4 == 0 uses 128-bit reductions; NCHW / other C use scalar atomics (single level only).  The order of the
+ * floating-point additions is not deterministic. */
+HD_API int hd_roi_align_backward(const float* grad_out, const float* rois, const int32_t* level_ids, int64_t K,
+                                 const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, int pooled_h, int pooled_w,
+                                 int sampling_ratio, int aligned, void* stream);
 /* RoIAlign kernel choice (process-wide; developer / test aid): 0 = automatic (the gather kernels), 1 = gather kernels only,
  * 2 = experimental staged-row (TMA ring) kernel whenever eligible (NHWC, C % 4 == 0, sampling_ratio 1 or 2, output <= 8x8;
  * bit-identical results, currently slower).  Returns the previous mode. */

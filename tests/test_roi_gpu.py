@@ -146,3 +146,25 @@ def test_staged_row_kernel_multilevel_large():
     assert torch.equal(gl.cpu(), rl)
     assert torch.equal(res[1], res[2])
     assert close(res[2], ref)
+
+
+@pytest.mark.parametrize("channels_last", [True, False])
+@pytest.mark.parametrize("C,sr,aligned", [(64, 2, False), (64, 0, True), (6, 2, True), (256, 1, False)])
+def test_roi_align_backward_matches_torchvision(channels_last, C, sr, aligned):
+    """8f-3: gradient w.r.t. the feature map against torchvision's CPU backward; the additions are the same terms in a
+    different order, so the bar is 1e-5 of the largest accumulated gradient."""
+    from heltondetection_b200 import ops, roi
+    x, rois = _data(B=2, C=C, H=40, W=36, K=200, img=320, seed=21)
+    g = torch.Generator().manual_seed(5)
+    go = torch.randn((rois.shape[0], C, 7, 7), generator=g)
+    ref = torch.ops.torchvision._roi_align_backward(go, rois, 0.125, 7, 7, 2, C, 40, 36, sr, aligned)
+    got = roi.roi_align_backward(go.cuda(), rois.cuda(), 0.125, 7, 7, 2, C, 40, 36, sr, aligned, channels_last=channels_last).cpu()
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    # through autograd
+    xin = (x.cuda().contiguous(memory_format=torch.channels_last) if channels_last else x.cuda()).requires_grad_(True)
+    out = ops.roi_align(xin, rois.cuda(), 7, 0.125, sr, aligned)
+    out.backward(go.cuda())
+    xr = x.clone().requires_grad_(True)
+    torchvision.ops.roi_align(xr, rois, 7, 0.125, sr, aligned).backward(go)
+    assert float((xin.grad.cpu() - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
