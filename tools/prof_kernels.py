@@ -32,6 +32,25 @@ out, lv = roi.multilevel_roi_align(feats, rois, 7, scales, 2, False)            
 out, lv = roi.multilevel_roi_align(feats, rois, 7, scales, 2, False, op="pool", layout="nhwc")
 print("cfg3 proposals/img", cnt.tolist(), out.shape)
 iou = ops.box_iou(rois[:2000, 1:], rois[2000:4000, 1:])
+# next rows (8f): RoI-head post-process, label assignment, RoIAlign backward, fp16 heads
+from heltondetection_b200 import roi_head, assign  # noqa: E402
+g = torch.Generator().manual_seed(1240)
+R = rois.shape[0] // B
+lg = (torch.randn(B * R, 81, generator=g) * 3).cuda()
+rg = (torch.randn(B * R, 324, generator=g) * 0.5).cuda()
+det, didx, dcnt = roi_head.RoIHeadPostprocessor((img, img), 0.05, 0.5, 100)(lg, rg, rois, cnt, B=B)
+sc_ = roi_head.scale_coords((img, img), det, [(1080, 1920)] * B, dcnt, xywh=True)
+gtb = rois[:64, 1:].contiguous()
+m = assign.Matcher(0.7, 0.3, True)(gtb, rois[:, 1:].contiguous())
+nhwc0 = feats[0].contiguous(memory_format=torch.channels_last)
+gi = roi.roi_align_backward(out[:2000].contiguous(), rois[:2000].contiguous(), 0.25, 7, 7, B, 256, nhwc0.shape[2], nhwc0.shape[3], 2, False)
+roi.set_mode(2)
+o2 = roi.roi_align(nhwc0, rois[:2000].contiguous(), 7, 0.25, 2, False)
+roi.set_mode(0)
+h16, _ = synth.yolo_heads(64, 640, 80, 20, 1235)
+d16 = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=True)([h.half().cuda() for h in h16])
+del h16
+print("8f rows ok", dcnt.tolist(), int((m >= 0).sum()))
 # cfg5
 views, _ = synth.tta_heads(8, 640, 80, G=20, seed=1239)
 fusion = wbf.TTAFusion([(r, f, s) for (_, r, f, s) in views], (640, 640), 80, max_det=300, iou_thr=0.55, skip_box_thr=0.001)
