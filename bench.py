@@ -47,6 +47,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.recording = False   # the thread starts during warm-up (first NVML calls are slow); only the timed region is kept
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -71,11 +72,13 @@ class ClockSampler(threading.Thread):
         }
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                if self.recording:
+                    self.samples.append(mhz)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(self.period)
@@ -191,6 +194,8 @@ def main():
         elif gather is not None:
             gather.finish()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for k in range(max(args.warmup, 3)):
         run_step(k)
     join()
@@ -199,11 +204,10 @@ def main():
     K = args.steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     ev_end = torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.recording = True
     for k in range(K):
         replay, det, cnt = replays[k % len(replays)]
         ev[k][0].record()
@@ -219,6 +223,7 @@ def main():
     join()                                    # every gather completes inside the timed region
     ev_end.record()
     torch.cuda.synchronize()
+    sampler.recording = False
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
