@@ -1,0 +1,359 @@
+// Greedy NMS of one image spread over a thread-block CLUSTER (shared by the RPN proposal kernel and the batched detection NMS).
+// Input: n boxes already in score order (rank = position) in global memory; output: the ranks of the first max_det keeps.
+// See rpn.cu for the description of the phases (size-stratified spatial hash -> adjacency lists -> Jacobi resolve, in rank
+// batches with early stop).  With CLS, boxes only interact inside their class (torchvision batched_nms): the class joins the
+// hash key and the exact test.  All CTAs of the cluster must call; the result is meaningful in CTA 0.
+#pragma once
+#include "hd_nms_core.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define RPNC_MAXCL 8       // CTAs per image: 1, 2, 4 or 8 (the portable cluster maximum), chosen per launch
+#define RPNC_MAXN 16384    // segment limit: the merge step holds all composites in shared memory (128 KB)
+#define RPNC_ADJ 64        // suppressor candidates stored per box
+#define RPNC_LOG2T 12
+#define RPNC_T (1 << RPNC_LOG2T)
+#define RPNC_NCLS 64
+
+// size class of a (positive) area: its binary exponent, clamped; monotone in the area
+__device__ __forceinline__ int rpnc_class(float area) { return min(max((__float_as_int(area) >> 23) - 127 + 16, 0), RPNC_NCLS - 1); }
+// 1 / cell size of class c: cell = 2^((c-16)/2) = the side of the smallest square box of the class
+__device__ __forceinline__ float rpnc_inv_cell(int c) { return exp2f(-0.5f * (float)(c - 16)); }
+__device__ __forceinline__ uint32_t rpnc_hash(int gx, int gy, int c) {
+    return ((((uint32_t)gx * 0x9E3779B1u) ^ ((uint32_t)gy * 0x85EBCA77u) ^ ((uint32_t)c * 0x27D4EB2Fu)) * 0xC2B2AE3Du) >> (32 - RPNC_LOG2T);
+}
+
+struct HdClSmem {          // static shared memory of the cluster NMS (one per CTA)
+    int hist2[2][256];
+    int tot[256];
+    int wsum[32];
+    float cinv[RPNC_NCLS], cgx[RPNC_NCLS], cgy[RPNC_NCLS];
+    uint32_t kept[RPNC_MAXN / 32 + 64];   // resolve state of CTA 0: bitmap over ranks
+    int done, total;
+};
+struct HdClLayout { int cen_off, irk_off, acnt_off, queue_off, queue_cap; };   // dynamic shared memory (bytes..., entries)
+struct HdClWs {            // per-image global scratch
+    const float4* sbox;    // [n] boxes by rank
+    const int* scls;       // [n] classes by rank (CLS only)
+    float4* gbox; int* grank;           // [n] bucket-ordered boxes and their ranks
+    int* adj_cnt; unsigned short* adj;  // [n], [n, RPNC_ADJ]
+    int* fallback;         // this image's "redo with the single-CTA kernel" flag
+    int* keep_r;           // [max_det] out: ranks of the keeps
+};
+static inline void hd_cluster_layout(int cap, size_t budget, HdClLayout* L, size_t* bytes) {
+    L->cen_off = (int)hd_align_up(((size_t)RPNC_T + 1) * 4, 16);
+    L->irk_off = (int)hd_align_up((size_t)L->cen_off + (size_t)cap * 8, 16);
+    L->acnt_off = (int)hd_align_up((size_t)L->irk_off + (size_t)cap * 2, 16);
+    L->queue_off = (int)hd_align_up((size_t)L->acnt_off + (size_t)1024 * 4, 16);
+    size_t want = (size_t)L->queue_off + 64 * 1024;                  // buckets + centres + ranks + candidate queue
+    if (want > budget) want = budget;
+    if (want < (size_t)L->queue_off + (size_t)RPNC_T * 4) want = (size_t)L->queue_off + (size_t)RPNC_T * 4;
+    if (*bytes < want) *bytes = want;
+    L->queue_cap = (int)((*bytes - L->queue_off) / 4);
+}
+
+#ifdef __CUDACC__
+template <int NT, bool CLS>
+__device__ int hd_cluster_greedy_nms(cg::cluster_group& cluster, unsigned char* dsm, const HdClLayout& L, HdClSmem& sm, const HdClWs& w, int n,
+                                     int max_det, float thr) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int crank = (int)cluster.block_rank(), CL = (int)cluster.num_blocks();
+    const float4* sbox = w.sbox;
+    // ---- N: greedy NMS in rank batches.  Only the ranks up to the n_post-th keep matter, so the first batch covers the
+    // top max(2 n_post, 128 CL) ranks and the second (rarely needed) the rest.  Per batch [lo_r, hi_r):
+    //   N1  size-stratified spatial hash over the ranks < hi_r, built cooperatively: a proper box of area a belongs to
+    //       class c = exponent(a) and is hashed by (centre / 2^(c/2), c) -- cells scale with the boxes they hold, so a
+    //       query touches a handful of cells whatever the box size;
+    //   N2  adjacency lists of the ranks in [lo_r, hi_r), an even share per CTA;
+    //   N3  CTA 0 resolves them 1024 ranks at a time and tells the cluster whether it is done.
+    // Class tables (max width/height per class -> growth of the query window) come from a reduction over all n boxes
+    // that every CTA runs itself (max is order independent -> identical in all CTAs).
+    int* s_cw = sm.hist2[0];   // [RPNC_NCLS] max width per class (float bits), the select histograms are dead
+    int* s_ch = sm.hist2[1];
+    for (int i = tid; i < RPNC_NCLS; i += NT) { s_cw[i] = 0; s_ch[i] = 0; }
+    if (tid == 0) sm.total = 0;
+    for (int i = tid; i < (n + 31) / 32 + 33; i += NT) sm.kept[i] = 0u;
+    __syncthreads();
+    {
+        float cmax = 0.f;
+        for (int r = tid; r < n; r += NT) {
+            const float4 bx = sbox[r];
+            if (hd_box_proper(bx)) {
+                const int c = rpnc_class(hd_area(bx));
+                atomicMax(&s_cw[c], __float_as_int(bx.z - bx.x));   // positive floats order like their bit patterns
+                atomicMax(&s_ch[c], __float_as_int(bx.w - bx.y));
+                cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(bx.x), fabsf(bx.y)), fmaxf(fabsf(bx.z), fabsf(bx.w))));
+            }
+        }
+        atomicMax(&sm.total, __float_as_int(cmax));
+    }
+    __syncthreads();
+    const float slack = 5.0e-7f * __int_as_float(sm.total);
+    const float grow = fmaxf(0.0f, 0.5f - (thr - 1.0e-3f));
+    const float tq = thr - 1.0e-3f;
+    if (tid < RPNC_NCLS) {   // per-class query tables (inverse cell size, window growth); 0 marks an empty class
+        const float wc = __int_as_float(s_cw[tid]), hc = __int_as_float(s_ch[tid]);
+        sm.cinv[tid] = (wc > 0.0f) ? rpnc_inv_cell(tid) : 0.0f;
+        sm.cgx[tid] = grow * wc + slack; sm.cgy[tid] = grow * hc + slack;
+    }
+    int* start = reinterpret_cast<int*>(dsm);                                  // [T+1] bucket starts (cluster-wide)
+    int* hist = reinterpret_cast<int*>(dsm + L.queue_off);                     // [T] per-CTA counts, then scatter cursors (dead before the queue is used)
+    float2* cen = reinterpret_cast<float2*>(dsm + L.cen_off);                  // [items] centres, bucket by bucket
+    unsigned short* irk = reinterpret_cast<unsigned short*>(dsm + L.irk_off);  // [items] their ranks
+    int* acnt = reinterpret_cast<int*>(dsm + L.acnt_off);                      // [NT] list lengths of the round's boxes
+    uint32_t* queue = reinterpret_cast<uint32_t*>(dsm + L.queue_off);
+    int* grank = w.grank;
+    float4* gbox = w.gbox;
+    unsigned short* adj = w.adj;
+    int* adj_cnt = w.adj_cnt;
+    int* keep_r = w.keep_r;
+    // per-warp queue segments and counters (a single CTA-wide counter would serialise ~10^4 shared-memory atomics per round)
+    const int segcap = L.queue_cap / (NT / 32);
+    uint32_t* myq = queue + wid * segcap;
+    int* s_qn = sm.wsum;            // [32] entries queued by each warp
+    int* s_qpre = sm.tot;           // [33] their exclusive prefix
+    // cells of class c under the query window of box bq: origin (x1,y1), nx columns; returns the cell count
+    auto window = [&](const float4 bq, int c, int& x1, int& y1, int& nx, float& lx, float& hx, float& ly, float& hy) -> int {
+        const float inv = sm.cinv[c];
+        if (inv == 0.0f) return 0;
+        lx = bq.x - sm.cgx[c]; hx = bq.z + sm.cgx[c]; ly = bq.y - sm.cgy[c]; hy = bq.w + sm.cgy[c];
+        x1 = hd_cell(lx, inv); y1 = hd_cell(ly, inv);
+        const long long dx = (long long)hd_cell(hx, inv) - x1 + 1, dy = (long long)hd_cell(hy, inv) - y1 + 1;
+        if (dx * dy > 1024) { *w.fallback = 1; return 0; }   // low thresholds / degenerate geometry: single-CTA kernel
+        nx = (int)dx;
+        return (int)(dx * dy);
+    };
+    // exact test of box j (rank jr, round slot bl) against the higher-ranked box i (rank ir)
+    auto exact = [&](int bl, int jr, const float4 bq, int ir, const float4 bi) {
+        const float aq = hd_area(bq), ai = hd_area(bi);
+        const float amin = tq * aq, amax = (tq > 0.0f) ? aq / tq : 3.0e38f;
+        if (ai < amin || ai > amax) return;
+        if (CLS && w.scls[ir] != w.scls[jr]) return;   // (a bucket can hold other classes through hash collisions)
+        const float cx = 0.5f * (bi.x + bi.z), cy = 0.5f * (bi.y + bi.w);
+        const float gx = grow * (bi.z - bi.x) + slack, gy = grow * (bi.w - bi.y) + slack;
+        if (cx < bq.x - gx || cx > bq.z + gx || cy < bq.y - gy || cy > bq.w + gy) return;
+        if (hd_iou_gt(bi, ai, bq, aq, thr)) {
+            const int slot = atomicAdd(&acnt[bl], 1);
+            if (slot < RPNC_ADJ) adj[(size_t)jr * RPNC_ADJ + slot] = (unsigned short)ir;
+        }
+    };
+    int kc = 0;
+    const int first = max(2 * max_det, 128 * CL);
+    for (int lo_r = 0, hi_r = min(n, first);; lo_r = hi_r, hi_r = n) {
+        HD_PHASE(3);
+        // ---- N1
+        for (int i = tid; i < RPNC_T; i += NT) hist[i] = 0;
+        __syncthreads();
+        const int mg = (hi_r + CL - 1) / CL, glo = min(crank * mg, hi_r), glen = min(hi_r, glo + mg) - glo;
+        for (int i = tid; i < glen; i += NT) {
+            const float4 bx = sbox[glo + i];
+            if (hd_box_proper(bx)) {
+                const int c = rpnc_class(hd_area(bx));
+                const float inv = rpnc_inv_cell(c);
+                atomicAdd(&hist[rpnc_hash(hd_cell(0.5f * (bx.x + bx.z), inv), hd_cell(0.5f * (bx.y + bx.w), inv), c + (CLS ? RPNC_NCLS * w.scls[glo + i] : 0))], 1);
+            }
+        }
+        __syncthreads();
+        cluster.sync();
+        {
+            constexpr int PER = RPNC_T / NT;   // consecutive buckets per thread
+            static_assert(PER == 4, "one int4 of buckets per thread");
+            int tot[PER], myoff[PER];
+            int loc = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { tot[j] = 0; myoff[j] = 0; }
+            for (int c = 0; c < CL; ++c) {
+                const int4 v = reinterpret_cast<const int4*>(cluster.map_shared_rank(hist, c))[tid];
+                tot[0] += v.x; tot[1] += v.y; tot[2] += v.z; tot[3] += v.w;
+                if (c < crank) { myoff[0] += v.x; myoff[1] += v.y; myoff[2] += v.z; myoff[3] += v.w; }
+            }
+#pragma unroll
+            for (int j = 0; j < PER; ++j) loc += tot[j];
+            int incl = loc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
+            if (lane == 31) sm.wsum[wid] = incl;
+            cluster.sync();   // every CTA has read every histogram: they may now be overwritten with cursors
+            int pre = incl - loc;
+            for (int w = 0; w < wid; ++w) pre += sm.wsum[w];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const int h = tid * PER + j;
+                start[h] = pre; hist[h] = pre + myoff[j]; pre += tot[j];
+            }
+            if (tid == NT - 1) start[RPNC_T] = pre;
+        }
+        __syncthreads();
+        for (int i = tid; i < glen; i += NT) {
+            const float4 bx = sbox[glo + i];
+            if (hd_box_proper(bx)) {
+                const int c = rpnc_class(hd_area(bx));
+                const float inv = rpnc_inv_cell(c);
+                const int pos = atomicAdd(&hist[rpnc_hash(hd_cell(0.5f * (bx.x + bx.z), inv), hd_cell(0.5f * (bx.y + bx.w), inv), c + (CLS ? RPNC_NCLS * w.scls[glo + i] : 0))], 1);
+                gbox[pos] = bx; grank[pos] = glo + i;
+            }
+        }
+        cluster.sync();
+        HD_PHASE(4);
+        // ---- N2: box j looks for the higher-ranked boxes i with iou(i,j) > thr:
+        //   iou > t  =>  centre_i inside box_j grown by max(0, .5 - t) * (w_i, h_i),  and  area_i in [t * area_j, area_j / t],
+        // i.e. the 3 (t = 0.7) size classes around j's own, a handful of cells each.  Phase A: a lane owns one box of the
+        // round; the (box, cell) pairs of the warp's 32 boxes are dealt out to the lanes (prefix sums + a shuffle binary
+        // search), so every lane visits one cell per step whatever the box sizes; item centres and ranks sit in shared
+        // memory bucket by bucket; survivors of the centre and rank tests go to per-warp queues.  Phase B drains the
+        // queues with all threads: exact test on the full boxes (balanced, several loads in flight), hits appended to
+        // j's list through a shared-memory counter.
+        const int nitem = start[RPNC_T];
+        for (int i = tid; i < nitem; i += NT) {
+            const float4 bx = gbox[i];
+            cen[i] = make_float2(0.5f * (bx.x + bx.z), 0.5f * (bx.y + bx.w));
+            irk[i] = (unsigned short)grank[i];
+        }
+        // consecutive ranks go to different CTAs and different warps: the top ranks are the dense object clusters, whose
+        // long buckets would otherwise all land in the first warps.  Round slot `bl` of this CTA <-> rank slot_rank(bl).
+        const int slen = (hi_r - lo_r + CL - 1) / CL;              // slots per CTA (the last ones may be empty)
+        for (int b0 = 0; b0 < slen; b0 += NT) {
+            auto slot_rank = [&](int bl) { return lo_r + (b0 + ((bl & 31) << 5) + (bl >> 5)) * CL + crank; };
+            if (tid < NT / 32) s_qn[tid] = 0;
+            acnt[tid] = 0;
+            __syncthreads();
+            const int jr = slot_rank(tid);
+            const bool has = jr < hi_r;
+            float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has) bq = sbox[jr];
+            const int cq = (CLS && has) ? w.scls[jr] : 0;
+            int ncell = 0;
+            if (has && jr > 0 && hd_box_proper(bq)) {
+                const float aq = hd_area(bq);
+                const int c0 = rpnc_class(tq * aq), c1 = rpnc_class((tq > 0.0f) ? aq / tq : 3.0e38f);
+                for (int c = c0; c <= c1; ++c) { int x1, y1, nx; float lx, hx, ly, hy; ncell += window(bq, c, x1, y1, nx, lx, hx, ly, hy); }
+            }
+            int incl = ncell;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
+            const int pre = incl - ncell, total = __shfl_sync(HD_FULL, incl, 31);
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                int src = 0;                                       // largest lane whose prefix is <= t
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) { const int v = __shfl_sync(HD_FULL, pre, src + d); if (v <= t) src += d; }
+                int local = t - __shfl_sync(HD_FULL, pre, src);
+                float4 bs;
+                bs.x = __shfl_sync(HD_FULL, bq.x, src); bs.y = __shfl_sync(HD_FULL, bq.y, src);
+                bs.z = __shfl_sync(HD_FULL, bq.z, src); bs.w = __shfl_sync(HD_FULL, bq.w, src);
+                const int cs = CLS ? __shfl_sync(HD_FULL, cq, src) : 0;
+                if (t >= total) continue;
+                const int sbl = (wid << 5) + src, sjr = slot_rank(sbl);
+                const float aq = hd_area(bs);
+                const int c1 = rpnc_class((tq > 0.0f) ? aq / tq : 3.0e38f);
+                int c = rpnc_class(tq * aq), x1 = 0, y1 = 0, nx = 1;
+                float lx = 0.f, hx = 0.f, ly = 0.f, hy = 0.f;
+                for (; c <= c1; ++c) {
+                    const int nc2 = window(bs, c, x1, y1, nx, lx, hx, ly, hy);
+                    if (local < nc2) break;
+                    local -= nc2;
+                }
+                if (c > c1) continue;                              // (cannot happen: the counts are recomputed identically)
+                const int gy = local / nx, gx = local - gy * nx;
+                const uint32_t hb = rpnc_hash(x1 + gx, y1 + gy, c + (CLS ? RPNC_NCLS * cs : 0));
+                const int s1 = start[hb + 1];
+                for (int kk = start[hb]; kk < s1; ++kk) {
+                    const float2 ce = cen[kk];
+                    if (ce.x < lx || ce.x > hx || ce.y < ly || ce.y > hy) continue;   // also rejects most hash collisions
+                    const int ir = irk[kk];
+                    if (ir >= sjr) continue;                                           // only higher-ranked boxes suppress
+                    const int slot = atomicAdd(&s_qn[wid], 1);
+                    if (slot < segcap) myq[slot] = ((uint32_t)sbl << 16) | (uint32_t)kk;
+                    else exact(sbl, sjr, bs, ir, gbox[kk]);
+                }
+            }
+            __syncthreads();
+            if (tid < 32) {
+                const int c = min(s_qn[tid], segcap);
+                int in2 = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, in2, d); if (lane >= d) in2 += y; }
+                s_qpre[tid] = in2 - c;
+                if (tid == 31) s_qpre[32] = in2;
+            }
+            __syncthreads();
+            const int nq = s_qpre[32];
+            for (int e0 = 0; e0 < nq; e0 += 2 * NT) {
+                int bl[2], ir[2]; float4 bb[2], bi[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int e = e0 + u * NT + tid;
+                    bl[u] = -1;
+                    if (e < nq) {
+                        int w = 0;                           // segment holding entry e
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) if (s_qpre[w + d] <= e) w += d;
+                        const uint32_t en = queue[w * segcap + (e - s_qpre[w])];
+                        bl[u] = (int)(en >> 16);
+                        const int pos = (int)(en & 0xffffu);
+                        ir[u] = irk[pos];
+                        bb[u] = sbox[slot_rank(bl[u])]; bi[u] = gbox[pos];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) if (bl[u] >= 0) exact(bl[u], slot_rank(bl[u]), bb[u], ir[u], bi[u]);
+            }
+            __syncthreads();
+            if (has) {
+                const int c = acnt[tid];
+                adj_cnt[jr] = min(c, RPNC_ADJ);
+                if (c > RPNC_ADJ) *w.fallback = 1;
+            }
+            __syncthreads();
+        }
+        cluster.sync();
+        HD_PHASE(5);
+        // ---- N3: CTA 0 resolves  kept[j] = !any(kept[i], i in adj[j])  1024 ranks at a time (Jacobi iteration to the
+        // unique fixed point = the greedy answer) and pushes "done" into every CTA of the cluster
+        if (crank == 0) {
+            int done = (hi_r >= n) ? 1 : 0;
+            if (*(volatile int*)w.fallback) done = 2;   // the single-CTA kernel redoes this image
+            for (int base = lo_r; done != 2 && base < hi_r && kc < max_det; base += NT) {
+                const int j = base + tid;
+                const bool in = j < hi_r;
+                const int cnt = in ? adj_cnt[j] : 0;
+                const unsigned short* lst = adj + (size_t)j * RPNC_ADJ;
+                const int wi = (base >> 5) + wid;
+                {
+                    const unsigned w0 = __ballot_sync(HD_FULL, in);
+                    if (lane == 0) sm.kept[wi] = w0;
+                }
+                __syncthreads();
+                for (;;) {
+                    bool nk = in;
+                    for (int e = 0; e < cnt; ++e) {
+                        const int i = lst[e];
+                        if ((sm.kept[i >> 5] >> (i & 31)) & 1u) { nk = false; break; }
+                    }
+                    const unsigned w1 = __ballot_sync(HD_FULL, nk);
+                    const bool ch = (w1 != sm.kept[wi]);
+                    __syncthreads();
+                    if (lane == 0) sm.kept[wi] = w1;
+                    if (!__syncthreads_or(ch)) break;
+                }
+                const unsigned wv = sm.kept[wi];
+                if (lane == 0) sm.wsum[wid] = __popc(wv);
+                __syncthreads();
+                int pre = kc, tot2 = kc;
+                for (int w = 0; w < NT / 32; ++w) { if (w < wid) pre += sm.wsum[w]; tot2 += sm.wsum[w]; }
+                if ((wv >> lane) & 1u) {
+                    const int pos = pre + __popc(wv & hd_lanemask_lt());
+                    if (pos < max_det) keep_r[pos] = j;
+                }
+                kc = min(tot2, max_det);
+                __syncthreads();
+            }
+            if (kc >= max_det && done == 0) done = 1;
+            if (tid < CL) *cluster.map_shared_rank(&sm.done, tid) = done;
+        }
+        cluster.sync();
+        if (sm.done) break;
+    }
+    return sm.done == 2 ? -1 : kc;
+}
+#endif  // __CUDACC__

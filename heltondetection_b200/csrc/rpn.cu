@@ -4,8 +4,7 @@
 // models/detection/rpn.py:231-297, _utils.py:183-224).
 #include "hd_sort.cuh"
 #include "hd_nms_core.cuh"
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
+#include "hd_cluster_nms.cuh"
 
 #define RPN_NT 1024
 #define RPN_U 8   // keys in flight per thread in the latency-bound scans over the N proposals of an image
@@ -352,21 +351,6 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
 //      fixed point (= the greedy answer), stopping at n_post keeps.
 // Bit-identical outputs to rpn_select_nms_kernel (same selection rule, same IoU predicate).
 // ------------------------------------------------------------------------------------------------
-#define RPNC_MAXCL 8       // CTAs per image: 1, 2, 4 or 8 (the portable cluster maximum), chosen per launch
-#define RPNC_MAXN 16384    // n_pre limit: the merge step holds all composites in shared memory (128 KB)
-#define RPNC_ADJ 64        // suppressor candidates stored per box
-#define RPNC_LOG2T 12
-#define RPNC_T (1 << RPNC_LOG2T)
-#define RPNC_NCLS 64
-
-// size class of a (positive) area: its binary exponent, clamped; monotone in the area
-__device__ __forceinline__ int rpnc_class(float area) { return min(max((__float_as_int(area) >> 23) - 127 + 16, 0), RPNC_NCLS - 1); }
-// 1 / cell size of class c: cell = 2^((c-16)/2) = the side of the smallest square box of the class
-__device__ __forceinline__ float rpnc_inv_cell(int c) { return exp2f(-0.5f * (float)(c - 16)); }
-__device__ __forceinline__ uint32_t rpnc_hash(int gx, int gy, int c) {
-    return ((((uint32_t)gx * 0x9E3779B1u) ^ ((uint32_t)gy * 0x85EBCA77u) ^ ((uint32_t)c * 0x27D4EB2Fu)) * 0xC2B2AE3Du) >> (32 - RPNC_LOG2T);
-}
-
 struct RpnClParams {
     RpnSelParams s;
     uint64_t* comp;      // [B,cap] compacted composites (index order)
@@ -379,20 +363,19 @@ struct RpnClParams {
     int* fallback;       // [B] set when an adjacency list overflows
     int per;             // keys per CTA slice
     int key_cache;       // 1: the slice is held in shared memory
-    int cen_off, irk_off, acnt_off, queue_off, queue_cap;   // dynamic shared memory layout of the adjacency phase (bytes..., entries)
+    HdClLayout lay;      // dynamic shared memory layout of the NMS phases
 };
 
 __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_cluster_kernel(const __grid_constant__ RpnClParams q) {
     extern __shared__ __align__(16) unsigned char dsm[];
-    __shared__ int s_hist[2][256];
-    __shared__ int s_tot[256];
-    __shared__ int s_wsum[RPN_NT / 32];
+    __shared__ HdClSmem csm;
+    int (&s_hist)[2][256] = csm.hist2;
+    int (&s_tot)[256] = csm.tot;
+    int (&s_wsum)[32] = csm.wsum;
+    int& s_total = csm.total;
     __shared__ int s_cnt[2];
-    __shared__ float s_cinv[RPNC_NCLS], s_cgx[RPNC_NCLS], s_cgy[RPNC_NCLS];
-    __shared__ uint32_t s_kept[RPNC_MAXN / 32 + 64];   // resolve state of CTA 0: bitmap over ranks
-    __shared__ int s_done;
     __shared__ uint32_t s_prefix;
-    __shared__ int s_need, s_base[2], s_total;
+    __shared__ int s_need, s_base[2];
 
     cg::cluster_group cluster = cg::this_cluster();
     const RpnSelParams& p = q.s;
@@ -596,299 +579,14 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_cluster_kernel(const
     }
     cluster.sync();
     HD_PHASE(3);
-    // ---- N: greedy NMS in rank batches.  Only the ranks up to the n_post-th keep matter, so the first batch covers the
-    // top max(2 n_post, 128 CL) ranks and the second (rarely needed) the rest.  Per batch [lo_r, hi_r):
-    //   N1  size-stratified spatial hash over the ranks < hi_r, built cooperatively: a proper box of area a belongs to
-    //       class c = exponent(a) and is hashed by (centre / 2^(c/2), c) -- cells scale with the boxes they hold, so a
-    //       query touches a handful of cells whatever the box size;
-    //   N2  adjacency lists of the ranks in [lo_r, hi_r), an even share per CTA;
-    //   N3  CTA 0 resolves them 1024 ranks at a time and tells the cluster whether it is done.
-    // Class tables (max width/height per class -> growth of the query window) come from a reduction over all n boxes
-    // that every CTA runs itself (max is order independent -> identical in all CTAs).
-    int* s_cw = s_hist[0];   // [RPNC_NCLS] max width per class (float bits), the select histograms are dead
-    int* s_ch = s_hist[1];
-    for (int i = tid; i < RPNC_NCLS; i += RPN_NT) { s_cw[i] = 0; s_ch[i] = 0; }
-    if (tid == 0) s_total = 0;
-    for (int i = tid; i < (n + 31) / 32 + 33; i += RPN_NT) s_kept[i] = 0u;
-    __syncthreads();
-    {
-        float cmax = 0.f;
-        for (int r = tid; r < n; r += RPN_NT) {
-            const float4 bx = sbox[r];
-            if (hd_box_proper(bx)) {
-                const int c = rpnc_class(hd_area(bx));
-                atomicMax(&s_cw[c], __float_as_int(bx.z - bx.x));   // positive floats order like their bit patterns
-                atomicMax(&s_ch[c], __float_as_int(bx.w - bx.y));
-                cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(bx.x), fabsf(bx.y)), fmaxf(fabsf(bx.z), fabsf(bx.w))));
-            }
-        }
-        atomicMax(&s_total, __float_as_int(cmax));
-    }
-    __syncthreads();
-    const float slack = 5.0e-7f * __int_as_float(s_total);
-    const float grow = fmaxf(0.0f, 0.5f - (p.thr - 1.0e-3f));
-    const float tq = p.thr - 1.0e-3f;
-    if (tid < RPNC_NCLS) {   // per-class query tables (inverse cell size, window growth); 0 marks an empty class
-        const float wc = __int_as_float(s_cw[tid]), hc = __int_as_float(s_ch[tid]);
-        s_cinv[tid] = (wc > 0.0f) ? rpnc_inv_cell(tid) : 0.0f;
-        s_cgx[tid] = grow * wc + slack; s_cgy[tid] = grow * hc + slack;
-    }
-    int* start = reinterpret_cast<int*>(dsm);                                  // [T+1] bucket starts (cluster-wide)
-    int* hist = reinterpret_cast<int*>(dsm + q.queue_off);                     // [T] per-CTA counts, then scatter cursors (dead before the queue is used)
-    float2* cen = reinterpret_cast<float2*>(dsm + q.cen_off);                  // [items] centres, bucket by bucket
-    unsigned short* irk = reinterpret_cast<unsigned short*>(dsm + q.irk_off);  // [items] their ranks
-    int* acnt = reinterpret_cast<int*>(dsm + q.acnt_off);                      // [RPN_NT] list lengths of the round's boxes
-    uint32_t* queue = reinterpret_cast<uint32_t*>(dsm + q.queue_off);
-    int* grank = q.grank + off;
-    float4* gbox = q.gbox + off;
-    unsigned short* adj = q.adj + off * RPNC_ADJ;
-    int* adj_cnt = q.adj_cnt + off;
-    int* keep_r = p.keep_r + off;
-    // per-warp queue segments and counters (a single CTA-wide counter would serialise ~10^4 shared-memory atomics per round)
-    const int segcap = q.queue_cap / (RPN_NT / 32);
-    uint32_t* myq = queue + wid * segcap;
-    int* s_qn = s_wsum;            // [32] entries queued by each warp
-    int* s_qpre = s_tot;           // [33] their exclusive prefix
-    // cells of class c under the query window of box bq: origin (x1,y1), nx columns; returns the cell count
-    auto window = [&](const float4 bq, int c, int& x1, int& y1, int& nx, float& lx, float& hx, float& ly, float& hy) -> int {
-        const float inv = s_cinv[c];
-        if (inv == 0.0f) return 0;
-        lx = bq.x - s_cgx[c]; hx = bq.z + s_cgx[c]; ly = bq.y - s_cgy[c]; hy = bq.w + s_cgy[c];
-        x1 = hd_cell(lx, inv); y1 = hd_cell(ly, inv);
-        const long long dx = (long long)hd_cell(hx, inv) - x1 + 1, dy = (long long)hd_cell(hy, inv) - y1 + 1;
-        if (dx * dy > 1024) { q.fallback[b] = 1; return 0; }   // low thresholds / degenerate geometry: single-CTA kernel
-        nx = (int)dx;
-        return (int)(dx * dy);
-    };
-    // exact test of box j (rank jr, round slot bl) against the higher-ranked box i (rank ir)
-    auto exact = [&](int bl, int jr, const float4 bq, int ir, const float4 bi) {
-        const float aq = hd_area(bq), ai = hd_area(bi);
-        const float amin = tq * aq, amax = (tq > 0.0f) ? aq / tq : 3.0e38f;
-        if (ai < amin || ai > amax) return;
-        const float cx = 0.5f * (bi.x + bi.z), cy = 0.5f * (bi.y + bi.w);
-        const float gx = grow * (bi.z - bi.x) + slack, gy = grow * (bi.w - bi.y) + slack;
-        if (cx < bq.x - gx || cx > bq.z + gx || cy < bq.y - gy || cy > bq.w + gy) return;
-        if (hd_iou_gt(bi, ai, bq, aq, p.thr)) {
-            const int slot = atomicAdd(&acnt[bl], 1);
-            if (slot < RPNC_ADJ) adj[(size_t)jr * RPNC_ADJ + slot] = (unsigned short)ir;
-        }
-    };
-    int kc = 0;
-    const int first = max(2 * p.n_post, 128 * CL);
-    for (int lo_r = 0, hi_r = min(n, first);; lo_r = hi_r, hi_r = n) {
-        HD_PHASE(3);
-        // ---- N1
-        for (int i = tid; i < RPNC_T; i += RPN_NT) hist[i] = 0;
-        __syncthreads();
-        const int mg = (hi_r + CL - 1) / CL, glo = min(crank * mg, hi_r), glen = min(hi_r, glo + mg) - glo;
-        for (int i = tid; i < glen; i += RPN_NT) {
-            const float4 bx = sbox[glo + i];
-            if (hd_box_proper(bx)) {
-                const int c = rpnc_class(hd_area(bx));
-                const float inv = rpnc_inv_cell(c);
-                atomicAdd(&hist[rpnc_hash(hd_cell(0.5f * (bx.x + bx.z), inv), hd_cell(0.5f * (bx.y + bx.w), inv), c)], 1);
-            }
-        }
-        __syncthreads();
-        cluster.sync();
-        {
-            constexpr int PER = RPNC_T / RPN_NT;   // consecutive buckets per thread
-            static_assert(PER == 4, "one int4 of buckets per thread");
-            int tot[PER], myoff[PER];
-            int loc = 0;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) { tot[j] = 0; myoff[j] = 0; }
-            for (int c = 0; c < CL; ++c) {
-                const int4 v = reinterpret_cast<const int4*>(cluster.map_shared_rank(hist, c))[tid];
-                tot[0] += v.x; tot[1] += v.y; tot[2] += v.z; tot[3] += v.w;
-                if (c < crank) { myoff[0] += v.x; myoff[1] += v.y; myoff[2] += v.z; myoff[3] += v.w; }
-            }
-#pragma unroll
-            for (int j = 0; j < PER; ++j) loc += tot[j];
-            int incl = loc;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
-            if (lane == 31) s_wsum[wid] = incl;
-            cluster.sync();   // every CTA has read every histogram: they may now be overwritten with cursors
-            int pre = incl - loc;
-            for (int w = 0; w < wid; ++w) pre += s_wsum[w];
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const int h = tid * PER + j;
-                start[h] = pre; hist[h] = pre + myoff[j]; pre += tot[j];
-            }
-            if (tid == RPN_NT - 1) start[RPNC_T] = pre;
-        }
-        __syncthreads();
-        for (int i = tid; i < glen; i += RPN_NT) {
-            const float4 bx = sbox[glo + i];
-            if (hd_box_proper(bx)) {
-                const int c = rpnc_class(hd_area(bx));
-                const float inv = rpnc_inv_cell(c);
-                const int pos = atomicAdd(&hist[rpnc_hash(hd_cell(0.5f * (bx.x + bx.z), inv), hd_cell(0.5f * (bx.y + bx.w), inv), c)], 1);
-                gbox[pos] = bx; grank[pos] = glo + i;
-            }
-        }
-        cluster.sync();
-        HD_PHASE(4);
-        // ---- N2: box j looks for the higher-ranked boxes i with iou(i,j) > thr:
-        //   iou > t  =>  centre_i inside box_j grown by max(0, .5 - t) * (w_i, h_i),  and  area_i in [t * area_j, area_j / t],
-        // i.e. the 3 (t = 0.7) size classes around j's own, a handful of cells each.  Phase A: a lane owns one box of the
-        // round; the (box, cell) pairs of the warp's 32 boxes are dealt out to the lanes (prefix sums + a shuffle binary
-        // search), so every lane visits one cell per step whatever the box sizes; item centres and ranks sit in shared
-        // memory bucket by bucket; survivors of the centre and rank tests go to per-warp queues.  Phase B drains the
-        // queues with all threads: exact test on the full boxes (balanced, several loads in flight), hits appended to
-        // j's list through a shared-memory counter.
-        const int nitem = start[RPNC_T];
-        for (int i = tid; i < nitem; i += RPN_NT) {
-            const float4 bx = gbox[i];
-            cen[i] = make_float2(0.5f * (bx.x + bx.z), 0.5f * (bx.y + bx.w));
-            irk[i] = (unsigned short)grank[i];
-        }
-        // consecutive ranks go to different CTAs and different warps: the top ranks are the dense object clusters, whose
-        // long buckets would otherwise all land in the first warps.  Round slot `bl` of this CTA <-> rank slot_rank(bl).
-        const int slen = (hi_r - lo_r + CL - 1) / CL;              // slots per CTA (the last ones may be empty)
-        for (int b0 = 0; b0 < slen; b0 += RPN_NT) {
-            auto slot_rank = [&](int bl) { return lo_r + (b0 + ((bl & 31) << 5) + (bl >> 5)) * CL + crank; };
-            if (tid < RPN_NT / 32) s_qn[tid] = 0;
-            acnt[tid] = 0;
-            __syncthreads();
-            const int jr = slot_rank(tid);
-            const bool has = jr < hi_r;
-            float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has) bq = sbox[jr];
-            int ncell = 0;
-            if (has && jr > 0 && hd_box_proper(bq)) {
-                const float aq = hd_area(bq);
-                const int c0 = rpnc_class(tq * aq), c1 = rpnc_class((tq > 0.0f) ? aq / tq : 3.0e38f);
-                for (int c = c0; c <= c1; ++c) { int x1, y1, nx; float lx, hx, ly, hy; ncell += window(bq, c, x1, y1, nx, lx, hx, ly, hy); }
-            }
-            int incl = ncell;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
-            const int pre = incl - ncell, total = __shfl_sync(HD_FULL, incl, 31);
-            for (int t0 = 0; t0 < total; t0 += 32) {
-                const int t = t0 + lane;
-                int src = 0;                                       // largest lane whose prefix is <= t
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) { const int v = __shfl_sync(HD_FULL, pre, src + d); if (v <= t) src += d; }
-                int local = t - __shfl_sync(HD_FULL, pre, src);
-                float4 bs;
-                bs.x = __shfl_sync(HD_FULL, bq.x, src); bs.y = __shfl_sync(HD_FULL, bq.y, src);
-                bs.z = __shfl_sync(HD_FULL, bq.z, src); bs.w = __shfl_sync(HD_FULL, bq.w, src);
-                if (t >= total) continue;
-                const int sbl = (wid << 5) + src, sjr = slot_rank(sbl);
-                const float aq = hd_area(bs);
-                const int c1 = rpnc_class((tq > 0.0f) ? aq / tq : 3.0e38f);
-                int c = rpnc_class(tq * aq), x1 = 0, y1 = 0, nx = 1;
-                float lx = 0.f, hx = 0.f, ly = 0.f, hy = 0.f;
-                for (; c <= c1; ++c) {
-                    const int nc2 = window(bs, c, x1, y1, nx, lx, hx, ly, hy);
-                    if (local < nc2) break;
-                    local -= nc2;
-                }
-                if (c > c1) continue;                              // (cannot happen: the counts are recomputed identically)
-                const int gy = local / nx, gx = local - gy * nx;
-                const uint32_t hb = rpnc_hash(x1 + gx, y1 + gy, c);
-                const int s1 = start[hb + 1];
-                for (int kk = start[hb]; kk < s1; ++kk) {
-                    const float2 ce = cen[kk];
-                    if (ce.x < lx || ce.x > hx || ce.y < ly || ce.y > hy) continue;   // also rejects most hash collisions
-                    const int ir = irk[kk];
-                    if (ir >= sjr) continue;                                           // only higher-ranked boxes suppress
-                    const int slot = atomicAdd(&s_qn[wid], 1);
-                    if (slot < segcap) myq[slot] = ((uint32_t)sbl << 16) | (uint32_t)kk;
-                    else exact(sbl, sjr, bs, ir, gbox[kk]);
-                }
-            }
-            __syncthreads();
-            if (tid < 32) {
-                const int c = min(s_qn[tid], segcap);
-                int in2 = c;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, in2, d); if (lane >= d) in2 += y; }
-                s_qpre[tid] = in2 - c;
-                if (tid == 31) s_qpre[32] = in2;
-            }
-            __syncthreads();
-            const int nq = s_qpre[32];
-            for (int e0 = 0; e0 < nq; e0 += 2 * RPN_NT) {
-                int bl[2], ir[2]; float4 bb[2], bi[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int e = e0 + u * RPN_NT + tid;
-                    bl[u] = -1;
-                    if (e < nq) {
-                        int w = 0;                           // segment holding entry e
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) if (s_qpre[w + d] <= e) w += d;
-                        const uint32_t en = queue[w * segcap + (e - s_qpre[w])];
-                        bl[u] = (int)(en >> 16);
-                        const int pos = (int)(en & 0xffffu);
-                        ir[u] = irk[pos];
-                        bb[u] = sbox[slot_rank(bl[u])]; bi[u] = gbox[pos];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) if (bl[u] >= 0) exact(bl[u], slot_rank(bl[u]), bb[u], ir[u], bi[u]);
-            }
-            __syncthreads();
-            if (has) {
-                const int c = acnt[tid];
-                adj_cnt[jr] = min(c, RPNC_ADJ);
-                if (c > RPNC_ADJ) q.fallback[b] = 1;
-            }
-            __syncthreads();
-        }
-        cluster.sync();
-        HD_PHASE(5);
-        // ---- N3: CTA 0 resolves  kept[j] = !any(kept[i], i in adj[j])  1024 ranks at a time (Jacobi iteration to the
-        // unique fixed point = the greedy answer) and pushes "done" into every CTA of the cluster
-        if (crank == 0) {
-            int done = (hi_r >= n) ? 1 : 0;
-            if (*(volatile int*)&q.fallback[b]) done = 2;   // the single-CTA kernel redoes this image
-            for (int base = lo_r; done != 2 && base < hi_r && kc < p.n_post; base += RPN_NT) {
-                const int j = base + tid;
-                const bool in = j < hi_r;
-                const int cnt = in ? adj_cnt[j] : 0;
-                const unsigned short* lst = adj + (size_t)j * RPNC_ADJ;
-                const int wi = (base >> 5) + wid;
-                {
-                    const unsigned w0 = __ballot_sync(HD_FULL, in);
-                    if (lane == 0) s_kept[wi] = w0;
-                }
-                __syncthreads();
-                for (;;) {
-                    bool nk = in;
-                    for (int e = 0; e < cnt; ++e) {
-                        const int i = lst[e];
-                        if ((s_kept[i >> 5] >> (i & 31)) & 1u) { nk = false; break; }
-                    }
-                    const unsigned w1 = __ballot_sync(HD_FULL, nk);
-                    const bool ch = (w1 != s_kept[wi]);
-                    __syncthreads();
-                    if (lane == 0) s_kept[wi] = w1;
-                    if (!__syncthreads_or(ch)) break;
-                }
-                const unsigned wv = s_kept[wi];
-                if (lane == 0) s_wsum[wid] = __popc(wv);
-                __syncthreads();
-                int pre = kc, tot2 = kc;
-                for (int w = 0; w < RPN_NT / 32; ++w) { if (w < wid) pre += s_wsum[w]; tot2 += s_wsum[w]; }
-                if ((wv >> lane) & 1u) {
-                    const int pos = pre + __popc(wv & hd_lanemask_lt());
-                    if (pos < p.n_post) keep_r[pos] = j;
-                }
-                kc = min(tot2, p.n_post);
-                __syncthreads();
-            }
-            if (kc >= p.n_post && done == 0) done = 1;
-            if (tid < CL) *cluster.map_shared_rank(&s_done, tid) = done;
-        }
-        cluster.sync();
-        if (s_done) break;
-    }
-    if (crank != 0 || s_done == 2) return;
+    // ---- N: greedy NMS over the cluster (hd_cluster_nms.cuh): size-stratified spatial hash -> adjacency lists -> Jacobi resolve,
+    // in rank batches with early stop
+    HdClWs w;
+    w.sbox = sbox; w.scls = nullptr; w.gbox = q.gbox + off; w.grank = q.grank + off; w.adj_cnt = q.adj_cnt + off;
+    w.adj = q.adj + off * RPNC_ADJ; w.fallback = q.fallback + b; w.keep_r = p.keep_r + off;
+    const int kc = hd_cluster_greedy_nms<RPN_NT, false>(cluster, dsm, q.lay, csm, w, n, p.n_post, p.thr);
+    if (crank != 0 || kc < 0) return;
+    const int* keep_r = w.keep_r;
     HD_PHASE(6);
     for (int r = tid; r < p.n_post; r += RPN_NT) {
         float* o = p.out_rois + ((size_t)b * p.n_post + r) * 5;
@@ -1066,15 +764,7 @@ extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores,
         size_t sm_c = np * 8;                                           // slice sort
         if (sm_c < (size_t)cap * 8) sm_c = (size_t)cap * 8;             // merge: all composites
         if (q.key_cache && sm_c < (size_t)q.per * 4) sm_c = (size_t)q.per * 4;
-        q.cen_off = (int)hd_align_up(((size_t)RPNC_T + 1) * 4, 16);
-        q.irk_off = (int)hd_align_up((size_t)q.cen_off + (size_t)cap * 8, 16);
-        q.acnt_off = (int)hd_align_up((size_t)q.irk_off + (size_t)cap * 2, 16);
-        q.queue_off = (int)hd_align_up((size_t)q.acnt_off + (size_t)RPN_NT * 4, 16);
-        size_t want = (size_t)q.queue_off + 64 * 1024;                  // adjacency: buckets + centres + candidate queue
-        if (want > budget) want = budget;
-        if (want < (size_t)q.queue_off + (size_t)RPNC_T * 4) want = (size_t)q.queue_off + (size_t)RPNC_T * 4;
-        if (sm_c < want) sm_c = want;
-        q.queue_cap = (int)((sm_c - q.queue_off) / 4);
+        hd_cluster_layout(cap, budget, &q.lay, &sm_c);
         HD_CUDA_CALL(cudaMemsetAsync(q.fallback, 0, (size_t)B * 4, (cudaStream_t)stream));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(B * CL)); cfg.blockDim = dim3(RPN_NT); cfg.dynamicSmemBytes = sm_c; cfg.stream = (cudaStream_t)stream;
