@@ -56,6 +56,7 @@ SIGNATURES = {
     "hd_yolo_postprocess": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _d, _d, _i, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hd_yolo_filter_pred": (_i, [_vp, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "hd_sort_nms_workspace_size": (_sz, [_i, _i]),
+    "hd_nms_set_mode": (_i, [_i]),
     "hd_sort_nms_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hd_sort_nms_batched_replicated": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _f, _i, _i, _vp, _vp, _vp, C.POINTER(Replicas), _vp, _sz, _vp]),
     "hd_yolo_postprocess_replicated": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _d, _d, _i, _i, _f, _i, _i, _vp, _vp, _vp, C.POINTER(Replicas), _vp, _sz, _vp]),

@@ -60,7 +60,7 @@ __device__ int hd_cluster_greedy_nms(cg::cluster_group& cluster, unsigned char* 
     const int crank = (int)cluster.block_rank(), CL = (int)cluster.num_blocks();
     const float4* sbox = w.sbox;
     // ---- N: greedy NMS in rank batches.  Only the ranks up to the n_post-th keep matter, so the first batch covers the
-    // top max(2 n_post, 128 CL) ranks and the second (rarely needed) the rest.  Per batch [lo_r, hi_r):
+    // top max(2 n_post, 128 CL) ranks and every further batch doubles the covered prefix.  Per batch [lo_r, hi_r):
     //   N1  size-stratified spatial hash over the ranks < hi_r, built cooperatively: a proper box of area a belongs to
     //       class c = exponent(a) and is hashed by (centre / 2^(c/2), c) -- cells scale with the boxes they hold, so a
     //       query touches a handful of cells whatever the box size;
@@ -138,8 +138,8 @@ __device__ int hd_cluster_greedy_nms(cg::cluster_group& cluster, unsigned char* 
         }
     };
     int kc = 0;
-    const int first = max(2 * max_det, 128 * CL);
-    for (int lo_r = 0, hi_r = min(n, first);; lo_r = hi_r, hi_r = n) {
+    const int first = (max(2 * max_det, 128 * CL) + 31) & ~31;   // batch boundaries on bitmap words (the resolve writes whole words)
+    for (int lo_r = 0, hi_r = min(n, first);; lo_r = hi_r, hi_r = min(n, 2 * hi_r)) {   // batches double: total work <= 2x the last one
         HD_PHASE(3);
         // ---- N1
         for (int i = tid; i < RPNC_T; i += NT) hist[i] = 0;

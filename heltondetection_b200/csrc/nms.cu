@@ -10,6 +10,7 @@
 // which is what the detection callers (max_det=300, RPN post_nms_top_n) need.
 #include "hd_sort.cuh"
 #include "hd_small_nms.cuh"
+#include "hd_cluster_nms.cuh"
 
 #define NMS_NT 1024
 
@@ -32,6 +33,7 @@ struct NmsParams {
     float4* sbox; int* scls; int* keep_r; float4* gitem;
     int sort_off, bitonic_cap;  // dynamic smem: word offset of the in-smem sort area and its capacity (0 = disabled)
     HdRep rep;
+    const int* only;            // nullable: run only the images whose flag is set (images the cluster kernel hands back)
 };
 
 __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_constant__ NmsParams p) {
@@ -44,6 +46,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     const int b = blockIdx.x;
     int n = p.counts ? min(p.counts[b], p.cap) : p.n_fixed;
     if (p.min_n >= 0 && n <= p.min_n) return;
+    if (p.only && p.only[b] == 0) return;
     if (n <= 0) {
         if (tid == 0) p.out_count[b] = 0;
         if (tid < p.rep.n) p.rep.cnt[tid][b] = 0;
@@ -138,6 +141,117 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     if (tid < p.rep.n) p.rep.cnt[tid][b] = kc;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Cluster variant for batches that leave SMs idle (B < #SMs / 2): 2, 4 or 8 CTAs per image.  Each CTA bitonic-sorts an
+// even slice of the (score desc, tiebreak asc) composites with the slot as payload, the final rank of an element is the
+// sum of its lower bounds in all sorted slices (shared-memory copy), and the greedy NMS is hd_cluster_greedy_nms
+// (hd_cluster_nms.cuh).  Images with more than RPNC_MAXN candidates, or whose adjacency lists overflow, are flagged and
+// redone by sort_nms_kernel; images with <= min_n candidates belong to small_nms_kernel.  Bit-identical outputs.
+// ------------------------------------------------------------------------------------------------------------
+struct NmsClParams {
+    NmsParams s;
+    uint64_t* skeys; uint32_t* svals;   // [B,cap] sorted slices
+    uint32_t* order;                    // [B,cap] rank -> slot
+    float4* gbox; int* grank; int* adj_cnt; unsigned short* adj; int* fallback;
+    HdClLayout lay;
+    int val_off;                        // byte offset of the payload array in dynamic shared memory
+    int capn;                           // per-image stride of the adjacency lists: min(cap, RPNC_MAXN)
+};
+
+__global__ void __launch_bounds__(NMS_NT, 1) sort_nms_cluster_kernel(const __grid_constant__ NmsClParams q) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ HdClSmem csm;
+    cg::cluster_group cluster = cg::this_cluster();
+    const NmsParams& p = q.s;
+    const int tid = threadIdx.x;
+    const int crank = (int)cluster.block_rank(), CL = (int)cluster.num_blocks();
+    const int b = blockIdx.x / CL;
+    const int n = p.counts ? min(p.counts[b], p.cap) : p.n_fixed;
+    if (p.min_n >= 0 && n <= p.min_n) return;          // small_nms_kernel's image (uniform over the cluster, no DSMEM touched yet)
+    if (n > RPNC_MAXN || n <= 0) {                      // sort_nms_kernel's image
+        if (crank == 0 && tid == 0) q.fallback[b] = 1;
+        return;
+    }
+    const size_t off = (size_t)b * p.cap;
+    // ---- slice sort (payload = slot) + merge ranks
+    const int m = (n + CL - 1) / CL;
+    const int slo = min(crank * m, n), slen = min(n, slo + m) - slo;
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(dsm);
+    uint32_t* sval = reinterpret_cast<uint32_t*>(dsm + q.val_off);
+    const int Np = hd_bitonic_padded(m);
+    for (int i = tid; i < Np; i += NMS_NT) {
+        if (i < slen) {
+            const int slot = slo + i;
+            const uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + slot] : (uint32_t)slot;
+            skey[i] = ((uint64_t)(~hd_orderable(p.scores[off + slot])) << 32) | tb;
+            sval[i] = (uint32_t)slot;
+        } else { skey[i] = ~0ull; sval[i] = 0u; }
+    }
+    __syncthreads();
+    if (Np == 2048) hd_cta_bitonic_reg<2, true>(skey, sval);
+    else if (Np == 4096) hd_cta_bitonic_reg<4, true>(skey, sval);
+    else hd_cta_bitonic_reg<8, true>(skey, sval);
+    uint64_t* sorted = q.skeys + off;
+    for (int i = tid; i < slen; i += NMS_NT) sorted[slo + i] = skey[i];
+    cluster.sync();
+    for (int i = tid; i < n; i += NMS_NT) skey[i] = sorted[i];
+    __syncthreads();
+    const int n_use = (p.max_nms > 0) ? min(n, p.max_nms) : n;
+    const int max_det = (p.max_det > 0) ? p.max_det : n_use;
+    uint32_t* order = q.order + off;
+    float4* sbox = p.sbox + off;
+    int* scls = p.scls + off;
+    for (int i = tid; i < slen; i += NMS_NT) {
+        const unsigned long long v = skey[slo + i];
+        int rank = i;
+        for (int c = 0; c < CL; ++c) {
+            if (c == crank) continue;
+            int a = min(c * m, n), z = min(n, a + m);
+            const int a0 = a;
+            while (a < z) { const int mid = (a + z) >> 1; if (skey[mid] < v) a = mid + 1; else z = mid; }
+            rank += a - a0;
+        }
+        const uint32_t slot = sval[i];
+        order[rank] = slot;
+        if (rank < n_use) {
+            float4 bx = p.boxes[off + slot];
+            const int c = p.cls ? p.cls[off + slot] : 0;
+            if (p.class_mode == HD_NMS_CLASS_OFFSET) {
+                const float o = __fmul_rn((float)c, p.offset_scale);
+                bx.x = __fadd_rn(bx.x, o); bx.y = __fadd_rn(bx.y, o); bx.z = __fadd_rn(bx.z, o); bx.w = __fadd_rn(bx.w, o);
+            }
+            sbox[rank] = bx;
+            scls[rank] = (p.class_mode == HD_NMS_CLASS_EXACT) ? c : 0;
+        }
+    }
+    cluster.sync();
+    HdClWs w;
+    w.sbox = sbox; w.scls = scls; w.gbox = q.gbox + off; w.grank = q.grank + off; w.adj_cnt = q.adj_cnt + off;
+    w.adj = q.adj + (size_t)b * q.capn * RPNC_ADJ; w.fallback = q.fallback + b; w.keep_r = p.keep_r + off;
+    const int kc = (p.class_mode == HD_NMS_CLASS_EXACT) ? hd_cluster_greedy_nms<NMS_NT, true>(cluster, dsm, q.lay, csm, w, n_use, max_det, p.thr)
+                                                        : hd_cluster_greedy_nms<NMS_NT, false>(cluster, dsm, q.lay, csm, w, n_use, max_det, p.thr);
+    if (crank != 0 || kc < 0) return;
+    const int* keep_r = w.keep_r;
+    for (int qi = tid; qi < kc; qi += NMS_NT) {
+        const int r = keep_r[qi];
+        const uint32_t slot = order[r];
+        if (p.out_det) {
+            const float4 bx = p.boxes[off + slot];
+            const float sc = p.scores[off + slot], cf = p.cls ? (float)p.cls[off + slot] : 0.0f;
+            const size_t ro = ((size_t)b * p.max_det + qi) * 6;
+            float* o = p.out_det + ro;
+            o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = sc; o[5] = cf;
+            for (int rr = 0; rr < p.rep.n; ++rr) {   // posted stores into the peers' gather buffers
+                float* pr = p.rep.det[rr] + ro;
+                pr[0] = bx.x; pr[1] = bx.y; pr[2] = bx.z; pr[3] = bx.w; pr[4] = sc; pr[5] = cf;
+            }
+        }
+        if (p.out_idx) p.out_idx[(size_t)b * p.max_det + qi] = p.tiebreak ? (long long)p.tiebreak[off + slot] : (long long)slot;
+    }
+    if (tid == 0) p.out_count[b] = kc;
+    if (tid < p.rep.n) p.rep.cnt[tid][b] = kc;
+}
+
 // small-image variant: 256 threads, everything in shared memory, several images per SM at once
 __global__ void __launch_bounds__(HD_SMALL_NT) small_nms_kernel(const __grid_constant__ NmsParams p, const __grid_constant__ HdNmsTail q) {
     __shared__ HdSmallSmem ssm;
@@ -177,6 +291,28 @@ __global__ void __launch_bounds__(256) box_iou_kernel(const float4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ host
+static int g_nms_mode = 0;   // 0 auto, 1 one CTA per image only, 2 cluster kernel whenever the batch allows
+extern "C" HD_API int hd_nms_set_mode(int mode) { int old = g_nms_mode; g_nms_mode = mode; return old; }
+static int nms_cluster_capacity(int CL) {
+    static int cached[RPNC_MAXCL + 1] = {0};
+    if (cached[CL]) return cached[CL];
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(NMS_NT); cfg.dynamicSmemBytes = 180 * 1024;
+    cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int nc = 0;
+    cudaFuncSetAttribute(sort_nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (cudaOccupancyMaxActiveClusters(&nc, sort_nms_cluster_kernel, &cfg) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = HD_NUM_SMS / CL; }
+    return cached[CL] = nc;
+}
+// CTAs per image for a batch of B images: the largest cluster (8 or 4) that still runs the whole batch in one wave; 0 = the
+// batch is large enough for one CTA per image (or the mode forbids clusters)
+static int nms_cluster_size(int B, bool for_layout = false) {
+    if ((g_nms_mode == 1 && !for_layout) || B <= 0) return 0;
+    for (int c = RPNC_MAXCL; c >= 4; c >>= 1)     // clusters of 2 measured no faster than one CTA per image (cfg4, B=64)
+        if (B <= nms_cluster_capacity(c)) return c;
+    return 0;
+}
 static void nms_ws_layout(int B, int cap, size_t* offs, size_t* total) {
     size_t n = (size_t)B * cap, o = 0;
     offs[0] = o; o = hd_align_up(o + n * 8, 256);   // k0
@@ -187,11 +323,17 @@ static void nms_ws_layout(int B, int cap, size_t* offs, size_t* total) {
     offs[5] = o; o = hd_align_up(o + n * 4, 256);   // scls
     offs[6] = o; o = hd_align_up(o + n * 4, 256);   // keep_r
     offs[7] = o; o = hd_align_up(o + n * 16, 256);  // grid records
+    // cluster kernel only (batches small enough to leave SMs idle)
+    const size_t nc = nms_cluster_size(B, true) ? n : 0;   // (independent of hd_nms_set_mode: the size query and the call must agree)
+    offs[8] = o; o = hd_align_up(o + nc * 4, 256);   // bucket ranks
+    offs[9] = o; o = hd_align_up(o + nc * 4, 256);   // adjacency counts
+    offs[10] = o; o = hd_align_up(o + (nc ? (size_t)B * (size_t)(cap < RPNC_MAXN ? cap : RPNC_MAXN) * RPNC_ADJ * 2 : 0), 256);   // adjacency lists, stride min(cap, RPNC_MAXN)
+    offs[11] = o; o = hd_align_up(o + (size_t)B * 4, 256);   // hand-back flags
     *total = o;
 }
 
 extern "C" HD_API size_t hd_sort_nms_workspace_size(int B, int cap) {
-    size_t offs[8], total;
+    size_t offs[12], total;
     nms_ws_layout(B < 0 ? 0 : B, cap < 0 ? 0 : cap, offs, &total);
     return total + 256;
 }
@@ -239,7 +381,7 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
     }
     HD_CHECK_ARG(boxes && scores, "boxes/scores is NULL");
     HD_CHECK_ARG(max_det > 0, "max_det must be > 0 (row stride of out_det/out_idx), got %d", max_det);
-    size_t offs[8], total;
+    size_t offs[12], total;
     nms_ws_layout(B, cap, offs, &total);
     uintptr_t w0 = hd_align_up((uintptr_t)workspace, 256);
     if (!workspace || w0 + total > (uintptr_t)workspace + workspace_bytes)
@@ -283,6 +425,29 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
         HD_CUDA_LAUNCH_CHECK("small_nms_kernel");
         p.min_n = HD_SMALL_N;
         if (counts == nullptr) return HD_OK;
+    }
+    p.only = nullptr;
+    const int CL = nms_cluster_size(B);
+    if (CL) {
+        NmsClParams q;
+        q.s = p;
+        q.skeys = p.k1; q.svals = p.v1; q.order = p.v0; q.gbox = p.gitem;
+        q.grank = (int*)(w0 + offs[8]); q.adj_cnt = (int*)(w0 + offs[9]); q.adj = (unsigned short*)(w0 + offs[10]); q.fallback = (int*)(w0 + offs[11]);
+        const int capn = cap < RPNC_MAXN ? cap : RPNC_MAXN;
+        q.capn = capn;
+        const int mslice = (capn + CL - 1) / CL;
+        const size_t np = mslice <= 2048 ? 2048 : (mslice <= 4096 ? 4096 : 8192);
+        size_t keys_b = (np > (size_t)capn ? np : (size_t)capn) * 8;
+        q.val_off = (int)keys_b;
+        size_t sm_c = keys_b + np * 4;
+        hd_cluster_layout(capn, 180 * 1024, &q.lay, &sm_c);
+        HD_CUDA_CALL(cudaMemsetAsync(q.fallback, 0, (size_t)B * 4, st));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * CL)); cfg.blockDim = dim3(NMS_NT); cfg.dynamicSmemBytes = sm_c; cfg.stream = st;
+        cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        HD_CUDA_CALL(cudaLaunchKernelEx(&cfg, sort_nms_cluster_kernel, q));
+        p.only = q.fallback;
     }
     sort_nms_kernel<<<B, NMS_NT, smem, st>>>(p);
     HD_CUDA_LAUNCH_CHECK("sort_nms_kernel");

@@ -8,6 +8,11 @@ import torch
 from . import _lib
 
 
+def set_nms_mode(mode):
+    """large-segment NMS kernel choice: 0 auto (thread-block clusters for small batches), 1 one CTA per image; returns the previous mode."""
+    return _lib.lib().hd_nms_set_mode(int(mode))
+
+
 def _check_nms_args(boxes, scores):
     if boxes.dim() != 2:
         raise RuntimeError(f"boxes should be a 2d tensor, got {boxes.dim()}D")

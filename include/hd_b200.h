@@ -113,6 +113,10 @@ HD_API int hd_yolo_filter_pred(const float* pred, int B, int N, int nc, double c
  * tiebreak ids must be unique per image.  cls may be NULL for HD_NMS_AGNOSTIC.
  * ------------------------------------------------------------------------------------------- */
 HD_API size_t hd_sort_nms_workspace_size(int B, int cap);
+/* Images with more than 512 candidates are sorted and suppressed by one CTA each, or -- when the batch is small enough to
+ * leave most SMs idle (B <= 33 on a B200) -- by a thread-block cluster of 4 or 8 CTAs per image; bit-identical outputs.
+ * hd_nms_set_mode: 0 = automatic (default), 1 = one CTA per image only.  Returns the previous mode (developer / test aid). */
+HD_API int hd_nms_set_mode(int mode);
 HD_API int hd_sort_nms_batched(const float* boxes, const float* scores, const int32_t* cls, const int32_t* tiebreak,
                         const int32_t* counts, int n_fixed, int B, int cap, double iou_thres, int class_mode,
                         float offset_scale, int max_nms, int max_det, float* out_det, int64_t* out_idx,

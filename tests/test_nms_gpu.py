@@ -124,3 +124,55 @@ def test_grid_pruned_path_with_adversarial_boxes(n, thr):
     refc = refc.sort().values
     refc = refc[torch.sort(s[refc], descending=True, stable=True)[1]]
     assert torch.equal(_run(b, s, thr, c.int(), 1), refc)
+
+
+@pytest.mark.parametrize("class_mode", [0, 1, 2])
+def test_cluster_and_single_cta_large_segment_kernels_bit_exact(class_mode):
+    """one padded batch whose images take every path: small kernel (<= 512), cluster kernel, > 16384 candidates (handed back
+    to the single-CTA kernel), dense clusters (adjacency overflow -> handed back), empty image.  Mode 0 (clusters) must equal
+    mode 1 (one CTA per image) and torchvision."""
+    from heltondetection_b200 import _lib, ops
+    counts = [100, 600, 5000, 16384, 20000, 0, 3000]
+    B, cap = len(counts), 20000
+    box = torch.zeros(B, cap, 4); sc = torch.zeros(B, cap); cl = torch.zeros(B, cap, dtype=torch.int32)
+    g = torch.Generator().manual_seed(4)
+    for b, n in enumerate(counts):
+        if n:
+            bb, ss = _boxes(n, 50 + b)
+            if b == 6:   # 20 objects x 150 near-identical boxes: more than 64 suppressor candidates per box
+                c0 = torch.randint(0, 20, (n,), generator=g)
+                base = torch.rand(20, 4, generator=g) * 300
+                base[:, 2:] = base[:, :2] + 120
+                bb = base[c0] + torch.randn(n, 4, generator=g)
+            box[b, :n], sc[b, :n] = bb, ss
+            cl[b, :n] = torch.randint(0, 5, (n,), generator=g).int()
+    L = _lib.lib()
+    outs = {}
+    dbox, dsc, dcl, dcounts = box.cuda(), sc.cuda(), cl.cuda(), torch.tensor(counts, dtype=torch.int32).cuda()
+    for mode in (0, 1):
+        old = ops.set_nms_mode(mode)
+        try:
+            ws_bytes = L.hd_sort_nms_workspace_size(B, cap)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device="cuda")
+            det = torch.zeros((B, 300, 6), device="cuda"); idx = torch.full((B, 300), -1, dtype=torch.int64, device="cuda")
+            cnt = torch.zeros((B,), dtype=torch.int32, device="cuda")
+            _lib.check(L.hd_sort_nms_batched(_lib.ptr(dbox), _lib.ptr(dsc), _lib.ptr(dcl), None, _lib.ptr(dcounts), 0, B, cap, 0.5, class_mode, 4096.0, 0, 300,
+                                             _lib.ptr(det), _lib.ptr(idx), _lib.ptr(cnt), _lib.ptr(ws), ws_bytes, _lib.stream()))
+            torch.cuda.synchronize()
+            outs[mode] = (det.cpu(), idx.cpu(), cnt.cpu())
+        finally:
+            ops.set_nms_mode(old)
+    for a, c in zip(outs[0], outs[1]):
+        assert torch.equal(a, c)
+    for b, n in enumerate(counts):
+        bb, ss, cc = box[b, :n], sc[b, :n], cl[b, :n]
+        if class_mode == 0:
+            ref = torchvision.ops.nms(bb, ss, 0.5) if n else torch.zeros(0, dtype=torch.int64)
+        elif class_mode == 1:
+            ref = torchvision.ops.boxes._batched_nms_vanilla(bb, ss, cc, 0.5).sort().values if n else torch.zeros(0, dtype=torch.int64)
+            ref = ref[torch.sort(ss[ref], descending=True, stable=True)[1]]
+        else:
+            ref = torchvision.ops.nms(bb + cc[:, None].float() * 4096.0, ss, 0.5) if n else torch.zeros(0, dtype=torch.int64)
+        k = int(outs[0][2][b])
+        assert k == min(ref.numel(), 300)
+        assert torch.equal(outs[0][1][b, :k], ref[:300])
