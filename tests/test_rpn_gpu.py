@@ -148,11 +148,14 @@ def _adversarial(seed, N, kind):
         sc[::97] = sc[1]
     elif kind == "all_equal":
         sc[:] = 0.5
+    elif kind == "triples":     # every object proposed 4x: keeps come at 1/4 of the ranks -> several (doubling) rank batches
+        base = bx[: (N + 3) // 4]
+        bx = base.repeat(4, 1)[:N] + torch.randn(N, 4, generator=g) * 0.5
     return bx.contiguous(), sc.contiguous(), valid
 
 
-@pytest.mark.parametrize("kind", ["plain", "ties", "clusters", "degenerate", "all_equal"])
-@pytest.mark.parametrize("N,n_pre,n_post", [(20000, 6000, 1000), (5000, 0, 5000), (40000, 16384, 2000), (777, 300, 100)])
+@pytest.mark.parametrize("kind", ["plain", "ties", "clusters", "degenerate", "all_equal", "triples"])
+@pytest.mark.parametrize("N,n_pre,n_post", [(20000, 6000, 1000), (5000, 0, 5000), (40000, 16384, 2000), (777, 300, 100), (30000, 12000, 333)])
 def test_cluster_and_single_cta_kernels_bit_exact(kind, N, n_pre, n_post):
     """explicit arrays through hd_rpn_select_nms: cluster kernel (mode 2) == single-CTA kernel (mode 1) == stable sort + torchvision nms"""
     from heltondetection_b200 import rpn
