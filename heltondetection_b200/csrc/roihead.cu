@@ -122,8 +122,10 @@ extern "C" HD_API int hd_roi_head_decode_filter(const float* cls_logits, const f
     HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
     roi_head_decode_filter_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
     HD_CUDA_LAUNCH_CHECK("roi_head_decode_filter_kernel");
-    roi_head_clamp_count_kernel<<<(B + 255) / 256, 256, 0, st>>>(cand_count, B, cap);
-    HD_CUDA_LAUNCH_CHECK("roi_head_clamp_count_kernel");
+    if ((long long)cap < (long long)R * (n_class - 1)) {   // only a caller-chosen smaller cap can overflow
+        roi_head_clamp_count_kernel<<<(B + 255) / 256, 256, 0, st>>>(cand_count, B, cap);
+        HD_CUDA_LAUNCH_CHECK("roi_head_clamp_count_kernel");
+    }
     return HD_OK;
 }
 

@@ -136,8 +136,24 @@ class DecodeBox:
         return out
 
 
+_META_CACHE = {}
+
+
 def letterbox_meta(img1_shape, img0_shapes, device):
-    """[B,5] (pad_x, pad_y, gain, w0, h0) of ultralytics scale_coords for a letterboxed input of img1_shape=(h,w)"""
+    """[B,5] (pad_x, pad_y, gain, w0, h0) of ultralytics scale_coords for a letterboxed input of img1_shape=(h,w); cached per
+    (shapes, device) so that repeated calls do not upload again"""
+    key = (tuple(img1_shape), tuple(tuple(x) for x in img0_shapes), str(device))
+    hit = _META_CACHE.get(key)
+    if hit is not None:
+        return hit
+    if len(_META_CACHE) > 64:
+        _META_CACHE.clear()
+    t = _letterbox_meta(img1_shape, img0_shapes, device)
+    _META_CACHE[key] = t
+    return t
+
+
+def _letterbox_meta(img1_shape, img0_shapes, device):
     rows = []
     for (h0, w0) in img0_shapes:
         gain = min(img1_shape[0] / h0, img1_shape[1] / w0)

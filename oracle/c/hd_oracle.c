@@ -138,3 +138,36 @@ void hdo_roi_pool(const float* in, int C, int H, int W, const float* rois, int64
         }
     }
 }
+
+/* ---- label assignment: torchvision det_utils.Matcher over box_iou (models/detection/_utils.py:318-400, boxes.py:308-370).
+ * matches[i] = argmax_g iou(g,i) (first on ties), -1 if max < low, -2 if low <= max < high; with allow_low every prediction that
+ * attains some GT's best IoU keeps its arg-max match.  Thresholds are compared after a cast to float, as torch does. */
+void hdo_match(const float* gt, int64_t G, const float* pred, int64_t N, double high, double low, int allow_low, int64_t* matches) {
+    float* iou = (float*)malloc(sizeof(float) * (size_t)G * (size_t)N);
+    hdo_box_iou(gt, G, pred, N, iou);
+    const float hf = (float)high, lf = (float)low;
+    int64_t* all = (int64_t*)malloc(sizeof(int64_t) * (size_t)N);
+    for (int64_t i = 0; i < N; ++i) {
+        float best = iou[i]; int64_t bj = 0;
+        for (int64_t g = 1; g < G; ++g) if (iou[g * N + i] > best) { best = iou[g * N + i]; bj = g; }
+        all[i] = bj;
+        matches[i] = (best < lf) ? -1 : ((best < hf) ? -2 : bj);
+    }
+    if (allow_low)
+        for (int64_t g = 0; g < G; ++g) {
+            float mx = iou[g * N];
+            for (int64_t i = 1; i < N; ++i) if (iou[g * N + i] > mx) mx = iou[g * N + i];
+            for (int64_t i = 0; i < N; ++i) if (iou[g * N + i] == mx) matches[i] = all[i];
+        }
+    free(iou); free(all);
+}
+
+/* ---- letterbox inverse + clip (ultralytics scale_coords / clip_coords), fp32 op order: (x - pad) / gain, clamp */
+void hdo_scale_coords(const float* det, int64_t n, float pad_x, float pad_y, float gain, float w0, float h0, int xywh, float* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        const float* d = det + 6 * i; float* o = out + 6 * i;
+        float x1 = (d[0] - pad_x) / gain, y1 = (d[1] - pad_y) / gain, x2 = (d[2] - pad_x) / gain, y2 = (d[3] - pad_y) / gain;
+        x1 = fminf(fmaxf(x1, 0.0f), w0); x2 = fminf(fmaxf(x2, 0.0f), w0); y1 = fminf(fmaxf(y1, 0.0f), h0); y2 = fminf(fmaxf(y2, 0.0f), h0);
+        o[0] = x1; o[1] = y1; o[2] = xywh ? x2 - x1 : x2; o[3] = xywh ? y2 - y1 : y2; o[4] = d[4]; o[5] = d[5];
+    }
+}

@@ -56,3 +56,20 @@ def roi_pool(x, rois, output_size, scale):
     out = np.empty((len(r), x.shape[1], PH, PW), np.float32)
     lib().hdo_roi_pool(xp, x.shape[1], x.shape[2], x.shape[3], rp, C.c_int64(len(r)), C.c_float(scale), PH, PW, out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def match(gt, pred, high, low, allow_low):
+    g, gp = _f(gt)
+    p, pp = _f(pred)
+    out = np.empty(len(p), np.int64)
+    lib().hdo_match(gp, C.c_int64(len(g)), pp, C.c_int64(len(p)), C.c_double(high), C.c_double(low), int(bool(allow_low)),
+                    out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def scale_coords(det, pad_x, pad_y, gain, w0, h0, xywh=False):
+    d, dp = _f(det)
+    out = np.empty_like(d)
+    lib().hdo_scale_coords(dp, C.c_int64(len(d)), C.c_float(pad_x), C.c_float(pad_y), C.c_float(gain), C.c_float(w0), C.c_float(h0), int(bool(xywh)),
+                           out.ctypes.data_as(C.c_void_p))
+    return out

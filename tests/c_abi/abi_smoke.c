@@ -1,6 +1,6 @@
 /* Pure-C consumer of libhd_b200.so: no torch, no Python -- only cudart + the C ABI of include/hd_b200.h.
- * Runs hd_box_iou, hd_sort_nms_batched (small, bitonic+pruned and class-aware paths) and hd_roi_align/hd_roi_pool on
- * seeded data and compares them with the plain-C oracle (oracle/c/hd_oracle.c).  Exit code 0 = parity. */
+ * Runs hd_box_iou, hd_sort_nms_batched (small, bitonic+pruned and class-aware paths), hd_roi_align/hd_roi_pool, hd_match and
+ * hd_scale_detections on seeded data and compares them with the plain-C oracle (oracle/c/hd_oracle.c).  Exit code 0 = parity. */
 #include <cuda_runtime_api.h>
 #include <math.h>
 #include <stdint.h>
@@ -13,6 +13,8 @@ int64_t hdo_nms(const float*, const float*, int64_t, double, int64_t, int64_t*);
 void hdo_box_iou(const float*, int64_t, const float*, int64_t, float*);
 void hdo_roi_align(const float*, int, int, int, const float*, int64_t, float, int, int, int, int, float*);
 void hdo_roi_pool(const float*, int, int, int, const float*, int64_t, float, int, int, float*);
+void hdo_match(const float*, int64_t, const float*, int64_t, double, double, int, int64_t*);
+void hdo_scale_coords(const float*, int64_t, float, float, float, float, float, int, float*);
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("cuda error %s at %s\n", cudaGetErrorString(e), #x); return 2; } } while (0)
 #define HD(x) do { int rc = (x); if (rc) { printf("hd error %d: %s at %s\n", rc, hd_last_error(), #x); return 3; } } while (0)
@@ -104,6 +106,39 @@ int main(void) {
             CK(cudaMemcpy(got, dout, 4 * no, cudaMemcpyDeviceToHost));
             int nb = memcmp(got, rp, 4 * no) != 0;
             printf("roi_pool  layout=%d: %s\n", layout, nb ? "MISMATCH" : "ok (bit-exact)");
+            bad |= nb;
+        }
+    }
+    {   /* label assignment (8f-3) and letterbox inverse (8f-2) */
+        const int G = 37, N = 3000;
+        float *gt = (float*)malloc(16 * G), *gs = (float*)malloc(4 * G), *pr = (float*)malloc(16 * N), *ps = (float*)malloc(4 * N);
+        make_boxes(gt, gs, G); make_boxes(pr, ps, N);
+        for (int i = 0; i < G / 2; ++i) memcpy(pr + 4 * i, gt + 4 * i, 16);   /* exact hits */
+        int64_t *ref = (int64_t*)malloc(8 * N), *got = (int64_t*)malloc(8 * N);
+        float *dg, *dp; int64_t* dm; void* ws;
+        size_t wsb = hd_match_workspace_size(1, G, N);
+        CK(cudaMalloc((void**)&dg, 16 * G)); CK(cudaMalloc((void**)&dp, 16 * N)); CK(cudaMalloc((void**)&dm, 8 * N)); CK(cudaMalloc(&ws, wsb));
+        CK(cudaMemcpy(dg, gt, 16 * G, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dp, pr, 16 * N, cudaMemcpyHostToDevice));
+        for (int allow = 0; allow < 2; ++allow) {
+            hdo_match(gt, G, pr, N, 0.7, 0.3, allow, ref);
+            HD(hd_match(dg, NULL, 1, G, dp, 0, N, 0.7, 0.3, allow, dm, NULL, ws, wsb, NULL));
+            CK(cudaMemcpy(got, dm, 8 * N, cudaMemcpyDeviceToHost));
+            int nb = memcmp(got, ref, 8 * (size_t)N) != 0;
+            printf("match allow_low=%d: %s\n", allow, nb ? "MISMATCH" : "ok (bit-exact)");
+            bad |= nb;
+        }
+        const int M = 200;
+        float *det = (float*)malloc(24 * M), *rs = (float*)malloc(24 * M), *gsc = (float*)malloc(24 * M), *dd, *dout, *dmeta;
+        for (int i = 0; i < M; ++i) { det[6 * i] = frand() * 600; det[6 * i + 1] = frand() * 600; det[6 * i + 2] = det[6 * i] + frand() * 200; det[6 * i + 3] = det[6 * i + 1] + frand() * 200; det[6 * i + 4] = frand(); det[6 * i + 5] = (float)(i % 7); }
+        const float gain = 640.0f / 1920.0f, meta[5] = {0.0f, (640.0f - 1080.0f * gain) / 2, gain, 1920.0f, 1080.0f};
+        CK(cudaMalloc((void**)&dd, 24 * M)); CK(cudaMalloc((void**)&dout, 24 * M)); CK(cudaMalloc((void**)&dmeta, 20));
+        CK(cudaMemcpy(dd, det, 24 * M, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dmeta, meta, 20, cudaMemcpyHostToDevice));
+        for (int xywh = 0; xywh < 2; ++xywh) {
+            hdo_scale_coords(det, M, meta[0], meta[1], meta[2], meta[3], meta[4], xywh, rs);
+            HD(hd_scale_detections(dd, NULL, 1, M, dmeta, xywh ? HD_BOX_XYWH : 0, dout, NULL));
+            CK(cudaMemcpy(gsc, dout, 24 * M, cudaMemcpyDeviceToHost));
+            int nb = memcmp(gsc, rs, 24 * (size_t)M) != 0;
+            printf("scale_detections xywh=%d: %s\n", xywh, nb ? "MISMATCH" : "ok (bit-exact)");
             bad |= nb;
         }
     }

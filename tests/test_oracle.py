@@ -224,3 +224,26 @@ def test_roi_head_oracle_against_committed_fixture():
     for i in range(2):
         assert np.array_equal(b[i].numpy(), G2[f"rh_boxes{i}"]) and np.array_equal(l[i].numpy(), G2[f"rh_labels{i}"])
         assert np.array_equal(oracle.roi_head.scale_coords((256, 320), b[i], (480, 640)).numpy(), G2[f"rh_scaled{i}"])
+
+
+def test_plain_c_oracle_match_and_scale_pinned_to_torchvision_and_restatement():
+    """oracle/c hdo_match == torchvision det_utils.Matcher(box_iou); hdo_scale_coords == oracle.roi_head.scale_coords"""
+    import numpy as np
+    import oracle
+    from oracle import cref
+    from torchvision.models.detection._utils import Matcher
+    g = torch.Generator().manual_seed(9)
+    def boxes(n):
+        xy = torch.rand(n, 2, generator=g) * 500
+        return torch.cat((xy, xy + torch.rand(n, 2, generator=g) * 200 + 4), 1)
+    gt, pr = boxes(23), boxes(1500)
+    pr[:10] = gt[:10]
+    for allow in (False, True):
+        ref = Matcher(0.7, 0.3, allow)(torchvision.ops.box_iou(gt, pr))
+        assert np.array_equal(cref.match(gt.numpy(), pr.numpy(), 0.7, 0.3, allow), ref.numpy())
+    det = torch.cat((boxes(64), torch.rand(64, 2, generator=g)), 1)
+    gain = min(640 / 1080, 640 / 1920)
+    pad = ((640 - 1920 * gain) / 2, (640 - 1080 * gain) / 2)
+    ref = oracle.roi_head.scale_coords((640, 640), det[:, :4], (1080, 1920))
+    got = cref.scale_coords(det.numpy(), np.float32(pad[0]), np.float32(pad[1]), np.float32(gain), 1920.0, 1080.0)
+    assert np.array_equal(got[:, :4], ref.numpy())

@@ -31,3 +31,22 @@ def test_roi_align_restated_equals_torchvision(rows, sr, aligned):
     got = oracle.roi.roi_align_restated(x.numpy(), r, (3, 4), 0.1, sr, aligned)
     assert np.allclose(got, ref, rtol=1e-5, atol=1e-5)
     assert np.array_equal(oracle.roi.roi_pool_restated(x.numpy(), r, (3, 4), 0.1), torchvision.ops.roi_pool(x, torch.from_numpy(r), (3, 4), 0.1).numpy())
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(1, 3), st.integers(1, 40), st.integers(2, 12), st.integers(0, 10_000), st.sampled_from([0.05, 0.3, 0.6]), st.sampled_from([0.3, 0.5, 0.7]))
+def test_roi_head_restatement_equals_torchvision_method_on_random_shapes(B, R, C, seed, score_thr, nms_thr):
+    """8f-1 oracle: the restatement (with its variant switches at their defaults) == torchvision's RoIHeads.postprocess_detections"""
+    import torch
+    import oracle
+    g = torch.Generator().manual_seed(seed)
+    lg = torch.randn(B * R, C, generator=g) * 3
+    rg = torch.randn(B * R, C * 4, generator=g) * 0.6
+    xy = torch.rand(B * R, 2, generator=g) * 200
+    pr = torch.cat((xy, xy + torch.rand(B * R, 2, generator=g) * 100 + 1), 1)
+    props, shapes = [pr[b * R:(b + 1) * R] for b in range(B)], [(240, 260)] * B
+    a = oracle.roi_head.postprocess_detections_tv(lg, rg, props, shapes, score_thr, nms_thr, 20)
+    b = oracle.roi_head.postprocess_detections(lg, rg, props, shapes, score_thr, nms_thr, 20)
+    for x, y in zip(a, b):
+        for u, v in zip(x, y):
+            assert torch.equal(u, v)

@@ -67,6 +67,11 @@ def yolo_cfg(tag, B, img, nc, G, seed, conf, iou, dense_scene):
     return heads_cpu, heads
 
 
+def cfg1():
+    """the reference's own CPU-runnable case: one image"""
+    yolo_cfg("cfg1", 1, 640, 80, 20, 1234, 0.25, 0.45, False)
+
+
 def cfg2():
     yolo_cfg("cfg2", 256, 640, 80, 20, 1235, 0.25, 0.45, False)
 
@@ -249,7 +254,7 @@ def cpu():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg2", "cfg2_half", "cfg3", "roihead", "cfg4", "cfg5", "zerocopy", "cpu"]
+    which = sys.argv[1:] or ["cfg1", "cfg2", "cfg2_half", "cfg3", "roihead", "cfg4", "cfg5", "zerocopy", "cpu"]
     torch.cuda.set_device(0)
     for w in which:
         print(f"==== {w}", flush=True)
