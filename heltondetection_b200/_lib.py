@@ -74,6 +74,7 @@ SIGNATURES = {
     "hd_roi_head_postprocess_workspace_size": (_sz, [_i, _i, _i]),
     "hd_roi_head_postprocess": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(C.c_float), _i, _f, _f, _f, _d, _f, _d, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hd_scale_detections": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    "hd_box_encode": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, C.POINTER(C.c_float), _vp, _vp]),
     "hd_match_workspace_size": (_sz, [_i, _i, _i]),
     "hd_match": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _d, _d, _i, _vp, _vp, _vp, _sz, _vp]),
     "hd_wbf_workspace_size": (_sz, [_i, _i, _i, _i]),
@@ -82,6 +83,7 @@ SIGNATURES = {
     "hd_roi_align": (_i, [C.POINTER(RoiLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
     "hd_roi_pool": (_i, [C.POINTER(RoiLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "hd_roi_set_mode": (_i, [_i]),
+    "hd_roi_pool_backward": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "hd_roi_align_backward": (_i, [_vp, _vp, _vp, _i64, C.POINTER(RoiLevel), _i, _i, _i, _i, _i, _i, _i, _vp]),
     "hd_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "hd_roi_level_map": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp]),

@@ -3,6 +3,7 @@
 ``Matcher`` keeps torchvision ``det_utils.Matcher`` semantics (models/detection/_utils.py:318-400) but takes the boxes
 instead of a materialised IoU matrix; ``anchor_labels`` reads the same matching as the lineage AnchorTargetCreator
 label rule (1 positive, 0 negative, -1 ignored; bubbliiiing frcnn utils_fit), without its random subsampling."""
+import ctypes as C
 import torch
 from . import _lib
 
@@ -47,3 +48,23 @@ def anchor_labels(gt_boxes, anchors, pos_iou_thresh=0.7, neg_iou_thresh=0.3, gt_
     m = Matcher(pos_iou_thresh, neg_iou_thresh, True)(gt_boxes, anchors, gt_count)
     label = torch.where(m >= 0, torch.ones_like(m), torch.where(m == BELOW_LOW_THRESHOLD, torch.zeros_like(m), -torch.ones_like(m)))
     return m.clamp(min=0), label
+
+
+def encode_boxes(gt_boxes, boxes, matches=None, weights=(1.0, 1.0, 1.0, 1.0)):
+    """torchvision BoxCoder.encode_single / lineage bbox2loc: regression targets of `boxes` towards their matched ground truth.
+    gt_boxes [G,4] | [B,G,4]; boxes [N,4] | [B,N,4]; matches [N] | [B,N] from Matcher (negative codes are read as GT 0, as
+    torchvision's clamp(min=0) does); matches=None encodes row i against row i."""
+    _lib.require_cuda(gt_boxes, boxes, matches)
+    single = gt_boxes.dim() == 2
+    gt = _lib.f32c(gt_boxes[None] if single else gt_boxes)
+    pr = _lib.f32c(boxes)
+    B, G = gt.shape[0], gt.shape[1]
+    per_image = pr.dim() == 3
+    N = pr.shape[-2]
+    out = torch.empty((B, N, 4), dtype=torch.float32, device=gt.device)
+    m = None
+    if matches is not None:
+        m = (matches[None] if matches.dim() == 1 else matches).to(torch.int64).contiguous()
+    w = (C.c_float * 4)(*[float(x) for x in weights])
+    _lib.check(_lib.lib().hd_box_encode(_lib.ptr(gt), B, G, _lib.ptr(m), _lib.ptr(pr), 1 if per_image else 0, N, w, _lib.ptr(out), _lib.stream()))
+    return out[0] if single else out

@@ -126,3 +126,43 @@ extern "C" HD_API int hd_match(const float* gt_boxes, const int32_t* gt_count, i
     if (matched_iou) HD_CUDA_CALL(cudaMemcpyAsync(matched_iou, best_iou, (size_t)B * N * 4, cudaMemcpyDeviceToDevice, st));
     return HD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ regression targets
+// BoxCoder.encode_single (torchvision models/detection/_utils.py:75-110) = lineage bbox2loc with weights: the targets that
+// train the RPN / RoI heads once the matching is known.  targets[b,i] = encode(gt[b, max(matches[b,i], 0)], pred[(b,) i]).
+__global__ void __launch_bounds__(256) box_encode_kernel(const float4* __restrict__ gt, int Gmax, const long long* __restrict__ matches,
+                                                         const float4* __restrict__ pred, long long pred_stride, int N, int B, float wx, float wy,
+                                                         float ww, float wh, float4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * N) return;
+    const int b = (int)(i / N), k = (int)(i - (long long)b * N);
+    const float4 p = pred[(size_t)b * pred_stride + k];
+    long long gi = matches ? matches[i] : k;
+    if (gi < 0) gi = 0;                       // torchvision clamps the -1 / -2 codes before gathering
+    const float4 g = gt[(size_t)b * Gmax + gi];
+    const float ew = __fsub_rn(p.z, p.x), eh = __fsub_rn(p.w, p.y);
+    const float ecx = __fadd_rn(p.x, __fmul_rn(0.5f, ew)), ecy = __fadd_rn(p.y, __fmul_rn(0.5f, eh));
+    const float gw = __fsub_rn(g.z, g.x), gh = __fsub_rn(g.w, g.y);
+    const float gcx = __fadd_rn(g.x, __fmul_rn(0.5f, gw)), gcy = __fadd_rn(g.y, __fmul_rn(0.5f, gh));
+    float4 t;
+    t.x = __fdiv_rn(__fmul_rn(wx, __fsub_rn(gcx, ecx)), ew);
+    t.y = __fdiv_rn(__fmul_rn(wy, __fsub_rn(gcy, ecy)), eh);
+    t.z = __fmul_rn(ww, logf(__fdiv_rn(gw, ew)));
+    t.w = __fmul_rn(wh, logf(__fdiv_rn(gh, eh)));
+    out[i] = t;
+}
+
+extern "C" HD_API int hd_box_encode(const float* gt_boxes, int B, int Gmax, const int64_t* matches, const float* pred_boxes, int pred_per_image,
+                                    int N, const float* weights, float* targets, void* stream) {
+    HD_CHECK_ARG(B >= 0 && Gmax >= 0 && N >= 0, "bad shape B=%d Gmax=%d N=%d", B, Gmax, N);
+    if (B == 0 || N == 0) return HD_OK;
+    HD_CHECK_ARG(Gmax > 0 && gt_boxes && pred_boxes && weights && targets, "null pointer or no ground-truth boxes");
+    HD_CHECK_ARG(matches != nullptr || Gmax == N, "without matches the call is elementwise: Gmax must equal N");
+    const long long n = (long long)B * N, blocks = (n + 255) / 256;
+    HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
+    box_encode_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)gt_boxes, Gmax, (const long long*)matches, (const float4*)pred_boxes,
+                                                                          pred_per_image ? (long long)N : 0, N, B, weights[0], weights[1], weights[2],
+                                                                          weights[3], (float4*)targets);
+    HD_CUDA_LAUNCH_CHECK("box_encode_kernel");
+    return HD_OK;
+}

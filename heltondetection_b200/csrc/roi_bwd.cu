@@ -164,3 +164,34 @@ extern "C" HD_API int hd_roi_align_backward(const float* grad_out, const float* 
     HD_CUDA_LAUNCH_CHECK("roi_align_bwd_strided_kernel");
     return HD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ RoIPool backward
+// torchvision _roi_pool_backward: grad_input[b, c, argmax[k,c,ph,pw]] += grad_output[k,c,ph,pw]  (argmax = h*W + w, -1 = empty bin)
+__global__ void __launch_bounds__(256) roi_pool_bwd_kernel(const float* __restrict__ grad_out, const int* __restrict__ argmax,
+                                                           const float* __restrict__ rois, long long K, int C, int nb, float* __restrict__ gi,
+                                                           long long sB, long long sC, long long sP) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * C * nb) return;
+    const int am = argmax[i];
+    if (am < 0) return;
+    const int c = (int)((i / nb) % C);
+    const long long k = i / ((long long)nb * C);
+    const int b = (int)rois[k * 5];
+    atomicAdd(gi + (size_t)b * sB + (size_t)c * sC + (size_t)am * sP, grad_out[i]);
+}
+
+extern "C" HD_API int hd_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois, int64_t K, float* grad_in, int layout,
+                                           int C, int H, int W, int pooled_h, int pooled_w, void* stream) {
+    HD_CHECK_ARG(K >= 0 && C >= 1 && H >= 1 && W >= 1 && pooled_h >= 1 && pooled_w >= 1, "bad shape");
+    HD_CHECK_ARG(layout == HD_LAYOUT_NCHW || layout == HD_LAYOUT_NHWC, "layout must be HD_LAYOUT_NCHW or HD_LAYOUT_NHWC, got %d", layout);
+    if (K == 0) return HD_OK;
+    HD_CHECK_ARG(grad_out && argmax && rois && grad_in, "null pointer");
+    const int nb = pooled_h * pooled_w;
+    const long long total = K * C * nb, blocks = (total + 255) / 256;
+    HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
+    const long long HW = (long long)H * W;
+    const long long sB = HW * C, sC = (layout == HD_LAYOUT_NHWC) ? 1 : HW, sP = (layout == HD_LAYOUT_NHWC) ? C : 1;
+    roi_pool_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, argmax, rois, K, C, nb, grad_in, sB, sC, sP);
+    HD_CUDA_LAUNCH_CHECK("roi_pool_bwd_kernel");
+    return HD_OK;
+}

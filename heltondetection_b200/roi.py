@@ -115,6 +115,38 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_height, pooled_width, b
     return gi
 
 
+def roi_pool_backward(grad, rois, argmax, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width, channels_last=False):
+    """torch.ops.torchvision._roi_pool_backward schema -> grad_input [B,C,H,W]"""
+    _lib.require_cuda(grad, rois, argmax)
+    grad, rois = _lib.f32c(grad), _lib.f32c(rois.to(torch.float32))
+    argmax = argmax.to(torch.int32).contiguous()
+    if channels_last:
+        gi = torch.zeros((batch_size, height, width, channels), dtype=torch.float32, device=grad.device).permute(0, 3, 1, 2)
+    else:
+        gi = torch.zeros((batch_size, channels, height, width), dtype=torch.float32, device=grad.device)
+    K = rois.shape[0]
+    if K:
+        _lib.check(_lib.lib().hd_roi_pool_backward(_lib.ptr(grad), _lib.ptr(argmax), _lib.ptr(rois), K, _lib.ptr(gi),
+                                                   _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, channels, height, width,
+                                                   int(pooled_height), int(pooled_width), _lib.stream()))
+    return gi
+
+
+class _RoIPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input, rois, output_size, spatial_scale, layout):
+        out, argmax = _run([input], [spatial_scale], rois, None, output_size, 0, False, True, layout, return_argmax=True)
+        ctx.save_for_backward(rois, argmax)
+        ctx.args = (tuple(input.shape), _pair(output_size), float(spatial_scale), _is_channels_last(input))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        rois, argmax = ctx.saved_tensors
+        (B, C, H, W), (PH, PW), scale, cl = ctx.args
+        return roi_pool_backward(grad, rois, argmax, scale, PH, PW, B, C, H, W, channels_last=cl), None, None, None, None
+
+
 class _RoIAlignFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, input, rois, output_size, spatial_scale, sampling_ratio, aligned, layout):
@@ -139,8 +171,10 @@ def roi_align(input, boxes, output_size, spatial_scale=1.0, sampling_ratio=-1, a
 
 
 def roi_pool(input, boxes, output_size, spatial_scale=1.0, layout="auto"):
-    """torchvision.ops.roi_pool (roi_pool.py:15-53)."""
+    """torchvision.ops.roi_pool (roi_pool.py:15-53); differentiable w.r.t. `input`."""
     rois = _check_rois(boxes)
+    if input.requires_grad and torch.is_grad_enabled():
+        return _RoIPoolFn.apply(input, rois, output_size, spatial_scale, layout)
     return _run([input], [spatial_scale], rois, None, output_size, 0, False, True, layout)
 
 

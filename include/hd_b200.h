@@ -179,6 +179,10 @@ HD_API int hd_roi_pool(const hd_roi_level* levels /*host*/, int n_levels, int la
 HD_API int hd_roi_align_backward(const float* grad_out, const float* rois, const int32_t* level_ids, int64_t K,
                                  const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, int pooled_h, int pooled_w,
                                  int sampling_ratio, int aligned, void* stream);
+/* RoIPool backward (torchvision _roi_pool_backward): grad_in[b,c,argmax[k,c,ph,pw]] += grad_out[k,c,ph,pw]; grad_in ([B,C,H,W] in the
+ * given layout) must be zero-filled by the caller; argmax as written by hd_roi_pool. */
+HD_API int hd_roi_pool_backward(const float* grad_out, const int32_t* argmax, const float* rois, int64_t K, float* grad_in, int layout, int C,
+                                int H, int W, int pooled_h, int pooled_w, void* stream);
 /* RoIAlign kernel choice (process-wide; developer / test aid): 0 = automatic (the gather kernels), 1 = gather kernels only,
  * 2 = experimental staged-row (TMA ring) kernel whenever eligible (NHWC, C % 4 == 0, sampling_ratio 1 or 2, output <= 8x8;
  * bit-identical results, currently slower).  Returns the previous mode. */
@@ -236,6 +240,10 @@ HD_API int hd_scale_detections(const float* det, const int32_t* count, int B, in
  *   allow_low_quality every prediction that attains some GT's best IoU keeps its arg-max match.
  *   matched_iou [B,N] (nullable): the best IoU.  Boxes are expected proper (x2 >= x1, y2 >= y1).
  * ------------------------------------------------------------------------------------------- */
+/* Regression targets once the matching is known: torchvision BoxCoder.encode_single (_utils.py:75-110) / lineage bbox2loc.
+ * targets[b,i] = weights * encode(gt[b, max(matches[b,i],0)], pred[(b,)i]); matches NULL = elementwise (Gmax == N).  weights: host[4]. */
+HD_API int hd_box_encode(const float* gt_boxes, int B, int Gmax, const int64_t* matches, const float* pred_boxes, int pred_per_image, int N,
+                         const float* weights /*host[4]*/, float* targets, void* stream);
 HD_API size_t hd_match_workspace_size(int B, int Gmax, int N);
 HD_API int hd_match(const float* gt_boxes, const int32_t* gt_count, int B, int Gmax, const float* pred_boxes, int pred_per_image, int N,
                     double high_threshold, double low_threshold, int allow_low_quality, int64_t* matches, float* matched_iou,

@@ -48,3 +48,17 @@ def test_matcher_batched_padded_and_labels():
     assert torch.equal(label.cpu(), torch.where(ref >= 0, 1, torch.where(ref == -1, 0, -1)))
     with pytest.raises(ValueError):
         assign.Matcher(0.7, 0.3)(torch.zeros(0, 4).cuda(), an.cuda())
+
+
+def test_box_encode_matches_torchvision_boxcoder():
+    """regression targets (BoxCoder.encode_single) on the matched pairs: <= 1e-5 relative (logf differs by ulps between libm and CUDA)"""
+    from torchvision.models.detection._utils import BoxCoder
+    from heltondetection_b200 import assign
+    gt, an = _boxes(25, 3), _boxes(4000, 4)
+    m = TVMatcher(0.7, 0.3, True)(torchvision.ops.box_iou(gt, an))
+    for w in ((1.0, 1.0, 1.0, 1.0), (10.0, 10.0, 5.0, 5.0)):
+        ref = BoxCoder(w).encode_single(gt[m.clamp(min=0)], an)
+        got = assign.encode_boxes(gt.cuda(), an.cuda(), m.cuda(), w).cpu()
+        assert bool(((got.double() - ref.double()).abs() <= 1e-5 * ref.double().abs().clamp(min=1e-2)).all())
+    ref = BoxCoder((1.0, 1.0, 1.0, 1.0)).encode_single(gt, an[:25])
+    assert bool(((assign.encode_boxes(gt.cuda(), an[:25].cuda()).cpu() - ref).abs() <= 1e-5 * ref.abs().clamp(min=1e-2)).all())

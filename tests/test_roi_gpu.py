@@ -168,3 +168,16 @@ def test_roi_align_backward_matches_torchvision(channels_last, C, sr, aligned):
     xr = x.clone().requires_grad_(True)
     torchvision.ops.roi_align(xr, rois, 7, 0.125, sr, aligned).backward(go)
     assert float((xin.grad.cpu() - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_roi_pool_backward_matches_torchvision(channels_last):
+    from heltondetection_b200 import ops
+    x, rois = _data(B=2, C=24, H=40, W=36, K=150, img=320, seed=31)
+    g = torch.Generator().manual_seed(6)
+    go = torch.randn((rois.shape[0], 24, 7, 7), generator=g)
+    xr = x.clone().requires_grad_(True)
+    torchvision.ops.roi_pool(xr, rois, 7, 0.125).backward(go)
+    xin = (x.cuda().contiguous(memory_format=torch.channels_last) if channels_last else x.cuda()).requires_grad_(True)
+    ops.roi_pool(xin, rois.cuda(), 7, 0.125).backward(go.cuda())
+    assert float((xin.grad.cpu() - xr.grad).abs().max()) <= 1e-5 * float(xr.grad.abs().max())
