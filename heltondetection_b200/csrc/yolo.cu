@@ -251,6 +251,101 @@ __global__ void __launch_bounds__(256, 4) yolo_decode_filter_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------
+// NHWC heads (HD_FLAG_IN_NHWC; SURVEY.md 8f-4: the layout the final 1x1 conv produces in channels_last).  The A*(5+nc)
+// values of a cell are contiguous, so a (cell, anchor) pair owns 5+nc consecutive floats.  A CTA takes a tile of
+// NHWC_TC consecutive cells of one (image, level):
+//   dense  -- the tile (TC * A * no floats, contiguous in memory) is streamed into shared memory with 128-bit loads,
+//             then each thread scans the values of one (cell, anchor) pair (lane stride = no words: conflict free for odd no);
+//   sparse -- each thread first reads only its pair's objectness; pairs that pass the gate read their own no floats
+//             straight from global memory (rare: ~0.5 % of the pairs at conf 0.25).
+// The per-pair arithmetic is the NCHW kernel's, value for value, so both layouts give identical candidates.
+// ------------------------------------------------------------------------------------------------
+#define NHWC_TC 64
+__global__ void __launch_bounds__(256) yolo_decode_filter_nhwc_kernel(const __grid_constant__ YoloParams p, float4* __restrict__ cand_box,
+                                                                      float* __restrict__ cand_score, int* __restrict__ cand_cls,
+                                                                      int* __restrict__ cand_anchor, int* __restrict__ cand_count) {
+    extern __shared__ __align__(16) float tile[];   // dense mode: [TC][A*no]
+    const int tid = threadIdx.x, lane = tid & 31;
+    // item -> (image, level, tile); tile_start[] counts NHWC_TC-cell tiles per image here (items_per_image = tiles, not A*tiles)
+    const long long item = blockIdx.x;
+    const int b = (int)(item / p.items_per_image);
+    int r = (int)(item - (long long)b * p.items_per_image);
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < HD_MAX_LEVELS; ++q)
+        if (q < p.n_levels && r >= p.tile_start[q]) l = q;
+    r -= p.tile_start[l];
+    const int HW = p.HW[l], W = p.W[l], no = p.no, row = p.A * no;
+    const int cell0 = r * NHWC_TC, ncell = min(NHWC_TC, HW - cell0);
+    const float* __restrict__ gbase = reinterpret_cast<const float*>(p.data[l]) + ((size_t)b * HW + cell0) * row;
+    const int nval = ncell * row;
+    if (p.dense) {
+        if ((((uintptr_t)gbase) & 15) == 0) {
+            for (int i = tid; i < (nval >> 2); i += 256) reinterpret_cast<float4*>(tile)[i] = hd_ldg_stream4(gbase + 4 * i);
+            for (int i = (nval & ~3) + tid; i < nval; i += 256) tile[i] = hd_ldg_stream(gbase + i);
+        } else {
+            for (int i = tid; i < nval; i += 256) tile[i] = hd_ldg_stream(gbase + i);
+        }
+        __syncthreads();
+    }
+    const int npair = ncell * p.A;
+    for (int t0 = 0; t0 < npair; t0 += 256) {           // block-uniform trip count (warp ballots inside)
+        const int t = t0 + tid;
+        bool pass = false;
+        float conf = 0.f; int j = 0, cell = 0, a = 0;
+        const float* v = nullptr;
+        if (t < npair) {
+            const int lc = t / p.A;
+            a = t - lc * p.A; cell = cell0 + lc;
+            v = p.dense ? (tile + (size_t)lc * row + a * no) : (gbase + (size_t)lc * row + a * no);
+            const float o = v[4];
+            if (o > p.gate) {
+                float m = -INFINITY, L = -INFINITY;
+                for (int c = 0; c < p.nc; ++c) {
+                    const float x = v[5 + c];
+                    const bool g = x > m;
+                    L = g ? m : L; j = g ? c : j; m = g ? x : m;
+                }
+                const float po = hd_sigmoid(o);
+                const float cf = __fmul_rn(hd_sigmoid(m), po);
+                const bool ok = p.ge ? (po >= p.thr && cf >= p.thr) : (po > p.thr && cf > p.thr);
+                if (ok) {
+                    if (L > -INFINITY && __fmul_rn(hd_sigmoid(L), po) == cf) {
+                        // an earlier class ties after rounding: torch.max returns the first maximal product
+                        for (int cc = 0; cc < j; ++cc)
+                            if (__fmul_rn(hd_sigmoid(v[5 + cc]), po) == cf) { j = cc; break; }
+                    }
+                    pass = true; conf = cf;
+                }
+            }
+        }
+        const unsigned mk = __ballot_sync(HD_FULL, pass);
+        if (mk) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cand_count + b, __popc(mk));
+            base = __shfl_sync(HD_FULL, base, 0);
+            const int slot = base + __popc(mk & hd_lanemask_lt());
+            if (pass && slot < p.cap) {
+                const float s = p.stride[l];
+                const float aw = p.anchor[l][2 * a], ah = p.anchor[l][2 * a + 1];
+                const int gi = cell / W, gj = cell - gi * W;
+                const float px = __fmul_rn(hd_sigmoid(v[0]), 2.0f), py = __fmul_rn(hd_sigmoid(v[1]), 2.0f);
+                const float pw = __fmul_rn(hd_sigmoid(v[2]), 2.0f), ph = __fmul_rn(hd_sigmoid(v[3]), 2.0f);
+                const float cx = __fmul_rn(__fadd_rn(__fsub_rn(px, 0.5f), (float)gj), s);
+                const float cy = __fmul_rn(__fadd_rn(__fsub_rn(py, 0.5f), (float)gi), s);
+                const float w = __fmul_rn(__fmul_rn(pw, pw), aw), h = __fmul_rn(__fmul_rn(ph, ph), ah);
+                const float hw2 = __fmul_rn(w, 0.5f), hh2 = __fmul_rn(h, 0.5f);
+                const size_t g = (size_t)b * p.cap + slot;
+                cand_box[g] = make_float4(__fsub_rn(cx, hw2), __fsub_rn(cy, hh2), __fadd_rn(cx, hw2), __fadd_rn(cy, hh2));
+                cand_score[g] = conf;
+                cand_cls[g] = j;
+                cand_anchor[g] = p.level_off[l] + a * HW + cell;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Dense decode to pred[B, N, 5+nc] (drop-in for decode_box).  A warp reads 32 consecutive cells of
 // every plane (coalesced), transposes through padded shared memory and writes the 32 output rows,
 // which are contiguous in pred, with fully coalesced stores.
@@ -420,6 +515,23 @@ extern "C" HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels, int n_l
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0) return HD_OK;
     HD_CUDA_CALL(cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)B, st));
+    if (flags & HD_FLAG_IN_NHWC) {
+        HD_CHECK_ARG(!(flags & (HD_FLAG_IN_F16 | HD_FLAG_IN_BF16)), "NHWC heads are fp32 only");
+        YoloParams pn;
+        rc = fill_params(pn, levels, n_levels, B, A, nc, NHWC_TC);
+        if (rc) return rc;
+        pn.thr = p.thr; pn.gate = p.gate; pn.ge = p.ge; pn.dense = p.dense; pn.cap = p.cap;
+        pn.items_per_image = pn.tile_start[n_levels];          // tiles of NHWC_TC cells; a CTA handles all A anchors of its cells
+        pn.total_items = (long long)B * pn.items_per_image;
+        HD_CHECK_ARG(pn.total_items < (1ll << 31), "grid too large");
+        const size_t sm = pn.dense ? (size_t)NHWC_TC * A * (5 + nc) * 4 : 0;
+        HD_CHECK_ARG(sm <= 200 * 1024, "A*(5+nc)=%d too large for the NHWC tile", A * (5 + nc));
+        static bool nhwc_attr = false;
+        if (!nhwc_attr) { HD_CUDA_CALL(cudaFuncSetAttribute(yolo_decode_filter_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); nhwc_attr = true; }
+        yolo_decode_filter_nhwc_kernel<<<(unsigned)pn.total_items, 256, sm, st>>>(pn, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count);
+        HD_CUDA_LAUNCH_CHECK("yolo_decode_filter_nhwc_kernel");
+        return HD_OK;
+    }
     const int dt = (flags & HD_FLAG_IN_F16) ? 1 : ((flags & HD_FLAG_IN_BF16) ? 2 : 0);
     HD_CHECK_ARG(!((flags & HD_FLAG_IN_F16) && (flags & HD_FLAG_IN_BF16)), "HD_FLAG_IN_F16 and HD_FLAG_IN_BF16 are exclusive");
     bool vec = true;

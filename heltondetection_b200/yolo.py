@@ -21,9 +21,17 @@ def _is_pinned_host(x):
 
 
 _HALF_FLAGS = {torch.float16: 4, torch.bfloat16: 8}   # HD_FLAG_IN_F16 / HD_FLAG_IN_BF16
+_FLAG_IN_NHWC = 128
+
+
+def _is_nhwc(x):
+    """channels_last storage of a [B,C,H,W] head (and not at the same time plain contiguous)"""
+    return x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
 
 
 def _dtype_flag(keep):
+    if keep[0].dtype == torch.float32 and all(_is_nhwc(x) for x in keep):
+        return _FLAG_IN_NHWC
     return _HALF_FLAGS.get(keep[0].dtype, 0)
 
 
@@ -45,6 +53,8 @@ def _levels(outputs, anchors, strides, host_ok=False, half_ok=False):
             raise RuntimeError(f"level {l}: expected [B={B}, {Ctot}, H, W], got {tuple(x.shape)}")
         if half_ok and x.dtype in _HALF_FLAGS and x.dtype == outputs[0].dtype:
             x = x if x.is_contiguous() else x.contiguous()   # 16-bit heads are widened to fp32 inside the kernel
+        elif half_ok and x.dtype == torch.float32 and x.is_cuda and all(_is_nhwc(o) and o.dtype == torch.float32 for o in outputs):
+            pass                                             # channels_last heads are read in place by the NHWC kernel
         else:
             x = _lib.f32c(x)
         keep.append(x)
@@ -94,7 +104,8 @@ class YoloPostprocessor:
     __call__(outputs) -> (det [B,max_det,6] = x1,y1,x2,y2,conf,cls ; count [B] int32 ; idx [B,max_det] anchor ids)
     all on the device, padded, with no host synchronisation (CUDA-graph capturable).  `outputs` may be fp32, or fp16 /
     bf16 heads (an autocast model): the kernel widens them to fp32 on load and computes in fp32, i.e. the result equals
-    the fp32 path run on ``outputs.float()``, at half the HBM traffic."""
+    the fp32 path run on ``outputs.float()``, at half the HBM traffic.  fp32 heads in torch.channels_last memory (what a
+    channels_last model's final 1x1 conv produces) are read in place by the NHWC kernel; same candidates as the NCHW path."""
 
     def __init__(self, anchors=DEFAULT_ANCHORS, strides=DEFAULT_STRIDES, conf_thres=0.25, iou_thres=0.45,
                  agnostic=False, max_det=300, max_nms=30000, max_wh=7680.0, class_mode="offset", ge=False,

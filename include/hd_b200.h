@@ -49,6 +49,8 @@ extern "C" {
 #define HD_FLAG_DENSE_READ 2  /* stream every head element (no objectness-tile skip) */
 #define HD_FLAG_IN_F16 4      /* hd_yolo_decode_filter / hd_yolo_postprocess*: levels[].data points to IEEE half heads */
 #define HD_FLAG_IN_BF16 8     /* ... to bfloat16 heads.  Elements are widened to fp32 on load (exact); all arithmetic is fp32 */
+#define HD_FLAG_IN_NHWC 128   /* ... to fp32 heads stored [B, H, W, A*(5+nc)] (torch channels_last of the NCHW head): the layout the
+                               * final 1x1 conv produces; same candidates as the NCHW path */
 
 /* class handling of the batched NMS */
 #define HD_NMS_AGNOSTIC 0

@@ -164,3 +164,27 @@ def test_half_precision_heads_equal_the_fp32_path_on_widened_inputs(dtype, dense
     bq = yolo.YoloPostprocessor(conf_thres=0.3, dense_read=dense).candidates([o.float() for o in odd])
     for (ca, ia), (cb, ib) in zip(a, bq):
         assert torch.equal(ca, cb) and torch.equal(ia, ib)
+
+
+@pytest.mark.parametrize("dense", [False, True])
+@pytest.mark.parametrize("nc,img", [(80, 320), (10, 416), (1, 160)])
+def test_channels_last_heads_give_the_same_detections(dense, nc, img):
+    """8f-4: heads in torch.channels_last memory go through the NHWC kernel (same per-(cell,anchor) arithmetic): identical
+    candidates, hence bit-identical detections, and equal to the oracle's keep indices."""
+    import oracle
+    from heltondetection_b200 import synth, yolo
+    heads, _ = synth.yolo_heads(3, img, nc, 10, 77 + nc)
+    nchw = [h.cuda() for h in heads]
+    nhwc = [h.contiguous(memory_format=torch.channels_last) for h in nchw]
+    assert all(yolo._is_nhwc(h) for h in nhwc)
+    a = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=dense).candidates(nchw)
+    b = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=dense).candidates(nhwc)
+    for (ca, ia), (cb, ib) in zip(a, b):
+        assert torch.equal(ia, ib) and torch.equal(ca, cb)
+    d1, c1, i1 = [t.clone() for t in yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=dense)(nchw)]
+    d2, c2, i2 = [t.clone() for t in yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=dense)(nhwc)]
+    assert torch.equal(c1, c2)
+    ref, ridx = oracle.yolo.non_max_suppression(oracle.yolo.decode_box(heads), 0.25, 0.45, return_index=True)
+    for k in range(3):
+        n = int(c1[k])
+        assert torch.equal(d1[k, :n], d2[k, :n]) and torch.equal(i1[k, :n], i2[k, :n]) and torch.equal(i2[k, :n].cpu(), ridx[k])

@@ -88,6 +88,13 @@ def cfg2_half():
             t = timeit(rp, iters=50)
             report(f"cfg2 {str(dt)[6:]} heads, full postprocess, graph ({'dense' if mode else 'sparse'})", t, nbytes, 256)
         del heads
+    heads = [h.cuda().contiguous(memory_format=torch.channels_last) for h in heads_cpu]
+    nbytes = sum(h.numel() * 4 for h in heads)
+    for mode in (True, False):
+        pp = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=mode)
+        rp, det, cnt, idx = pp.graph(heads)
+        t = timeit(rp, iters=50)
+        report(f"cfg2 fp32 channels_last (NHWC) heads, full postprocess, graph ({'dense' if mode else 'sparse'})", t, nbytes, 256)
 
 
 def cfg4():
