@@ -50,6 +50,12 @@ roi.set_mode(0)
 h16, _ = synth.yolo_heads(64, 640, 80, 20, 1235)
 d16 = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=True)([h.half().cuda() for h in h16])
 del h16
+tg = assign.encode_boxes(gtb, rois[:, 1:].contiguous(), m, (10.0, 10.0, 5.0, 5.0))
+po, pam = roi.roi_pool_with_argmax(nhwc0, rois[:2000].contiguous(), 7, 0.25)
+gp = roi.roi_pool_backward(po, rois[:2000].contiguous(), pam, 0.25, 7, 7, B, 256, nhwc0.shape[2], nhwc0.shape[3], channels_last=True)
+hcl, _ = synth.yolo_heads(64, 640, 80, 20, 1235)
+dcl = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45, dense_read=True)([h.cuda().contiguous(memory_format=torch.channels_last) for h in hcl])
+del hcl
 print("8f rows ok", dcnt.tolist(), int((m >= 0).sum()))
 # cfg5
 views, _ = synth.tta_heads(8, 640, 80, G=20, seed=1239)
