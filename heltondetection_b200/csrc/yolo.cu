@@ -345,6 +345,133 @@ __global__ void __launch_bounds__(256) yolo_decode_filter_nhwc_kernel(const __gr
     }
 }
 
+// Dense NHWC variant with the tile moved by the TMA engine: a persistent CTA walks its tiles (32 cells = 32.6 KB at 255
+// channels, contiguous in memory) with two shared-memory buffers; one thread issues cp.async.bulk for tile k+1 (completion on
+// an mbarrier) while all threads scan tile k, so no issue slots or registers are spent on the loads and a load is always in
+// flight per CTA.  Per-pair arithmetic identical to the kernels above.
+#define NHWC_TMA_TC 32
+__device__ __forceinline__ void yl_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void yl_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void yl_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void yl_bulk_load(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(128) yolo_decode_filter_nhwc_tma_kernel(const __grid_constant__ YoloParams p, float4* __restrict__ cand_box,
+                                                                          float* __restrict__ cand_score, int* __restrict__ cand_cls,
+                                                                          int* __restrict__ cand_anchor, int* __restrict__ cand_count, int buf_floats) {
+    extern __shared__ __align__(128) float tiles[];   // [2][buf_floats]
+    __shared__ unsigned long long bar[2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int no = p.no, row = p.A * no;
+    auto locate = [&](long long item, int& b, int& l, int& cell0, int& ncell, const float*& g) {
+        b = (int)(item / p.items_per_image);
+        int r = (int)(item - (long long)b * p.items_per_image);
+        l = 0;
+#pragma unroll
+        for (int q = 1; q < HD_MAX_LEVELS; ++q)
+            if (q < p.n_levels && r >= p.tile_start[q]) l = q;
+        r -= p.tile_start[l];
+        cell0 = r * NHWC_TMA_TC; ncell = min(NHWC_TMA_TC, p.HW[l] - cell0);
+        g = reinterpret_cast<const float*>(p.data[l]) + ((size_t)b * p.HW[l] + cell0) * row;
+    };
+    if (tid == 0) {
+        yl_mbar_init(&bar[0], 1); yl_mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    long long item = blockIdx.x;
+    if (item >= p.total_items) return;
+    if (tid == 0) {
+        int b, l, c0, nc_; const float* g;
+        locate(item, b, l, c0, nc_, g);
+        const unsigned bytes = (unsigned)(nc_ * row * 4);
+        yl_mbar_expect_tx(&bar[0], bytes);
+        yl_bulk_load(tiles, g, bytes, &bar[0]);
+    }
+    for (int k = 0; item < p.total_items; item += gridDim.x, ++k) {
+        const int cur = k & 1;
+        const long long nxt = item + gridDim.x;
+        if (tid == 0 && nxt < p.total_items) {   // buffer cur^1 was released by the __syncthreads that ended iteration k-1
+            int b, l, c0, nc_; const float* g;
+            locate(nxt, b, l, c0, nc_, g);
+            const unsigned bytes = (unsigned)(nc_ * row * 4);
+            yl_mbar_expect_tx(&bar[cur ^ 1], bytes);
+            yl_bulk_load(tiles + (size_t)(cur ^ 1) * buf_floats, g, bytes, &bar[cur ^ 1]);
+        }
+        int b, l, cell0, ncell; const float* gsrc;
+        locate(item, b, l, cell0, ncell, gsrc);
+        yl_mbar_wait(&bar[cur], (unsigned)((k >> 1) & 1));
+        const float* tile = tiles + (size_t)cur * buf_floats;
+        const int HW = p.HW[l], W = p.W[l];
+        const int npair = ncell * p.A;
+        for (int t0 = 0; t0 < npair; t0 += 128) {
+            const int t = t0 + tid;
+            bool pass = false;
+            float conf = 0.f; int j = 0, cell = 0, a = 0;
+            const float* v = nullptr;
+            if (t < npair) {
+                const int lc = t / p.A;
+                a = t - lc * p.A; cell = cell0 + lc;
+                v = tile + (size_t)lc * row + a * no;
+                const float o = v[4];
+                if (o > p.gate) {
+                    float m = -INFINITY, L = -INFINITY;
+                    for (int c = 0; c < p.nc; ++c) {
+                        const float x = v[5 + c];
+                        const bool g = x > m;
+                        L = g ? m : L; j = g ? c : j; m = g ? x : m;
+                    }
+                    const float po = hd_sigmoid(o);
+                    const float cf = __fmul_rn(hd_sigmoid(m), po);
+                    const bool ok = p.ge ? (po >= p.thr && cf >= p.thr) : (po > p.thr && cf > p.thr);
+                    if (ok) {
+                        if (L > -INFINITY && __fmul_rn(hd_sigmoid(L), po) == cf) {
+                            for (int cc = 0; cc < j; ++cc)
+                                if (__fmul_rn(hd_sigmoid(v[5 + cc]), po) == cf) { j = cc; break; }
+                        }
+                        pass = true; conf = cf;
+                    }
+                }
+            }
+            const unsigned mk = __ballot_sync(HD_FULL, pass);
+            if (mk) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(cand_count + b, __popc(mk));
+                base = __shfl_sync(HD_FULL, base, 0);
+                const int slot = base + __popc(mk & hd_lanemask_lt());
+                if (pass && slot < p.cap) {
+                    const float s = p.stride[l];
+                    const float aw = p.anchor[l][2 * a], ah = p.anchor[l][2 * a + 1];
+                    const int gi = cell / W, gj = cell - gi * W;
+                    const float px = __fmul_rn(hd_sigmoid(v[0]), 2.0f), py = __fmul_rn(hd_sigmoid(v[1]), 2.0f);
+                    const float pw = __fmul_rn(hd_sigmoid(v[2]), 2.0f), ph = __fmul_rn(hd_sigmoid(v[3]), 2.0f);
+                    const float cx = __fmul_rn(__fadd_rn(__fsub_rn(px, 0.5f), (float)gj), s);
+                    const float cy = __fmul_rn(__fadd_rn(__fsub_rn(py, 0.5f), (float)gi), s);
+                    const float w = __fmul_rn(__fmul_rn(pw, pw), aw), h = __fmul_rn(__fmul_rn(ph, ph), ah);
+                    const float hw2 = __fmul_rn(w, 0.5f), hh2 = __fmul_rn(h, 0.5f);
+                    const size_t g = (size_t)b * p.cap + slot;
+                    cand_box[g] = make_float4(__fsub_rn(cx, hw2), __fsub_rn(cy, hh2), __fadd_rn(cx, hw2), __fadd_rn(cy, hh2));
+                    cand_score[g] = conf;
+                    cand_cls[g] = j;
+                    cand_anchor[g] = p.level_off[l] + a * HW + cell;
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with buffer `cur`: it may be refilled two iterations from now
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Dense decode to pred[B, N, 5+nc] (drop-in for decode_box).  A warp reads 32 consecutive cells of
 // every plane (coalesced), transposes through padded shared memory and writes the 32 output rows,
@@ -524,6 +651,32 @@ extern "C" HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels, int n_l
         pn.items_per_image = pn.tile_start[n_levels];          // tiles of NHWC_TC cells; a CTA handles all A anchors of its cells
         pn.total_items = (long long)B * pn.items_per_image;
         HD_CHECK_ARG(pn.total_items < (1ll << 31), "grid too large");
+        // dense + 16-byte aligned rows: TMA double-buffered persistent kernel
+        bool tma_ok = pn.dense != 0;
+        for (int l = 0; l < n_levels; ++l) tma_ok = tma_ok && (((uintptr_t)pn.data[l] & 15) == 0) && (((size_t)pn.HW[l] * A * (5 + nc) * 4) % 16 == 0);
+        tma_ok = tma_ok && (((size_t)NHWC_TMA_TC * A * (5 + nc) * 4) % 16 == 0);
+        if (tma_ok) {
+            YoloParams pt;
+            rc = fill_params(pt, levels, n_levels, B, A, nc, NHWC_TMA_TC);
+            if (rc) return rc;
+            pt.thr = p.thr; pt.gate = p.gate; pt.ge = p.ge; pt.dense = 1; pt.cap = p.cap;
+            pt.items_per_image = pt.tile_start[n_levels];
+            pt.total_items = (long long)B * pt.items_per_image;
+            const int buf_floats = (int)hd_align_up((size_t)NHWC_TMA_TC * A * (5 + nc), 32);
+            const size_t smt = 2 * (size_t)buf_floats * 4;
+            if (smt <= 200 * 1024) {
+                static bool tma_attr = false;
+                if (!tma_attr) { HD_CUDA_CALL(cudaFuncSetAttribute(yolo_decode_filter_nhwc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); tma_attr = true; }
+                int per_sm = (int)((220 * 1024) / (smt + 1024));
+                if (per_sm < 1) per_sm = 1;
+                if (per_sm > 8) per_sm = 8;
+                long long grid = (long long)HD_NUM_SMS * per_sm;
+                if (grid > pt.total_items) grid = pt.total_items;
+                yolo_decode_filter_nhwc_tma_kernel<<<(unsigned)grid, 128, smt, st>>>(pt, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count, buf_floats);
+                HD_CUDA_LAUNCH_CHECK("yolo_decode_filter_nhwc_tma_kernel");
+                return HD_OK;
+            }
+        }
         const size_t sm = pn.dense ? (size_t)NHWC_TC * A * (5 + nc) * 4 : 0;
         HD_CHECK_ARG(sm <= 200 * 1024, "A*(5+nc)=%d too large for the NHWC tile", A * (5 + nc));
         static bool nhwc_attr = false;
