@@ -16,7 +16,7 @@ FLAG_CONF_GE = 1
 FLAG_DENSE_READ = 2
 NMS_AGNOSTIC, NMS_CLASS_EXACT, NMS_CLASS_OFFSET = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
-RPN_SOFTMAX, RPN_CLAMP_DWH = 1, 2
+RPN_SOFTMAX, RPN_CLAMP_DWH, RPN_KEY_LOGIT = 1, 2, 4
 ROIHEAD_MUL_STD, ROIHEAD_CLAMP_DWH, ROIHEAD_LABEL_MINUS1 = 16, 32, 64
 BOX_XYWH = 1
 WBF_AVG, WBF_MAX = 0, 1

@@ -20,6 +20,7 @@ struct RpnParams {
     int n_levels, B, A, softmax;
     float img_h, img_w, min_size, clamp_dwh;
     int use_clamp;
+    int key_logit;          // sort key from the raw objectness logit (torchvision takes its per-level top-k on the logits)
     long long total_cells;  // B * sum(HW)
     int N;                  // anchors per image
 };
@@ -50,14 +51,15 @@ __global__ void __launch_bounds__(256) rpn_decode_kernel(const __grid_constant__
     const float* __restrict__ dl = p.dlt[l] + (size_t)b * 4 * p.A * HW + cell;
     const size_t out0 = (size_t)b * p.N + p.level_off[l] + (size_t)cell * p.A;
     for (int a = 0; a < p.A; ++a) {
-        float score;
+        float score, logit = 0.0f;
         if (p.softmax) {  // F.softmax over (bg, fg): exp(x - max) / sum
             const float s0 = hd_ldg_stream(ob + (size_t)(2 * a) * HW), s1 = hd_ldg_stream(ob + (size_t)(2 * a + 1) * HW);
             const float m = fmaxf(s0, s1);
             const float e0 = expf(__fsub_rn(s0, m)), e1 = expf(__fsub_rn(s1, m));
             score = __fdiv_rn(e1, __fadd_rn(e0, e1));
         } else {
-            score = hd_sigmoid(hd_ldg_stream(ob + (size_t)a * HW));
+            logit = hd_ldg_stream(ob + (size_t)a * HW);
+            score = hd_sigmoid(logit);
         }
         const float dx = hd_ldg_stream(dl + (size_t)(4 * a) * HW), dy = hd_ldg_stream(dl + (size_t)(4 * a + 1) * HW);
         float dw = hd_ldg_stream(dl + (size_t)(4 * a + 2) * HW), dh = hd_ldg_stream(dl + (size_t)(4 * a + 3) * HW);
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) rpn_decode_kernel(const __grid_constant__
         const bool ok = (__fsub_rn(x2, x1) >= p.min_size) && (__fsub_rn(y2, y1) >= p.min_size);
         boxes[out0 + a] = make_float4(x1, y1, x2, y2);
         scores[out0 + a] = score;
-        uint32_t k = hd_orderable(score);
+        uint32_t k = hd_orderable((p.key_logit && !p.softmax) ? logit : score);
         keys[out0 + a] = ok ? (k == 0u ? 1u : k) : 0u;
     }
 }
@@ -630,6 +632,7 @@ static int rpn_fill(RpnParams& p, const hd_rpn_level* levels, int n_levels, int 
     p.n_levels = n_levels; p.B = B; p.A = A; p.softmax = (flags & HD_RPN_SOFTMAX) ? 1 : 0;
     p.img_h = img_h; p.img_w = img_w; p.min_size = min_size;
     p.use_clamp = (flags & HD_RPN_CLAMP_DWH) ? 1 : 0; p.clamp_dwh = clamp_dwh;
+    p.key_logit = (flags & HD_RPN_KEY_LOGIT) ? 1 : 0;
     p.total_cells = (long long)B * cells; p.N = anchors;
     return HD_OK;
 }

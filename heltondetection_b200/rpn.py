@@ -156,3 +156,69 @@ class ProposalCreator:
         if return_index:
             return rois[0, :k, 1:], sc[0, :k], idx[0, :k]
         return rois[0, :k, 1:]
+
+
+class RpnProposalsPerLevel:
+    """torchvision RegionProposalNetwork.filter_proposals semantics (models/detection/rpn.py:231-297; SURVEY.md A.3 brackets):
+    top pre_nms_top_n PER LEVEL on the objectness logits -> sigmoid -> clip -> drop boxes smaller than min_size (1e-3) or below
+    score_thresh -> NMS per level (batched_nms with the level as class) -> first post_nms_top_n by score.
+    Composed from the C-ABI entry points on the device, no host sync: hd_rpn_decode (logit keys, dw/dh clamp), one
+    hd_rpn_select_nms per level with an IoU threshold nothing can exceed (= stable top-k + sort), a stable valid-first
+    partition, hd_sort_nms_batched(HD_NMS_CLASS_EXACT).  Returns (rois [B*post,5], count [B], scores [B,post], idx [B,post])."""
+
+    def __init__(self, anchor_bases, strides, img_size, nms_thresh=0.7, pre_nms_top_n=1000, post_nms_top_n=1000, min_size=1e-3,
+                 score_thresh=0.0, clamp_dwh=math.log(1000.0 / 16)):
+        self.dec = RpnProposals(anchor_bases, strides, img_size, nms_thresh, pre_nms_top_n, post_nms_top_n, min_size=-3.0e38,
+                                score_mode="sigmoid", clamp_dwh=clamp_dwh)
+        self.dec.flags |= _lib.RPN_KEY_LOGIT
+        self.nms_thresh, self.pre, self.post = float(nms_thresh), int(pre_nms_top_n), int(post_nms_top_n)
+        self.min_size, self.score_thresh = float(min_size), float(score_thresh)
+
+    def __call__(self, objectness, deltas):
+        boxes, scores, keys = self.dec.decode(objectness, deltas)
+        return self.filter_proposals(boxes, scores, keys, [d.shape[1] // 4 * d.shape[2] * d.shape[3] for d in deltas])
+
+    def filter_proposals(self, boxes, scores, keys, num_anchors_per_level):
+        """stage 2 on the decoded arrays: boxes [B,N,4], scores [B,N] (probabilities), keys [B,N] int32 (sortable logit bits)"""
+        L = _lib.lib()
+        B, N = scores.shape
+        dev = scores.device
+        sel_idx, sel_lvl = [], []
+        off = 0
+        for l, n_l in enumerate(num_anchors_per_level):
+            k_l = min(self.pre, n_l)
+            bl, sl, kl = boxes[:, off:off + n_l].contiguous(), scores[:, off:off + n_l].contiguous(), keys[:, off:off + n_l].contiguous()
+            ws_bytes = L.hd_rpn_select_nms_workspace_size(B, n_l, k_l)
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            rois = torch.empty((B, k_l, 5), dtype=torch.float32, device=dev)
+            idx = torch.empty((B, k_l), dtype=torch.int64, device=dev)
+            cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+            # IoU threshold 2: nothing is ever suppressed -> the call is a stable top-k + sort of the level
+            _lib.check(L.hd_rpn_select_nms(_lib.ptr(bl), _lib.ptr(sl), _lib.ptr(kl), B, n_l, k_l, k_l, 2.0, _lib.ptr(rois), None, _lib.ptr(idx),
+                                           _lib.ptr(cnt), _lib.ptr(ws), ws_bytes, _lib.stream()))
+            sel_idx.append(torch.where(idx >= 0, idx + off, idx))
+            sel_lvl.append(torch.full((B, k_l), l, dtype=torch.int32, device=dev))
+            off += n_l
+        idx = torch.cat(sel_idx, 1)                       # [B,K] flat anchor index or -1, level-major, score-descending inside a level
+        lvl = torch.cat(sel_lvl, 1)
+        K = idx.shape[1]
+        safe = idx.clamp(min=0)
+        cb = torch.gather(boxes, 1, safe[..., None].expand(B, K, 4))
+        cs = torch.gather(scores, 1, safe)
+        valid = (idx >= 0) & ((cb[..., 2] - cb[..., 0]) >= self.min_size) & ((cb[..., 3] - cb[..., 1]) >= self.min_size) & (cs >= self.score_thresh)
+        order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)          # valid candidates first, relative order kept
+        cb = torch.gather(cb, 1, order[..., None].expand(B, K, 4)).contiguous()
+        cs, lvl, idx = torch.gather(cs, 1, order).contiguous(), torch.gather(lvl, 1, order).contiguous(), torch.gather(idx, 1, order)
+        counts = valid.sum(1).to(torch.int32)
+        ws_bytes = L.hd_sort_nms_workspace_size(B, K)
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+        det = torch.zeros((B, self.post, 6), dtype=torch.float32, device=dev)
+        slot = torch.full((B, self.post), -1, dtype=torch.int64, device=dev)
+        cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+        _lib.check(L.hd_sort_nms_batched(_lib.ptr(cb), _lib.ptr(cs), _lib.ptr(lvl), None, _lib.ptr(counts), 0, B, K, self.nms_thresh, _lib.NMS_CLASS_EXACT,
+                                         0.0, 0, self.post, _lib.ptr(det), _lib.ptr(slot), _lib.ptr(cnt), _lib.ptr(ws), ws_bytes, _lib.stream()))
+        live = torch.arange(self.post, device=dev)[None, :] < cnt[:, None]
+        out_idx = torch.where(live, torch.gather(idx, 1, slot.clamp(min=0)), torch.full_like(slot, -1))
+        rois = torch.cat((torch.arange(B, device=dev, dtype=torch.float32)[:, None, None].expand(B, self.post, 1), det[..., :4]), 2)
+        rois = torch.where(live[..., None], rois, torch.cat((rois[..., :1], torch.zeros_like(rois[..., 1:])), 2))
+        return rois.reshape(B * self.post, 5), cnt, torch.where(live, det[..., 4], torch.zeros_like(det[..., 4])), out_idx

@@ -265,6 +265,7 @@ HD_API int hd_match(const float* gt_boxes, const int32_t* gt_count, int B, int G
  * ------------------------------------------------------------------------------------------- */
 #define HD_RPN_SOFTMAX 1   /* 2-channel softmax objectness instead of 1-channel sigmoid */
 #define HD_RPN_CLAMP_DWH 2 /* clamp dw,dh to clamp_dwh before exp (torchvision bbox_xform_clip) */
+#define HD_RPN_KEY_LOGIT 4 /* sigmoid mode: keys[] order the raw logits instead of the probabilities (torchvision's per-level top-k) */
 typedef struct {
     const float* objectness; /* device */
     const float* deltas;     /* device */

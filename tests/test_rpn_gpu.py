@@ -182,3 +182,34 @@ def test_cluster_and_single_cta_kernels_bit_exact(kind, N, n_pre, n_post):
         n = int(outs[2][3][b])
         assert n == ref.numel()
         assert torch.equal(outs[2][2][b, :n], ref)
+
+
+@pytest.mark.parametrize("pre,post", [(1000, 1000), (300, 100), (2000, 50)])
+def test_per_level_topk_variant_matches_torchvision_rpn(pre, post):
+    """torchvision's own RegionProposalNetwork.filter_proposals (rpn.py:231-297) run on CPU on the SAME decoded boxes and raw
+    logits: per-level top-k on the logits, sigmoid, small-box filter, per-level NMS, post top-n.  Proposal indices bit-exact
+    (probabilities that differ by an ulp between CUDA and CPU could only swap exactly tied neighbours)."""
+    from torchvision.models.detection.rpn import RegionProposalNetwork
+    from heltondetection_b200 import rpn, synth
+    B, img = 2, 416
+    obj, dlt, bases, _ = synth.rpn_heads(B, img, G=12, seed=1301)
+    pl = rpn.RpnProposalsPerLevel(bases, (4, 8, 16, 32), (img, img), nms_thresh=0.7, pre_nms_top_n=pre, post_nms_top_n=post)
+    boxes, scores, keys = pl.dec.decode([o.cuda() for o in obj], [d.cuda() for d in dlt])
+    nl = [d.shape[1] // 4 * d.shape[2] * d.shape[3] for d in dlt]
+    rois, cnt, sc, idx = pl.filter_proposals(boxes, scores, keys, nl)
+    rois = rois.view(B, post, 5)
+    logits = torch.cat([o.permute(0, 2, 3, 1).reshape(B, -1) for o in obj], 1)
+    tv = RegionProposalNetwork(None, None, 0.7, 0.3, 256, 0.5, {"training": pre, "testing": pre}, {"training": post, "testing": post}, 0.7, 0.0)
+    tv.eval()
+    ref_boxes, ref_scores = tv.filter_proposals(boxes.cpu(), logits.reshape(-1, 1), [(img, img)] * B, nl)
+    bx = boxes.cpu()
+    for b in range(B):
+        n = int(cnt[b])
+        assert n == ref_boxes[b].shape[0]
+        assert torch.equal(rois[b, :n, 1:].cpu(), ref_boxes[b])
+        assert torch.equal(bx[b][idx[b, :n].cpu()], ref_boxes[b])
+        assert bool(((sc[b, :n].cpu() - ref_scores[b]).abs() <= 1e-6).all())
+        assert bool((idx[b, n:] == -1).all()) and bool((rois[b, n:, 1:] == 0).all())
+    # end to end from the heads (decode + filter in one call) gives the same result
+    r2, c2, s2, i2 = pl([o.cuda() for o in obj], [d.cuda() for d in dlt])
+    assert torch.equal(i2, idx) and torch.equal(c2, cnt)

@@ -114,6 +114,9 @@ def cfg3():
     report("cfg3 rpn decode+select+nms", t, rpn_bytes, B)
     rois, cnt, sc, idx = pr(obj, dlt)
     print("    proposals kept/img:", cnt.tolist())
+    pl = rpn.RpnProposalsPerLevel(bases, (4, 8, 16, 32), (img, img), nms_thresh=0.7, pre_nms_top_n=1000, post_nms_top_n=1000)
+    t = timeit(lambda: pl(obj, dlt), iters=5)
+    report("cfg3 rpn per-level variant (1000/level, torchvision semantics)", t, rpn_bytes, B)
     scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
     fbytes = sum(f.numel() * 4 for f in feats)
     obytes = rois.shape[0] * 256 * 49 * 4
