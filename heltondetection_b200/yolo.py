@@ -209,17 +209,24 @@ def _collect_candidates(buf):
     return out
 
 
-def _slice(det, count, idx=None):
+def _slice(det, count, idx=None, group_by_class=False):
     counts = count.tolist()  # the one host sync of the list-returning drop-in
-    if idx is None:
-        return [det[b, :n] for b, n in enumerate(counts)]
-    return [det[b, :n] for b, n in enumerate(counts)], [idx[b, :n] for b, n in enumerate(counts)]
+    dets = [det[b, :n] for b, n in enumerate(counts)]
+    idxs = None if idx is None else [idx[b, :n] for b, n in enumerate(counts)]
+    if group_by_class:   # lineage (bubbliiiing) order: class by class, score-descending inside a class
+        for b, d in enumerate(dets):
+            o = torch.sort(d[:, 5], stable=True)[1]
+            dets[b] = d[o]
+            if idxs is not None:
+                idxs[b] = idxs[b][o]
+    return dets if idx is None else (dets, idxs)
 
 
-def postprocess(outputs, conf_thres=0.25, iou_thres=0.45, return_index=False, **kw):
-    """Raw heads -> list of [k,6] detections (fast path)."""
+def postprocess(outputs, conf_thres=0.25, iou_thres=0.45, return_index=False, group_by_class=False, **kw):
+    """Raw heads -> list of [k,6] detections (fast path).  group_by_class=True with class_mode="exact", ge=True and a large
+    max_det reproduces the bubbliiiing-lineage output (per-class nms, results concatenated class by class)."""
     det, count, idx = YoloPostprocessor(conf_thres=conf_thres, iou_thres=iou_thres, **kw)(outputs)
-    return _slice(det, count, idx) if return_index else _slice(det, count)
+    return _slice(det, count, idx, group_by_class) if return_index else _slice(det, count, None, group_by_class)
 
 
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000,

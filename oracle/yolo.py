@@ -94,3 +94,23 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, agnostic=Fa
         out.append(x[i])
         out_idx.append(aidx[i])
     return (out, out_idx) if return_index else out
+
+
+def non_max_suppression_per_class(prediction, conf_thres=0.5, nms_thres=0.4):
+    """bubbliiiing-lineage form of A.2 (yolov5-v6.1-pytorch DecodeBox.non_max_suppression): keep conf >= conf_thres, then a Python
+    loop over the unique class ids (ascending), nms per class, results concatenated class by class (no max_det cut)."""
+    import torchvision
+    prediction = prediction.detach().cpu().float()
+    out = []
+    for xi in range(prediction.shape[0]):
+        x, _ = filter_candidates(prediction[xi], conf_thres, ge=True)
+        if x.shape[0] == 0:
+            out.append(x.new_zeros((0, 6)))
+            continue
+        rows = []
+        for c in x[:, 5].unique():
+            d = x[x[:, 5] == c]
+            keep = torchvision.ops.nms(d[:, :4], d[:, 4], nms_thres)
+            rows.append(d[keep])
+        out.append(torch.cat(rows, 0))
+    return out

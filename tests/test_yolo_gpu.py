@@ -188,3 +188,16 @@ def test_channels_last_heads_give_the_same_detections(dense, nc, img):
     for k in range(3):
         n = int(c1[k])
         assert torch.equal(d1[k, :n], d2[k, :n]) and torch.equal(i1[k, :n], i2[k, :n]) and torch.equal(i2[k, :n].cpu(), ridx[k])
+
+
+def test_bubbliiiing_per_class_output_order():
+    """lineage variant of A.2: conf >= thr, nms per class, detections concatenated class by class"""
+    import oracle
+    from heltondetection_b200 import synth, yolo
+    heads, _ = synth.yolo_heads(2, 320, 20, 14, 55)
+    ref = oracle.yolo.non_max_suppression_per_class(oracle.yolo.decode_box(heads), 0.5, 0.4)
+    got = yolo.postprocess([h.cuda() for h in heads], 0.5, 0.4, group_by_class=True, class_mode="exact", ge=True, max_det=4096)
+    for b in range(2):
+        assert got[b].shape == ref[b].shape
+        assert torch.equal(got[b][:, 5].cpu(), ref[b][:, 5])
+        assert torch.allclose(got[b].cpu(), ref[b], rtol=1e-5, atol=1e-3)
