@@ -38,6 +38,22 @@ def test_argument_errors_come_back_as_codes_with_text():
     assert L.hd_sort_nms_workspace_size(4, 1000) > 4 * 1000 * 44
     with pytest.raises(RuntimeError):
         _lib.check(-1)
+    # entry points added for the rows next to the path
+    w = (ctypes.c_float * 4)(10.0, 10.0, 5.0, 5.0)
+    assert L.hd_roi_head_postprocess(None, None, None, None, 2, 10, 1, w, 0, 0.0, 100.0, 100.0, 0.05, 0.01, 0.5, 10, None, None, None, None, 0, None) == -1
+    assert b"n_class" in L.hd_last_error()
+    assert L.hd_roi_head_postprocess(None, None, None, None, 2, 10, 5, w, 0, 0.0, 100.0, 100.0, 0.05, 0.01, 0.5, 10, None, None, None, None, 0, None) == -3
+    assert L.hd_roi_head_postprocess_workspace_size(2, 10, 5) > 2 * 10 * 4 * 28
+    assert L.hd_match(None, None, 1, 4, None, 0, 8, 0.3, 0.7, 0, None, None, None, 0, None) == -1
+    assert b"low_threshold" in L.hd_last_error()
+    assert L.hd_match(None, None, 1, 0, None, 0, 8, 0.7, 0.3, 0, None, None, None, 0, None) == -1
+    assert b"ground-truth" in L.hd_last_error()
+    assert L.hd_box_encode(None, 1, 4, None, None, 0, 8, w, None, None) == -1
+    assert L.hd_scale_detections(None, None, -1, 4, None, 0, None, None) == -1
+    assert L.hd_roi_align_backward(None, None, None, 4, None, 1, 0, 8, 7, 7, 2, 0, None) == -1
+    assert L.hd_roi_pool_backward(None, None, None, 4, None, 7, 8, 4, 4, 7, 7, None) == -1
+    assert L.hd_rpn_cluster_capacity(3) == -1
+    assert L.hd_nms_set_mode(0) in (0, 1, 2) and L.hd_rpn_set_mode(0) in (0, 1, 2) and L.hd_roi_set_mode(0) >= 0
 
 
 def test_cpu_tensors_are_refused():
