@@ -339,18 +339,20 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
-// select + sort + NMS spread over a thread-block CLUSTER: 8 CTAs (8 SMs) per image instead of one.
-//   S. radix select of the k-th largest 32-bit score key: every CTA histograms its 1/8 slice of the keys (held in
-//      shared memory after one global read), the 8 histograms are summed through distributed shared memory (DSMEM);
-//      ties on the threshold key go to the lowest indices (stable-sort rule) by giving each CTA a quota of them.
+// select + sort + NMS spread over a thread-block CLUSTER: CL = 1, 2, 4 or 8 CTAs (SMs) per image, chosen per launch from the
+// batch size and the number of clusters the device holds at once (15 of 8, 33 of 4, 74 of 2 on a B200).
+//   S. radix select of the k-th largest 32-bit score key: every CTA histograms its 1/CL slice of the keys (held in
+//      shared memory after one global read), the histograms are summed through distributed shared memory (DSMEM), the
+//      digit is picked by a parallel suffix scan; ties on the threshold key go to the lowest indices (stable-sort rule) by
+//      giving each CTA a quota of them.
 //   C. ordered compaction of the selected set (index order kept) as unique composites (~key << 32 | index).
-//   M. each CTA bitonic-sorts an even 1/8 slice of the composites in registers/shared memory; the final rank of an
-//      element is the sum of its lower bounds in the 8 sorted slices (binary searches in a shared-memory copy).
-//   N. greedy NMS as a DAG problem: the spatial hash of hd_nms_core.cuh is built cooperatively (per-CTA bucket
-//      counts combined over DSMEM), every CTA then lists, for its boxes j, the higher-ranked boxes i with
-//      IoU(i,j) > thr (<= RPNC_ADJ of them, else the image is flagged for the single-CTA kernel), and CTA 0
-//      resolves  kept[j] = !any(kept[i], i in adj[j])  1024 ranks at a time by Jacobi iteration to the unique
-//      fixed point (= the greedy answer), stopping at n_post keeps.
+//   M. each CTA bitonic-sorts an even 1/CL slice of the composites in registers/shared memory; the final rank of an
+//      element is the sum of its lower bounds in all sorted slices (binary searches in a shared-memory copy).
+//   N. greedy NMS as a DAG problem (hd_cluster_nms.cuh): a size-stratified spatial hash is built cooperatively (per-CTA
+//      bucket counts combined over DSMEM), every CTA lists, for its boxes j, the higher-ranked boxes i with IoU(i,j) > thr
+//      (<= RPNC_ADJ of them, else the image is flagged for the single-CTA kernel), and CTA 0 resolves
+//      kept[j] = !any(kept[i], i in adj[j])  1024 ranks at a time by Jacobi iteration to the unique fixed point (= the
+//      greedy answer); ranks are taken in doubling batches and the loop stops at n_post keeps.
 // Bit-identical outputs to rpn_select_nms_kernel (same selection rule, same IoU predicate).
 // ------------------------------------------------------------------------------------------------
 struct RpnClParams {
