@@ -2,11 +2,16 @@
 """bench.py -- post-process images/sec of the YOLOv5 decode+filter+NMS hot path (BASELINE.json configs[1]:
 YOLOv5s 640x640, batch 256, 80 classes, 25 200 anchors, image-sharded over N GPUs).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode dense|sparse]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling strong|weak] [--depth D] [--no-configs]
 
-One "step" = one pass of the hot path over one batch of 256 synthetic images per rank (weak scaling:
-every rank owns its own 256-image shard; at N>1 the step ends with the NCCL all-gather of the padded
-per-image detections).  Rank 0 prints ONE JSON line.
+One "step" = one pass of the hot path over one global batch of 256 synthetic images.  With N ranks the batch is SHARDED
+(strong scaling, BASELINE configs[1] / SURVEY.md 8e: 256 images -> 256/N per rank, 32 at N=8): every rank runs the fused
+decode+filter kernel and the NMS kernels on its slice, and the NMS kernels store the kept rows into every rank's gather buffer
+over NVLink (the all-gather fused into the kernel epilogue; one cross-GPU barrier per step).  Steps are software-pipelined
+D deep over CUDA streams (yolo.PostprocessPipeline): the NMS of step k overlaps the HBM-bound decode of step k+1.  Every rank
+rotates through a pool of N distinct shard inputs (2.19 GB per rank at every N), so the cache behaviour does not change with N.
+`--scaling weak` keeps the round-1 behaviour (256 images per rank).  Rank 0 prints ONE JSON line; at N=1 it also carries a
+`configs` object with device-timed lines for BASELINE configs 1, 3, 4, 5 (L2 flushed between iterations).
 """
 import argparse
 import json
@@ -23,7 +28,7 @@ sys.path.insert(0, ROOT)
 IMG, NC, G, BATCH = 640, 80, 20, 256
 CONF, IOU, MAX_DET = 0.25, 0.45, 300
 BYTES_PER_IMG = 25200 * 85 * 4  # 8 568 000 B: every head element once
-WORKLOAD = "cfg2: YOLOv5s 640x640 batch 256/GPU nc=80 25200 anchors decode+conf-filter+class-aware NMS"
+WORKLOAD = "cfg2: YOLOv5s 640x640 global batch 256 nc=80 25200 anchors decode+conf-filter+class-aware NMS"
 
 
 def parse():
@@ -34,9 +39,13 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="dense", choices=["dense", "sparse"],
                     help="dense: every head byte is read (roofline-honest headline); sparse: objectness-tile skip")
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the global batch is sharded over the ranks (the contracted config); weak: --batch images per rank")
+    ap.add_argument("--depth", type=int, default=2, help="software-pipeline depth (CUDA streams)")
+    ap.add_argument("--batch", type=int, default=BATCH, help="global batch (strong) / per-rank batch (weak)")
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-sample", type=int, default=32)
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg1/3/4/5 lines (they are only produced at N=1)")
     return ap.parse_args()
 
 
@@ -90,20 +99,23 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------------------------------------ CPU reference legs
+def _best(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
 def cpu_reference_rate(heads_cpu, n_img, repeats=3):
     """The oracle (torch CPU + torchvision CPU ops, the reference's CPU path) on n_img images."""
-    import torch
     import oracle
     sub = [h[:n_img] for h in heads_cpu]
-    best = float("inf")
-    for it in range(repeats + 1):
-        t0 = time.perf_counter()
-        pred = oracle.yolo.decode_box(sub)
-        oracle.yolo.non_max_suppression(pred, CONF, IOU, max_det=MAX_DET)
-        dt = time.perf_counter() - t0
-        if it > 0:
-            best = min(best, dt)
-    return n_img / best
+    return n_img / _best(lambda: oracle.yolo.non_max_suppression(oracle.yolo.decode_box(sub), CONF, IOU, max_det=MAX_DET), repeats)
 
 
 def run_reference(args, rank):
@@ -115,7 +127,7 @@ def run_reference(args, rank):
     n = min(args.cpu_sample, args.batch)
     heads, _ = synth.yolo_heads(n, IMG, NC, G, 1235)
     import oracle
-    for _ in range(max(args.warmup, 1) if args.warmup < 3 else 3):
+    for _ in range(3):
         oracle.yolo.non_max_suppression(oracle.yolo.decode_box(heads), CONF, IOU, max_det=MAX_DET)
     steps = min(args.steps, 20)
     t0 = time.perf_counter()
@@ -126,7 +138,7 @@ def run_reference(args, rank):
     sample = f"{n} images/step x {steps} steps of the same synthetic workload (oracle = torch CPU + torchvision CPU ops)"
     print(json.dumps({
         "impl": "reference", "metric": "post-process images/sec", "value": v, "unit": "img/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 3, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": 3, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": v, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
@@ -134,6 +146,162 @@ def run_reference(args, rank):
     }), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ cfg1/3/4/5 lines (N=1)
+class Flusher:
+    """writes a buffer larger than the 126 MB L2 between timed iterations"""
+
+    def __init__(self, dev, mb=256):
+        import torch
+        self.buf = torch.empty((mb << 20,), dtype=torch.uint8, device=dev)
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def time_flushed(fn, flush, iters=20, warm=3):
+    """average device time of fn() over `iters` iterations, L2 flushed before each one (flush not timed) -> ms"""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in evs:
+        flush()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / iters
+
+
+def roof(nbytes, ms, peak):
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "algorithmic_bytes_per_step": nbytes}
+
+
+def extra_configs(dev, peak, cpu_cores):
+    """Device-timed lines for BASELINE configs 1, 3, 4, 5 (one GPU), each with its roofline fraction (algorithmic bytes of SURVEY.md 8d
+    over the measured step), a bounded CPU sample of the same workload through the oracle, and -- for nms / roi_align -- the
+    torchvision CUDA kernels on the same inputs on the same box."""
+    import numpy as np
+    import torch
+    import oracle
+    from heltondetection_b200 import synth, yolo, rpn, roi, wbf
+    out = {}
+    flush = Flusher(dev)
+    torch.set_num_threads(cpu_cores)
+
+    def yolo_line(B, img, nc, Gn, seed, conf, iou, dense_scene, cpu_n, iters):
+        heads_cpu, _ = synth.yolo_heads(B, img, nc, Gn, seed, dense=dense_scene)
+        heads = [h.to(dev) for h in heads_cpu]
+        nbytes = sum(h.numel() * 4 for h in heads)
+        pp = yolo.YoloPostprocessor(conf_thres=conf, iou_thres=iou, max_det=MAX_DET, dense_read=True, device=dev)
+        rp, det, cnt, idx = pp.graph(heads)
+        ms = time_flushed(rp, flush, iters)
+        sub = [h[:cpu_n] for h in heads_cpu]
+        cpu_t = _best(lambda: oracle.yolo.non_max_suppression(oracle.yolo.decode_box(sub), conf, iou, max_det=MAX_DET), 2)
+        ref = oracle.yolo.non_max_suppression(oracle.yolo.decode_box(sub), conf, iou, max_det=MAX_DET, return_index=True)[1]
+        got = [idx[b, :int(cnt[b])].cpu() for b in range(cpu_n)]
+        line = {"ms": ms, "img_s": B / ms * 1e3, "roofline": roof(nbytes, ms, peak), "batch": B,
+                "candidates_per_img": None, "kept_per_img": float(cnt.float().mean()),
+                "keep_indices_match_oracle": bool(all(torch.equal(a, b) for a, b in zip(got, ref))),
+                "cpu_baseline": {"value": cpu_n / cpu_t, "unit": "img/s", "cores": cpu_cores, "kind": "port", "sample": f"{cpu_n} images of the batch, best of 2"}}
+        del heads
+        return line
+
+    # cfg1: the reference's own CPU-runnable case, one image; both thresholds of SURVEY.md 8d
+    out["cfg1_conf0.25"] = yolo_line(1, 640, 80, 20, 1234, 0.25, 0.45, False, 1, 50)
+    out["cfg1_conf0.001"] = yolo_line(1, 640, 80, 20, 1234, 0.001, 0.45, False, 1, 50)
+    out["cfg1_conf0.25"]["workload"] = out["cfg1_conf0.001"]["workload"] = "cfg1: YOLOv5s 640x640 batch 1 nc=80 decode+filter+NMS (latency-bound: one image is 8.6 MB)"
+    # cfg4: dense VisDrone-style scenes
+    out["cfg4"] = yolo_line(64, 1280, 10, 300, 1238, 0.001, 0.6, True, 2, 20)
+    out["cfg4"]["workload"] = "cfg4: YOLOv5l 1280x1280 batch 64 nc=10 dense scenes conf 0.001 iou 0.6 (NMS-bound, ~6.8k candidates/img)"
+
+    # cfg3: RPN proposals + multi-level RoIAlign
+    B, img = 16, 832
+    obj_c, dlt_c, bases, _ = synth.rpn_heads(B, img, G=20, seed=1237)
+    feats_c = synth.fpn_features(B, img, 256, 1237)
+    obj, dlt = [o.to(dev) for o in obj_c], [d.to(dev) for d in dlt_c]
+    nhwc = [f.to(dev).contiguous(memory_format=torch.channels_last) for f in feats_c]
+    scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
+    pr = rpn.RpnProposals(bases, (4, 8, 16, 32), (img, img), n_pre_nms=12000, n_post_nms=2000, min_size=16)
+    rois, cnt, sc, idx = pr(obj, dlt)
+    rpn_bytes = sum(o.numel() * 4 for o in obj) + sum(d.numel() * 4 for d in dlt)
+    fbytes = sum(f.numel() * 4 for f in nhwc)
+    obytes = rois.shape[0] * 256 * 49 * 4
+    t_rpn = time_flushed(lambda: pr(obj, dlt), flush, 10)
+    t_roi = time_flushed(lambda: roi.multilevel_roi_align(nhwc, rois, 7, scales, 2, False), flush, 10)
+    t_roi0 = time_flushed(lambda: roi.multilevel_roi_align(nhwc, rois, 7, scales, 0, False), flush, 5)
+    t_pool = time_flushed(lambda: roi.multilevel_roi_align(nhwc, rois, 7, scales, 2, False, op="pool"), flush, 5)
+    t_both = time_flushed(lambda: (pr(obj, dlt), roi.multilevel_roi_align(nhwc, rois, 7, scales, 2, False)), flush, 10)
+    cpu_rpn = _best(lambda: oracle.rpn.rpn_proposals([o[:1] for o in obj_c], [d[:1] for d in dlt_c], bases, (4, 8, 16, 32), (img, img),
+                                                     n_pre_nms=12000, n_post_nms=2000, min_size=16), 1)
+    r0 = rois[:2000].cpu()
+    cpu_roi = _best(lambda: oracle.roi.multilevel_roi_align([f[:1] for f in feats_c], r0, 7, scales, 2, False), 1)
+    line = {"workload": "cfg3: FasterRCNN-PAFPN 832x832 batch 16: RPN decode + top-12000 + NMS 0.7 + top-2000, then multi-level RoIAlign 7x7x256 (sr=2, NHWC features)",
+            "ms": t_both, "img_s": B / t_both * 1e3, "roofline": roof(rpn_bytes + fbytes + obytes + rois.numel() * 4, t_both, peak),
+            "rpn_ms": t_rpn, "roi_align_ms": t_roi, "roi_align_roofline": roof(fbytes + obytes, t_roi, peak),
+            "roi_align_adaptive_sr0_ms": t_roi0, "roi_pool_ms": t_pool, "proposals_per_img": int(cnt.float().mean()),
+            "cpu_baseline": {"value": 1.0 / (cpu_rpn + cpu_roi), "unit": "img/s", "cores": cpu_cores, "kind": "port",
+                             "sample": "1 image: oracle RPN proposals + torchvision CPU multi-level roi_align, best of 1 after 1 warm-up"}}
+    try:   # the torchvision sm_100 kernels on the same inputs, same box (comparison only; never on the product path)
+        import torchvision
+        lv1 = rois[(roi.level_map(rois[:, 1:]) == 1)][:4000].contiguous()
+        if lv1.shape[0] < 64:
+            lv1 = rois[:4000]
+        nchw1 = nhwc[1].contiguous()
+        t_tv = time_flushed(lambda: torchvision.ops.roi_align(nchw1, lv1, 7, 1 / 8, 2, False), flush, 5)
+        t_hd = time_flushed(lambda: roi.roi_align(nhwc[1], lv1, 7, 1 / 8, 2, False), flush, 5)
+        bx = rois[:12000, 1:].contiguous()
+        ss = torch.rand(12000, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+        from heltondetection_b200 import ops
+        t_tvn = time_flushed(lambda: torchvision.ops.nms(bx, ss, 0.7), flush, 5)
+        t_hdn = time_flushed(lambda: ops.nms(bx, ss, 0.7), flush, 5)
+        same = bool(torch.equal(torchvision.ops.nms(bx, ss, 0.7), ops.nms(bx, ss, 0.7)))
+        line["torchvision_cuda_same_box"] = {"roi_align_ms": {"torchvision": t_tv, "hd_b200": t_hd, "rois": int(lv1.shape[0])},
+                                             "nms_n12000_ms": {"torchvision": t_tvn, "hd_b200": t_hdn, "keep_equal": same}}
+    except Exception as e:  # noqa: BLE001
+        line["torchvision_cuda_same_box"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    out["cfg3"] = line
+    del obj, dlt, nhwc
+
+    # cfg5: TTA (3 scales x {id, hflip}) + WBF
+    B = 64
+    views, _ = synth.tta_heads(B, 640, 80, G=20, seed=1239)
+    vspec = [(r, flip, size) for (_, r, flip, size) in views]
+    devh = [[h.to(dev) for h in heads] for (heads, _, _, _) in views]
+    fusion = wbf.TTAFusion(vspec, (640, 640), 80, max_det=MAX_DET, iou_thr=0.55, skip_box_thr=0.001)
+    pps = [yolo.YoloPostprocessor(conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=True, device=dev) for _ in views]
+
+    def full():
+        for v in range(len(views)):
+            det, c, _ = pps[v](devh[v])
+            fusion.map_back(v, det, c)
+        return fusion.fuse()
+    nbytes = sum(h.numel() * 4 for d in devh for h in d)
+    t_full = time_flushed(full, flush, 10)
+    full()
+    t_wbf = time_flushed(lambda: fusion.fuse(), flush, 10)
+
+    def tta_cpu():
+        for b in range(2):
+            bl, sl, ll = [], [], []
+            for (hh, rr, ff, ss_) in views:
+                d = oracle.yolo.non_max_suppression(oracle.yolo.decode_box([x[b:b + 1] for x in hh]), CONF, IOU)[0]
+                bb, s_, lb = oracle.tta.map_back(d, rr, ff, float(ss_), 640.0, 640.0)
+                bl.append(bb.numpy()); sl.append(s_.numpy()); ll.append(lb.numpy())
+            oracle.wbf.weighted_boxes_fusion(bl, sl, ll, None, 0.55, 0.001)
+    cpu_t = _best(tta_cpu, 1)
+    out["cfg5"] = {"workload": "cfg5: YOLOv5s TTA 6 views (544/640/768 x {id,hflip}) batch 64: 6x(decode+filter+NMS) + map-back + Weighted Boxes Fusion",
+                   "ms": t_full, "img_s": B / t_full * 1e3, "roofline": roof(nbytes, t_full, peak), "wbf_alone_ms": t_wbf,
+                   "fused_per_img": float(fusion.wbf.oc.float().mean()),
+                   "cpu_baseline": {"value": 2 / cpu_t, "unit": "img/s", "cores": cpu_cores, "kind": "port", "sample": "2 images x 6 views, best of 1 after 1 warm-up"}}
+    out["timing"] = "CUDA events around every iteration, a 256 MB buffer written between iterations (L2 flush, not timed)"
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ main arm
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -149,170 +317,190 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = hd_dist.bind_to_gpu_numa(local) if world > 1 else None   # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
-    torch.set_num_threads(max(1, (os.cpu_count() or 8) // max(world, 1)))
-    heads_cpu, _ = synth.yolo_heads(B, IMG, NC, G, 1235 + rank)
-    heads = [h.to(dev) for h in heads_cpu]
-    pp = yolo.YoloPostprocessor(conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=(args.mode == "dense"), device=dev)
-    # multi-GPU: the NMS kernels store every kept row into every rank's gather buffer (symmetric memory, posted NVLink
-    # stores) -- the all-gather is fused into the kernel epilogue; a cross-GPU barrier per step runs on a side stream.
+    strong = args.scaling == "strong"
+    if strong and args.batch % world:
+        raise SystemExit(f"--batch {args.batch} must be divisible by the number of ranks ({world}) for equal shards")
+    Bl = args.batch // world if strong else args.batch          # images this rank processes per step
+    imgs_per_step = args.batch if strong else args.batch * world
+    torch.set_num_threads(max(1, (len(os.sched_getaffinity(0)) or 8) // (1 if numa is not None else max(world, 1))))
+    heads_cpu, _ = synth.yolo_heads(args.batch, IMG, NC, G, 1235 + (0 if strong else rank))
+    if strong:      # pool slot j holds the shard of rank (rank + j) % world: slot 0 is this rank's own slice of the global batch
+        shards = [hd_dist.shard_slice(args.batch, (rank + j) % world, world) for j in range(world)]
+        pool_cpu = [[h[s] for h in heads_cpu] for s in shards]
+    else:
+        pool_cpu = [heads_cpu]
+    pool = [[h.to(dev) for h in hs] for hs in pool_cpu]
+    dense = args.mode == "dense"
+    depth = max(1, args.depth)
+
+    # multi-GPU: the NMS kernels store every kept row into every rank's gather buffer (symmetric memory, posted NVLink stores) --
+    # the all-gather is fused into the kernel epilogue; one cross-GPU barrier per step on the step's stream.
     # Fallback if symmetric memory is unavailable: pack + NCCL all_gather_into_tensor on a side stream.
-    gather, peer, gather_mode = None, None, "none"
+    gather, peer, gather_mode, gather_parity = None, None, "none", None
     if world > 1:
         try:
-            peer = hd_dist.PeerDetectionBuffers(B, MAX_DET, dev)
+            peer = hd_dist.PeerDetectionBuffers(Bl, MAX_DET, dev, slots=depth)
             gather_mode = "fused: NMS kernels write into every peer's gather buffer over NVLink (symmetric memory) + per-step device barrier"
         except Exception as e:  # noqa: BLE001
             peer = None
-            gather = hd_dist.DetectionGather(B, MAX_DET, dev)
+            gather = hd_dist.DetectionGather(Bl, MAX_DET, dev)
             gather_mode = f"NCCL all_gather of padded detections on a side stream (symmetric memory unavailable: {type(e).__name__})"
-
-    # the step is ONE C-ABI call (decode+filter kernel, small-image NMS kernel, large-image pass), captured once in a CUDA graph
-    if peer is not None:
-        replays = [pp.graph(heads, peer=peer, slot=s_)[0:3] for s_ in (0, 1)]
-        side = torch.cuda.Stream(dev)
-        ev_step = torch.cuda.Event()
-    else:
-        replays = [pp.graph(heads)[0:3]]
+    pipe = yolo.PostprocessPipeline(pool, depth=depth, peer=peer, device=dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=dense)
 
     def run_step(k):
-        replay, det, cnt = replays[k % len(replays)]
-        replay()
-        if peer is not None:
-            ev_step.record()
-            with torch.cuda.stream(side):
-                side.wait_event(ev_step)
-                peer.barrier()                # all ranks' stores of this step have landed; overlaps the next replay
-        elif gather is not None:
-            gather(det, cnt)                  # side stream: overlaps the next replay
+        det, cnt, _ = pipe.step(k)
+        if gather is not None:
+            with torch.cuda.stream(pipe.stream_of(k)):
+                gather(det, cnt)
 
     def join():
-        if peer is not None:
-            torch.cuda.current_stream().wait_stream(side)
-        elif gather is not None:
+        pipe.join()
+        if gather is not None:
             gather.finish()
+
+    if peer is not None:
+        # one step through the fused gather, compared with pack + NCCL all_gather of the same detections
+        pipe.fork(); pipe.step(0); pipe.join()
+        torch.cuda.synchronize()
+        det_l, cnt_l = peer.local(0)
+        ref = hd_dist.DetectionGather(Bl, MAX_DET, dev)
+        slot = ref(det_l.contiguous(), cnt_l.contiguous())
+        ref_det, ref_cnt = ref.result(slot)
+        torch.cuda.synchronize()
+        got_det, got_cnt = peer.gathered(0)
+        ok = torch.tensor([int(torch.equal(got_det, ref_det.reshape(got_det.shape)) and torch.equal(got_cnt, ref_cnt))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gather_parity = bool(ok.item())
 
     sampler = ClockSampler(local)
     sampler.start()
-    for k in range(max(args.warmup, 3)):
+    W = max(args.warmup, 3)
+    pipe.fork()
+    for k in range(W):
         run_step(k)
     join()
     torch.cuda.synchronize()
-    # ---------------- timed region: K steps, device-resident inputs (2.19 GB/rank >> 126 MB L2)
+    # ---------------- timed region: K pipelined steps, device-resident inputs (2.19 GB pool per rank >> 126 MB L2)
     K = args.steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    ev_end = torch.cuda.Event(enable_timing=True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     sampler.recording = True
+    ev0.record()
+    pipe.fork()
     for k in range(K):
-        replay, det, cnt = replays[k % len(replays)]
-        ev[k][0].record()
-        replay()
-        ev[k][1].record()
-        if peer is not None:
-            ev_step.record()
-            with torch.cuda.stream(side):
-                side.wait_event(ev_step)
-                peer.barrier()
-        elif gather is not None:
-            gather(det, cnt)
-    join()                                    # every gather completes inside the timed region
-    ev_end.record()
+        run_step(k)
+    join()                                    # every step (and its gather) completes inside the timed region
+    ev1.record()
     torch.cuda.synchronize()
     sampler.recording = False
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
-    total_ms = ev[0][0].elapsed_time(ev_end)
-    # dominant kernel = yolo_decode_filter_kernel (~95% of the step); the event bracket is the whole C-ABI call (memset +
-    # decode + NMS kernels), so the roofline figure is conservative
-    decode_ms = sum(a.elapsed_time(b) for a, b in ev) / K
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * B * K / (total_ms * 1e-3)
+    value = imgs_per_step * K / (total_ms * 1e-3)
 
-    # ---------------- e2e: public API with HOST (pinned) inputs; host<->device traffic inside the timed region
-    pinned = [h.pin_memory() for h in heads_cpu]
-    stage = [torch.empty_like(h, device=dev) for h in heads_cpu]
-    det_h = torch.empty((B, MAX_DET, 6), dtype=torch.float32).pin_memory()
-    cnt_h = torch.empty((B,), dtype=torch.int32).pin_memory()
-    pp_copy = yolo.YoloPostprocessor(conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=False, device=dev)
-    pp_zc = yolo.YoloPostprocessor(conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=False, device=dev)
+    # un-pipelined step time on one stream (explains the pipelined figure; not the headline)
+    ks = min(K, 50)
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    es0.record()
+    for k in range(ks):
+        pipe.replays[k % pipe.n_graphs]()
+    es1.record()
+    torch.cuda.synchronize()
+    serial_ms = es0.elapsed_time(es1) / ks
 
-    e2e_gather = hd_dist.DetectionGather(B, MAX_DET, dev) if world > 1 else None
+    # ---------------- e2e: public API with HOST (pinned) inputs; host<->device traffic inside the timed region, every step
+    own_cpu = pool_cpu[0]
+    pinned = [h.contiguous().pin_memory() for h in own_cpu]
+    det_h = [torch.empty((Bl, MAX_DET, 6), dtype=torch.float32).pin_memory() for _ in range(depth)]
+    cnt_h = [torch.empty((Bl,), dtype=torch.int32).pin_memory() for _ in range(depth)]
+    stages = [[torch.empty_like(h, device=dev) for h in own_cpu] for _ in range(depth)]
+    pipe_copy = yolo.PostprocessPipeline(stages, depth=depth, peer=peer, device=dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=False)
+    e2e_steps = max(args.e2e_steps, 2) * (world if strong else 1)
 
-    def finish(det, cnt):
-        if e2e_gather is not None:
-            e2e_gather(det, cnt)
-            e2e_gather.finish()
-        det_h.copy_(det, non_blocking=True)
-        cnt_h.copy_(cnt, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    def e2e_loop(p, h2d):
+        p.fork()
+        for k in range(e2e_steps):
+            s = p.stream_of(k)
+            if h2d:
+                with torch.cuda.stream(s):
+                    for s_, p_ in zip(stages[k % depth], pinned):
+                        s_.copy_(p_, non_blocking=True)
+            det, cnt, _ = p.step(k)
+            with torch.cuda.stream(s):
+                det_h[k % depth].copy_(det, non_blocking=True)
+                cnt_h[k % depth].copy_(cnt, non_blocking=True)
+        p.join()
+        torch.cuda.synchronize()
 
-    def e2e_copy():      # (a) explicit H2D of the whole head tensors, then the device path
-        for s_, p_ in zip(stage, pinned):
-            s_.copy_(p_, non_blocking=True)
-        finish(*pp_copy(stage)[:2])
-
-    def e2e_zero_copy():  # (b) the kernel reads the pinned host tensors itself (UVA): only surviving tiles cross PCIe
-        finish(*pp_zc(pinned)[:2])
-
-    def time_e2e(fn):
-        fn()
+    def time_e2e(p, h2d):
+        e2e_loop(p, h2d)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            fn()
-        torch.cuda.synchronize()
+        e2e_loop(p, h2d)
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        return world * B * args.e2e_steps / float(te.item())
+        return imgs_per_step * e2e_steps / float(te.item())
 
-    e2e_a = time_e2e(e2e_copy)
-    det_a = det_h.clone()
+    e2e_a = time_e2e(pipe_copy, True)
+    det_a, cnt_a = det_h[0].clone(), cnt_h[0].clone()
     try:
-        e2e_b = time_e2e(e2e_zero_copy)
-        zc_ok = bool(torch.equal(det_a, det_h))
+        pipe_zc = yolo.PostprocessPipeline([pinned], depth=depth, peer=peer, device=dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=False)
+        e2e_b = time_e2e(pipe_zc, False)
+        zc_ok = bool(torch.equal(det_a, det_h[0]) and torch.equal(cnt_a, cnt_h[0]))
     except RuntimeError:
         e2e_b, zc_ok = 0.0, False
-    full_bytes = sum(h.numel() * 4 for h in heads_cpu)
+    full_bytes = sum(h.numel() * 4 for h in own_cpu) * world
     gate = math.log(CONF / (1 - CONF)) - 0.01
     zc_bytes = 0
-    for h in heads_cpu:                      # bytes the zero-copy kernel pulls: objectness planes + surviving 128-cell tiles
-        Bn, Ctot, H, W = h.shape
-        o = h.view(Bn, 3, Ctot // 3, H * W)[:, :, 4]
+    for h in own_cpu:                        # bytes the zero-copy kernel pulls: objectness planes + surviving 32-byte sectors
+        Bn, Ctot, H, Wd = h.shape
+        o = h.reshape(Bn, 3, Ctot // 3, H * Wd)[:, :, 4]
         pad = (-o.shape[-1]) % 8
         o = torch.nn.functional.pad(o, (0, pad), value=-100.0).view(Bn, 3, -1, 8)
         alive = (o > gate).any(-1)           # 32-byte sectors (8 cells) that hold a possible survivor
-        zc_bytes += h.shape[0] * 3 * H * W * 4 + int(alive.sum()) * (Ctot // 3 - 1) * 32
-    d2h = det_h.numel() * 4 + cnt_h.numel() * 4
-    if e2e_b > e2e_a and zc_ok:
-        e2e_val, h2d, e2e_path = e2e_b, zc_bytes, "zero-copy: kernel reads pinned host tensors over PCIe (objectness planes + 32 B sectors of possible survivors)"
-    else:
-        e2e_val, h2d, e2e_path = e2e_a, full_bytes, "cudaMemcpyAsync of the full head tensors, then device path"
+        zc_bytes += h.shape[0] * 3 * H * Wd * 4 + int(alive.sum()) * (Ctot // 3 - 1) * 32
+    zc_bytes *= world                        # all ranks (shards are statistically alike)
+    d2h = (det_h[0].numel() * 4 + cnt_h[0].numel() * 4) * world
+    e2e_zero = {"value": e2e_b, "unit": "img/s", "h2d_bytes_per_step": zc_bytes, "d2h_bytes_per_step": d2h, "matches_full_copy": zc_ok,
+                "path": "zero-copy: the decode kernel reads the pinned host tensors over PCIe (objectness planes + 32 B sectors of possible survivors)"}
+    e2e_full = {"value": e2e_a, "unit": "img/s", "h2d_bytes_per_step": full_bytes, "d2h_bytes_per_step": d2h,
+                "path": "cudaMemcpyAsync of the full head tensors from pinned memory, then the device path"}
+    e2e = dict(e2e_zero if (e2e_b > e2e_a and zc_ok) else e2e_full)
+    e2e["pipelined_steps"] = depth
 
-    # ---------------- sparse (objectness-tile skip) variant, reported beside the dense headline
-    extra = {"e2e_full_copy_value": e2e_a, "e2e_zero_copy_value": e2e_b, "e2e_zero_copy_matches": zc_ok}
-    if args.mode == "dense":
-        pps = yolo.YoloPostprocessor(conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=False, device=dev)
-        replay_s = pps.graph(heads)[0]
+    extra = {"e2e_zero_copy": e2e_zero, "e2e_full_copy": e2e_full, "step_ms_serial": serial_ms, "numa_node": numa}
+    if dense:   # sparse (objectness-tile skip) variant, reported beside the dense headline
+        pps = yolo.PostprocessPipeline(pool, depth=depth, peer=None, device=dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=False)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pps.fork()
+        for k in range(5):
+            pps.step(k)
+        pps.join()
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(K):
-            replay_s()
+        pps.fork()
+        for k in range(K):
+            pps.step(k)
+        pps.join()
         e1.record()
         torch.cuda.synchronize()
-        extra["sparse_skip_value"] = B * K / (e0.elapsed_time(e1) * 1e-3) * world
+        ts = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        extra["sparse_skip_value"] = imgs_per_step * K / (float(ts.item()) * 1e-3)
 
     if rank == 0:
         peaks = {}
@@ -322,31 +510,48 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        achieved = BYTES_PER_IMG * B / (decode_ms * 1e-3) / 1e9
+        achieved = BYTES_PER_IMG * Bl * K / (total_ms * 1e-3) / 1e9       # per GPU, over the whole pipelined timed region
+        traffic, traffic_src = None, "no ncu capture of this round found under profiles/"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            ent = tj.get(f"yolo_decode_filter_kernel:B={Bl}:{args.mode}")
+            if ent:
+                traffic, traffic_src = ent["dram_read_bytes"] + ent["dram_write_bytes"], ent["source"]
+        except Exception:
+            pass
         out = {
             "metric": "post-process images/sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": K,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "conf_thres": CONF, "iou_thres": IOU, "max_det": MAX_DET,
-                       "read_mode": args.mode, "l2": "inputs (2.19 GB/rank) larger than the 126 MB L2", "launch": "CUDA graph replay of one hd_yolo_postprocess call",
-                       "parallelism": f"image-sharded x{world}", "gather": gather_mode},
+            "config": {"workload": WORKLOAD, "global_batch": imgs_per_step, "batch_per_gpu": Bl, "conf_thres": CONF, "iou_thres": IOU,
+                       "max_det": MAX_DET, "read_mode": args.mode,
+                       "l2": f"every rank rotates through a pool of {len(pool)} distinct shard inputs = {len(pool) * Bl * BYTES_PER_IMG / 1e9:.2f} GB per rank, larger than the 126 MB L2",
+                       "launch": f"one CUDA-graph replay of one hd_yolo_postprocess call per step; steps pipelined {depth} deep over CUDA streams",
+                       "parallelism": f"image-sharded x{world}" + ("" if strong else " (weak: own batch per rank)"), "gather": gather_mode},
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "path": e2e_path},
-            "gpu_launches": 3 * K,
-            "roofline": {"kernel": "yolo_decode_filter_kernel (decode+sigmoid+filter+compaction) [bracket also holds the NMS kernels]", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
-                         "traffic": (2193531000 if (args.mode == "dense" and B == 256) else None),
-                         "traffic_source": "ncu --set full dram__bytes_read.sum+write.sum of this kernel at B=256, profiles/r1_ncu_summary.txt",
-                         "peak_source": peak_src, "kernel_ms": decode_ms,
-                         "algorithmic_bytes_per_launch": BYTES_PER_IMG * B},
+            "e2e": e2e,
+            "gpu_launches": int(pipe.launches_per_step) * K,
+            "gather_parity": gather_parity,
+            "roofline": {"kernel": "yolo_decode_filter_kernel (decode+sigmoid+filter+compaction); measured over the whole pipelined step, NMS kernels included",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": BYTES_PER_IMG * Bl, "per": "GPU"},
         }
         out.update(extra)
         if world == 1:
-            torch.set_num_threads(os.cpu_count() or 1)
-            n = min(args.cpu_sample, B)
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            n = min(args.cpu_sample, args.batch)
             v = cpu_reference_rate(heads_cpu, n)
             out["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
                                    "sample": f"{n} images of the same batch, best of 3 after 1 warm-up"}
+            if not args.no_configs:
+                del pool, pipe, pipe_copy, stages
+                torch.cuda.empty_cache()
+                try:
+                    out["configs"] = extra_configs(dev, peak, cores)
+                except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+                    out["configs"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -4,6 +4,7 @@ There is deliberately no CPU fallback: if the CUDA library is missing or a tenso
 is not on a CUDA device the call raises.
 """
 import ctypes as C
+import functools
 import os
 import torch
 
@@ -16,7 +17,7 @@ FLAG_CONF_GE = 1
 FLAG_DENSE_READ = 2
 NMS_AGNOSTIC, NMS_CLASS_EXACT, NMS_CLASS_OFFSET = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
-RPN_SOFTMAX, RPN_CLAMP_DWH, RPN_KEY_LOGIT = 1, 2, 4
+RPN_SOFTMAX, RPN_CLAMP_DWH, RPN_KEY_LOGIT, RPN_EXACT_MATH = 1, 2, 4, 8
 ROIHEAD_MUL_STD, ROIHEAD_CLAMP_DWH, ROIHEAD_LABEL_MINUS1 = 16, 32, 64
 BOX_XYWH = 1
 WBF_AVG, WBF_MAX = 0, 1
@@ -50,6 +51,7 @@ SIGNATURES = {
     "hd_version": (_i, []),
     "hd_last_error": (C.c_char_p, []),
     "hd_debug_phases": (_i, [_i, C.POINTER(C.c_longlong)]),
+    "hd_debug_launch_count": (C.c_ulonglong, []),
     "hd_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _vp, _vp]),
     "hd_yolo_decode_filter": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "hd_yolo_postprocess_workspace_size": (_sz, [_i, _i]),
@@ -118,6 +120,31 @@ def ptr(t):
 
 def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _first_cuda_device(objs):
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            if o.is_cuda:
+                return o.device
+        elif isinstance(o, (list, tuple)):
+            d = _first_cuda_device(o)
+            if d is not None:
+                return d
+    return None
+
+
+def on_device(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current (as torchvision's ops do with a device guard):
+    the C ABI launches on the current device, and the stream handed to it must belong to that device."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _first_cuda_device(args) or _first_cuda_device(tuple(kwargs.values()))
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def require_cuda(*tensors):

@@ -16,6 +16,7 @@ class Matcher:
             raise AssertionError("low_threshold should be <= high_threshold")
         self.high, self.low, self.allow = float(high_threshold), float(low_threshold), bool(allow_low_quality_matches)
 
+    @_lib.on_device
     def __call__(self, gt_boxes, boxes, gt_count=None, return_iou=False):
         """gt_boxes [G,4] | [B,Gmax,4] (+ gt_count [B]), boxes [N,4] (shared anchors) | [B,N,4] -> matches [N] | [B,N] int64"""
         _lib.require_cuda(gt_boxes, boxes, gt_count)
@@ -50,6 +51,7 @@ def anchor_labels(gt_boxes, anchors, pos_iou_thresh=0.7, neg_iou_thresh=0.3, gt_
     return m.clamp(min=0), label
 
 
+@_lib.on_device
 def encode_boxes(gt_boxes, boxes, matches=None, weights=(1.0, 1.0, 1.0, 1.0)):
     """torchvision BoxCoder.encode_single / lineage bbox2loc: regression targets of `boxes` towards their matched ground truth.
     gt_boxes [G,4] | [B,G,4]; boxes [N,4] | [B,N,4]; matches [N] | [B,N] from Matcher (negative codes are read as GT 0, as

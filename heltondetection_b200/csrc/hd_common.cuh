@@ -7,7 +7,22 @@
 #include <string.h>
 #include "../../include/hd_b200.h"
 
-#define HD_NUM_SMS 148
+#define HD_MAX_DEVICES 64   // per-device caches below are indexed by the CUDA device ordinal
+
+// ---------------------------------------------------------------- per-device state (api.cu)
+// Function attributes (cudaFuncSetAttribute) and occupancy figures are properties of a (function, device) pair, and the
+// library may drive several GPUs from one process and from several host threads: every cache is per device and atomic.
+int hd_current_device(void);                 // cudaGetDevice, -1 on error
+int hd_num_sms(void);                        // multiProcessorCount of the current device (cached per device; 148 on a B200)
+struct HdDeviceOnce { unsigned long long done; };   // one bit per device; zero-initialised static
+// raise MaxDynamicSharedMemorySize of `func` on the current device once per device; returns an hd error code
+int hd_ensure_max_smem(HdDeviceOnce* once, const void* func, int bytes, const char* name);
+#define HD_ENSURE_SMEM(kernel, bytes)                                                                      \
+    do {                                                                                                   \
+        static HdDeviceOnce once__ = {0ull};                                                               \
+        int rc__ = hd_ensure_max_smem(&once__, (const void*)(kernel), (int)(bytes), #kernel);              \
+        if (rc__) return rc__;                                                                             \
+    } while (0)
 
 // ---------------------------------------------------------------- host error plumbing
 void hd_set_error(const char* fmt, ...);
@@ -20,10 +35,12 @@ void hd_set_error(const char* fmt, ...);
     do {                                               \
         if (!(cond)) HD_FAIL(HD_ERR_INVALID, __VA_ARGS__); \
     } while (0)
+void hd_count_launch(void);   // every kernel launch of the library is counted (hd_debug_launch_count)
 #define HD_CUDA_LAUNCH_CHECK(name)                                                        \
     do {                                                                                  \
         cudaError_t e__ = cudaGetLastError();                                             \
         if (e__ != cudaSuccess) HD_FAIL(HD_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__)); \
+        hd_count_launch();                                                                \
     } while (0)
 #define HD_CUDA_CALL(x)                                                                       \
     do {                                                                                      \

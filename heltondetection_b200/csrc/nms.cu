@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     if (n <= 0) {
         if (tid == 0) p.out_count[b] = 0;
         if (tid < p.rep.n) p.rep.cnt[tid][b] = 0;
+        hd_zero_tail(p.out_det, p.out_idx, p.rep, p.max_det, b, 0);
         return;
     }
     const size_t off = (size_t)b * p.cap;
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     }
     if (tid == 0) p.out_count[b] = kc;
     if (tid < p.rep.n) p.rep.cnt[tid][b] = kc;
+    hd_zero_tail(p.out_det, p.out_idx, p.rep, p.max_det, b, kc);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_cluster_kernel(const __gri
     }
     if (tid == 0) p.out_count[b] = kc;
     if (tid < p.rep.n) p.rep.cnt[tid][b] = kc;
+    hd_zero_tail(p.out_det, p.out_idx, p.rep, p.max_det, b, kc);
 }
 
 // small-image variant: 256 threads, everything in shared memory, several images per SM at once
@@ -291,10 +294,13 @@ __global__ void __launch_bounds__(256) box_iou_kernel(const float4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ host
-static int g_nms_mode = 0;   // 0 auto, 1 one CTA per image only, 2 cluster kernel whenever the batch allows
-extern "C" HD_API int hd_nms_set_mode(int mode) { int old = g_nms_mode; g_nms_mode = mode; return old; }
+// developer/test knob (process-wide, atomic): 0 auto, 1 one CTA per image only, 2 cluster kernel whenever the batch allows
+static int g_nms_mode = 0;
+extern "C" HD_API int hd_nms_set_mode(int mode) { return __atomic_exchange_n(&g_nms_mode, mode, __ATOMIC_ACQ_REL); }
 static int nms_cluster_capacity(int CL) {
-    static int cached[RPNC_MAXCL + 1] = {0};
+    static int cached_dev[HD_MAX_DEVICES][RPNC_MAXCL + 1] = {{0}};   // per device; racing writers store the same value
+    const int dev = hd_current_device();
+    int* cached = cached_dev[(dev >= 0 && dev < HD_MAX_DEVICES) ? dev : 0];
     if (cached[CL]) return cached[CL];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(NMS_NT); cfg.dynamicSmemBytes = 180 * 1024;
@@ -302,13 +308,13 @@ static int nms_cluster_capacity(int CL) {
     cfg.attrs = &at; cfg.numAttrs = 1;
     int nc = 0;
     cudaFuncSetAttribute(sort_nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (cudaOccupancyMaxActiveClusters(&nc, sort_nms_cluster_kernel, &cfg) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = HD_NUM_SMS / CL; }
+    if (cudaOccupancyMaxActiveClusters(&nc, sort_nms_cluster_kernel, &cfg) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = hd_num_sms() / CL; }
     return cached[CL] = nc;
 }
 // CTAs per image for a batch of B images: the largest cluster (8 or 4) that still runs the whole batch in one wave; 0 = the
 // batch is large enough for one CTA per image (or the mode forbids clusters)
 static int nms_cluster_size(int B, bool for_layout = false) {
-    if ((g_nms_mode == 1 && !for_layout) || B <= 0) return 0;
+    if ((__atomic_load_n(&g_nms_mode, __ATOMIC_ACQUIRE) == 1 && !for_layout) || B <= 0) return 0;
     for (int c = RPNC_MAXCL; c >= 4; c >>= 1)     // clusters of 2 measured no faster than one CTA per image (cfg4, B=64)
         if (B <= nms_cluster_capacity(c)) return c;
     return 0;
@@ -409,11 +415,7 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
     p.sort_off = (int)words;
     p.bitonic_cap = 8192;
     size_t smem = words * 4 + (size_t)p.bitonic_cap * 12;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        HD_CUDA_CALL(cudaFuncSetAttribute(sort_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 186 * 1024));
-        smem_set = 186 * 1024;
-    }
+    HD_ENSURE_SMEM(sort_nms_kernel, 186 * 1024);
     if (min_n < 0 && (counts != nullptr || n_fixed <= HD_SMALL_N)) {
         // images with <= HD_SMALL_N candidates: shared-memory kernel; the radix-sort kernel below then only
         // works on the larger ones (it returns at once for the rest)
@@ -447,6 +449,7 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
         cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
         HD_CUDA_CALL(cudaLaunchKernelEx(&cfg, sort_nms_cluster_kernel, q));
+        hd_count_launch();
         p.only = q.fallback;
     }
     sort_nms_kernel<<<B, NMS_NT, smem, st>>>(p);

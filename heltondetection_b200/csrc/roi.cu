@@ -900,11 +900,12 @@ static int fill_roi(RoiParams& p, const hd_roi_level* levels, int n_levels, int 
 // 0 auto (= gather kernels: the staged-row kernel measured 2.5x slower on B200, see profiles/r1_results.md), 1 gather kernels
 // only, 2 staged-row kernel whenever eligible; bits 4.. are debug switches of the staged-row kernel (1: no tile store,
 // 2: no compute, 8: nothing staged)
-static int g_roi_mode = 0;
-extern "C" HD_API int hd_roi_set_mode(int mode) { int old = g_roi_mode; g_roi_mode = mode; return old; }
+static int g_roi_mode_ = 0;   // developer/test knob (process-wide, atomic)
+extern "C" HD_API int hd_roi_set_mode(int mode) { return __atomic_exchange_n(&g_roi_mode_, mode, __ATOMIC_ACQ_REL); }
 
 static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st) {
     if (p.K == 0) return HD_OK;
+    const int g_roi_mode = __atomic_load_n(&g_roi_mode_, __ATOMIC_ACQUIRE);
     HD_CHECK_ARG(p.rois && p.out, "rois/out is NULL");
     if (layout == HD_LAYOUT_NHWC) {
         size_t tile = (size_t)p.C * p.PH * p.PW * 4;
@@ -917,17 +918,13 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
         HD_CHECK_ARG(smem <= 220 * 1024, "C*PH*PW=%d floats exceed the shared-memory tile", p.C * p.PH * p.PW);
         HD_CHECK_ARG(p.K < (1ll << 31), "too many RoIs");
         int use_tma = (tile % 16 == 0) && (((uintptr_t)p.out & 15) == 0);
-        static bool attr_set = false;
-        if (!attr_set) {
-            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            HD_CUDA_CALL(cudaFuncSetAttribute(roi_pool_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_nhwc_quad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            HD_CUDA_CALL(cudaFuncSetAttribute(roi_pool_nhwc_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-            attr_set = true;
-        }
+        HD_ENSURE_SMEM(roi_align_nhwc_kernel, 220 * 1024);
+        HD_ENSURE_SMEM(roi_pool_nhwc_kernel, 220 * 1024);
+        HD_ENSURE_SMEM(roi_align_nhwc_quad_kernel<4>, 220 * 1024);
+        HD_ENSURE_SMEM(roi_align_nhwc_quad_kernel<8>, 220 * 1024);
+        HD_ENSURE_SMEM(roi_align_nhwc_quad_kernel<16>, 220 * 1024);
+        HD_ENSURE_SMEM(roi_align_nhwc_quad_kernel<0>, 220 * 1024);
+        HD_ENSURE_SMEM(roi_pool_nhwc_quad_kernel, 220 * 1024);
         int threads = p.C >= 256 ? 256 : ((p.C + 31) / 32 * 32 < 128 ? 128 : (p.C + 31) / 32 * 32);
         for (int l = 0; l < p.n_levels; ++l) HD_CHECK_ARG((long long)p.H[l] * p.W[l] * p.C < (1ll << 31), "level %d: H*W*C must be < 2^31", l);
         bool quad = (p.C % 4 == 0);
@@ -942,10 +939,9 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
             int n_slots = tile_b + meta_b < budget ? (int)((budget - tile_b - meta_b) / slot_b) : 0;
             if (n_slots > RR_MAXSLOTS) n_slots = RR_MAXSLOTS;
             if (n_slots >= 6 && use_tma) {
-                static bool ring_attr = false;
-                if (!ring_attr) { HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget)); ring_attr = true; }
+                HD_ENSURE_SMEM(roi_align_ring_kernel, budget);
                 const size_t smem_ring = tile_b + (size_t)n_slots * slot_b + meta_b;
-                const unsigned grid = (unsigned)(p.K < HD_NUM_SMS ? p.K : HD_NUM_SMS);
+                const unsigned grid = (unsigned)(p.K < hd_num_sms() ? p.K : hd_num_sms());
                 roi_align_ring_kernel<<<grid, RR_THREADS, smem_ring, st>>>(p, n_slots, (int)slot_b, (int)tile_b, (int)(tile_b + (size_t)n_slots * slot_b), g_roi_mode >> 4);
                 HD_CUDA_LAUNCH_CHECK("roi_align_ring_kernel");
                 return HD_OK;

@@ -146,8 +146,7 @@ extern "C" HD_API int hd_roi_align_backward(const float* grad_out, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const size_t tile = (size_t)C * pooled_h * pooled_w * 4;
     if (quad && tile <= 200 * 1024 && K < (1ll << 31)) {
-        static bool attr_set = false;
-        if (!attr_set) { HD_CUDA_CALL(cudaFuncSetAttribute(roi_align_bwd_nhwc_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+        HD_ENSURE_SMEM(roi_align_bwd_nhwc_quad_kernel, 200 * 1024);
         int nq = C / 4, QT = 8;
         while (QT < nq && QT < 256) QT <<= 1;
         roi_align_bwd_nhwc_quad_kernel<<<(unsigned)K, 256, tile, st>>>(p, QT);

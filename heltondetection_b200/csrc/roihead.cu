@@ -97,7 +97,7 @@ static int roi_head_fill(RoiHeadParams& p, const float* logits, const float* del
     p.logits = logits; p.deltas = deltas; p.rois = rois; p.roi_count = roi_count; p.B = B; p.R = R; p.n_class = n_class; p.flags = flags;
     p.wx = weights[0]; p.wy = weights[1]; p.ww = weights[2]; p.wh = weights[3];
     p.clamp_dwh = clamp_dwh; p.img_h = img_h; p.img_w = img_w;
-    p.score_thr = (flags & HD_FLAG_CONF_GE) ? hd_thr_ceil(score_thresh) : hd_thr_floor(score_thresh);
+    p.score_thr = (float)score_thresh;   // torch compares the fp32 scores with the scalar cast to fp32 (scores > score_thresh), as yolo.cu does
     p.min_size = min_size;
     p.cand_box = (float4*)cand_box; p.cand_score = cand_score; p.cand_cls = cand_cls; p.cand_id = cand_id; p.cand_count = cand_count; p.cap = cap;
     return HD_OK;

@@ -21,6 +21,7 @@ struct RpnParams {
     float img_h, img_w, min_size, clamp_dwh;
     int use_clamp;
     int key_logit;          // sort key from the raw objectness logit (torchvision takes its per-level top-k on the logits)
+    int exact;              // HD_RPN_EXACT_MATH: transcendentals in fp64, rounded once to fp32
     long long total_cells;  // B * sum(HW)
     int N;                  // anchors per image
 };
@@ -55,11 +56,16 @@ __global__ void __launch_bounds__(256) rpn_decode_kernel(const __grid_constant__
         if (p.softmax) {  // F.softmax over (bg, fg): exp(x - max) / sum
             const float s0 = hd_ldg_stream(ob + (size_t)(2 * a) * HW), s1 = hd_ldg_stream(ob + (size_t)(2 * a + 1) * HW);
             const float m = fmaxf(s0, s1);
-            const float e0 = expf(__fsub_rn(s0, m)), e1 = expf(__fsub_rn(s1, m));
-            score = __fdiv_rn(e1, __fadd_rn(e0, e1));
+            if (p.exact) {
+                const double e0 = exp((double)s0 - (double)m), e1 = exp((double)s1 - (double)m);
+                score = (float)(e1 / (e0 + e1));
+            } else {
+                const float e0 = expf(__fsub_rn(s0, m)), e1 = expf(__fsub_rn(s1, m));
+                score = __fdiv_rn(e1, __fadd_rn(e0, e1));
+            }
         } else {
             logit = hd_ldg_stream(ob + (size_t)a * HW);
-            score = hd_sigmoid(logit);
+            score = p.exact ? (float)(1.0 / (1.0 + exp(-(double)logit))) : hd_sigmoid(logit);
         }
         const float dx = hd_ldg_stream(dl + (size_t)(4 * a) * HW), dy = hd_ldg_stream(dl + (size_t)(4 * a + 1) * HW);
         float dw = hd_ldg_stream(dl + (size_t)(4 * a + 2) * HW), dh = hd_ldg_stream(dl + (size_t)(4 * a + 3) * HW);
@@ -71,7 +77,8 @@ __global__ void __launch_bounds__(256) rpn_decode_kernel(const __grid_constant__
         const float wa = __fsub_rn(ax2, ax1), ha = __fsub_rn(ay2, ay1);
         const float cxa = __fadd_rn(ax1, __fmul_rn(0.5f, wa)), cya = __fadd_rn(ay1, __fmul_rn(0.5f, ha));
         const float cx = __fadd_rn(__fmul_rn(dx, wa), cxa), cy = __fadd_rn(__fmul_rn(dy, ha), cya);
-        const float w = __fmul_rn(expf(dw), wa), h = __fmul_rn(expf(dh), ha);
+        const float ew = p.exact ? (float)exp((double)dw) : expf(dw), eh = p.exact ? (float)exp((double)dh) : expf(dh);
+        const float w = __fmul_rn(ew, wa), h = __fmul_rn(eh, ha);
         float x1 = __fsub_rn(cx, __fmul_rn(0.5f, w)), y1 = __fsub_rn(cy, __fmul_rn(0.5f, h));
         float x2 = __fadd_rn(cx, __fmul_rn(0.5f, w)), y2 = __fadd_rn(cy, __fmul_rn(0.5f, h));
         // clip to the image (torch.clamp(min=0, max=size))
@@ -635,6 +642,7 @@ static int rpn_fill(RpnParams& p, const hd_rpn_level* levels, int n_levels, int 
     p.img_h = img_h; p.img_w = img_w; p.min_size = min_size;
     p.use_clamp = (flags & HD_RPN_CLAMP_DWH) ? 1 : 0; p.clamp_dwh = clamp_dwh;
     p.key_logit = (flags & HD_RPN_KEY_LOGIT) ? 1 : 0;
+    p.exact = (flags & HD_RPN_EXACT_MATH) ? 1 : 0;
     p.total_cells = (long long)B * cells; p.N = anchors;
     return HD_OK;
 }
@@ -681,7 +689,9 @@ static void rpn_ws_layout(int B, int cap, size_t* offs, size_t* total) {
 }
 static int rpn_cluster_capacity(int CL) {
     // how many CL-CTA clusters of the stage-2 kernel the device holds at once (1 CTA per SM: 1024 threads x 64 registers)
-    static int cached[RPNC_MAXCL + 1] = {0};
+    static int cached_dev[HD_MAX_DEVICES][RPNC_MAXCL + 1] = {{0}};   // per device; racing writers store the same value
+    const int dev = hd_current_device();
+    int* cached = cached_dev[(dev >= 0 && dev < HD_MAX_DEVICES) ? dev : 0];
     if (cached[CL]) return cached[CL];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(RPN_NT); cfg.dynamicSmemBytes = 200 * 1024;
@@ -689,17 +699,18 @@ static int rpn_cluster_capacity(int CL) {
     cfg.attrs = &at; cfg.numAttrs = 1;
     int nc = 0;
     cudaFuncSetAttribute(rpn_select_nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (cudaOccupancyMaxActiveClusters(&nc, rpn_select_nms_cluster_kernel, &cfg) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = HD_NUM_SMS / CL; }
+    if (cudaOccupancyMaxActiveClusters(&nc, rpn_select_nms_cluster_kernel, &cfg) != cudaSuccess || nc <= 0) { cudaGetLastError(); nc = hd_num_sms() / CL; }
     return cached[CL] = nc;
 }
 extern "C" HD_API int hd_rpn_cluster_capacity(int cluster_size) {
     if (cluster_size != 1 && cluster_size != 2 && cluster_size != 4 && cluster_size != 8) return -1;
     return rpn_cluster_capacity(cluster_size);
 }
+// developer/test knobs (process-wide, atomic): they select between kernels that return identical results
 static int g_rpn_cluster = 0;   // 0: chosen per launch
-extern "C" HD_API int hd_rpn_set_cluster_size(int cl) { int old = g_rpn_cluster; g_rpn_cluster = (cl == 1 || cl == 2 || cl == 4 || cl == 8) ? cl : 0; return old; }
+extern "C" HD_API int hd_rpn_set_cluster_size(int cl) { return __atomic_exchange_n(&g_rpn_cluster, (cl == 1 || cl == 2 || cl == 4 || cl == 8) ? cl : 0, __ATOMIC_ACQ_REL); }
 static int g_rpn_mode = 0;   // 0 auto, 1 single CTA per image, 2 cluster (when eligible)
-extern "C" HD_API int hd_rpn_set_mode(int mode) { int old = g_rpn_mode; g_rpn_mode = mode; return old; }
+extern "C" HD_API int hd_rpn_set_mode(int mode) { return __atomic_exchange_n(&g_rpn_mode, mode, __ATOMIC_ACQ_REL); }
 static int rpn_cap(int N, int n_pre) { return (n_pre > 0 && n_pre < N) ? n_pre : N; }
 
 extern "C" HD_API size_t hd_rpn_select_nms_workspace_size(int B, int N, int n_pre) {
@@ -736,16 +747,13 @@ extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores,
     // passes and keep the shared memory for L1 (the pruned NMS streams its records through it)
     p.bitonic_cap = (cap <= 8192) ? 8192 : 0;
     size_t smem = words * 4 + (size_t)p.bitonic_cap * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CUDA_CALL(cudaFuncSetAttribute(rpn_select_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 186 * 1024));
-        HD_CUDA_CALL(cudaFuncSetAttribute(rpn_select_nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
-    if (g_rpn_mode != 1 && rpn_cluster_ok(cap) && N > 0) {
+    HD_ENSURE_SMEM(rpn_select_nms_kernel, 186 * 1024);
+    HD_ENSURE_SMEM(rpn_select_nms_cluster_kernel, 200 * 1024);
+    const int rpn_mode = __atomic_load_n(&g_rpn_mode, __ATOMIC_ACQUIRE);
+    if (rpn_mode != 1 && rpn_cluster_ok(cap) && N > 0) {
         // CL SMs per image; an image whose adjacency lists overflow is redone by the single-CTA kernel below.
         // CL minimises waves * (serial + parallel / CL) with phase times measured on B200 (profiles/r1_results.md).
-        int CL = g_rpn_cluster;
+        int CL = __atomic_load_n(&g_rpn_cluster, __ATOMIC_ACQUIRE);
         if (!CL) {
             double best = 1e30;
             for (int c = RPNC_MAXCL; c >= 1; c >>= 1) {
@@ -776,6 +784,7 @@ extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores,
         cudaLaunchAttribute at; at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
         cfg.attrs = &at; cfg.numAttrs = 1;
         HD_CUDA_CALL(cudaLaunchKernelEx(&cfg, rpn_select_nms_cluster_kernel, q));
+        hd_count_launch();
         p.only = q.fallback;
     }
     rpn_select_nms_kernel<<<B, RPN_NT, smem, (cudaStream_t)stream>>>(p);

@@ -665,12 +665,11 @@ extern "C" HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels, int n_l
             const int buf_floats = (int)hd_align_up((size_t)NHWC_TMA_TC * A * (5 + nc), 32);
             const size_t smt = 2 * (size_t)buf_floats * 4;
             if (smt <= 200 * 1024) {
-                static bool tma_attr = false;
-                if (!tma_attr) { HD_CUDA_CALL(cudaFuncSetAttribute(yolo_decode_filter_nhwc_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); tma_attr = true; }
+                HD_ENSURE_SMEM(yolo_decode_filter_nhwc_tma_kernel, 200 * 1024);
                 int per_sm = (int)((220 * 1024) / (smt + 1024));
                 if (per_sm < 1) per_sm = 1;
                 if (per_sm > 8) per_sm = 8;
-                long long grid = (long long)HD_NUM_SMS * per_sm;
+                long long grid = (long long)hd_num_sms() * per_sm;
                 if (grid > pt.total_items) grid = pt.total_items;
                 yolo_decode_filter_nhwc_tma_kernel<<<(unsigned)grid, 128, smt, st>>>(pt, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count, buf_floats);
                 HD_CUDA_LAUNCH_CHECK("yolo_decode_filter_nhwc_tma_kernel");
@@ -679,8 +678,7 @@ extern "C" HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels, int n_l
         }
         const size_t sm = pn.dense ? (size_t)NHWC_TC * A * (5 + nc) * 4 : 0;
         HD_CHECK_ARG(sm <= 200 * 1024, "A*(5+nc)=%d too large for the NHWC tile", A * (5 + nc));
-        static bool nhwc_attr = false;
-        if (!nhwc_attr) { HD_CUDA_CALL(cudaFuncSetAttribute(yolo_decode_filter_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); nhwc_attr = true; }
+        HD_ENSURE_SMEM(yolo_decode_filter_nhwc_kernel, 200 * 1024);
         yolo_decode_filter_nhwc_kernel<<<(unsigned)pn.total_items, 256, sm, st>>>(pn, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count);
         HD_CUDA_LAUNCH_CHECK("yolo_decode_filter_nhwc_kernel");
         return HD_OK;
@@ -710,11 +708,7 @@ extern "C" HD_API int hd_yolo_decode(const hd_yolo_level* levels, int n_levels, 
     const int warps = 4;
     size_t smem = (size_t)warps * p.no * 33 * sizeof(float);
     HD_CHECK_ARG(smem <= 200 * 1024, "nc=%d too large for the decode transpose tile", nc);
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CUDA_CALL(cudaFuncSetAttribute(yolo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    HD_ENSURE_SMEM(yolo_decode_kernel, 200 * 1024);
     long long blocks = (p.total_items + warps - 1) / warps;
     HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
     yolo_decode_kernel<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(p, pred, p.level_off[n_levels]);

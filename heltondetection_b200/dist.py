@@ -7,6 +7,33 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE pinned host buffers are allocated (first touch
+    then places them on that node), so that zero-copy reads and H2D copies of 8 ranks do not all cross the socket interconnect.
+    Best effort: returns the node id, or None when the topology cannot be read."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def shard_slice(n_images, rank, world):
     """Contiguous image slice of `rank`: the first (n % world) ranks take one extra image."""
     base, rem = divmod(n_images, world)
@@ -137,6 +164,7 @@ class PeerDetectionBuffers:
         """(det [world*B,max_det,6], count [world*B]) -- complete once every rank's step has finished (see barrier())"""
         return self.det[slot], self.count[slot]
 
-    def barrier(self):
-        """cross-GPU barrier on the current stream: afterwards the stores of all ranks' previous kernels have landed"""
-        self.h_det.barrier()
+    def barrier(self, channel=0):
+        """cross-GPU barrier on the current stream: afterwards the stores of all ranks' previous kernels have landed.
+        Barriers that may be in flight at the same time (pipelined steps on different streams) must use different channels."""
+        self.h_det.barrier(channel=channel)

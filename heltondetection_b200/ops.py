@@ -29,6 +29,7 @@ def _check_nms_args(boxes, scores):
         raise NotImplementedError(f'"nms_kernel" not implemented for \'{str(boxes.dtype).split(".")[-1].capitalize()}\' (hd_b200 is fp32-only)')
 
 
+@_lib.on_device
 def _nms_single(boxes, scores, iou_threshold, cls=None, mode=_lib.NMS_AGNOSTIC, offset=0.0, max_det=None, max_nms=0):
     """One image through hd_sort_nms_batched -> int64 keep indices in score order."""
     _lib.require_cuda(boxes, scores, cls)
@@ -70,6 +71,7 @@ def box_iou(boxes1, boxes2):
     return torch.ops.hd_b200.box_iou(boxes1, boxes2)
 
 
+@_lib.on_device
 def _box_iou_impl(boxes1, boxes2):
     _lib.require_cuda(boxes1, boxes2)
     if boxes1.dim() != 2 or boxes1.size(1) != 4 or boxes2.dim() != 2 or boxes2.size(1) != 4:

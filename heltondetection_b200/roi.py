@@ -62,6 +62,7 @@ def _levels_struct(tensors, scales):
     return arr
 
 
+@_lib.on_device
 def _run(features, scales, rois, level_ids, output_size, sampling_ratio, aligned, pool, layout, return_argmax=False):
     PH, PW = _pair(output_size)
     for f in features:
@@ -94,6 +95,7 @@ def _run(features, scales, rois, level_ids, output_size, sampling_ratio, aligned
     return (out, argmax) if return_argmax else out
 
 
+@_lib.on_device
 def roi_align_backward(grad, rois, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width, sampling_ratio, aligned,
                        channels_last=True):
     """torch.ops.torchvision._roi_align_backward schema -> grad_input [B,C,H,W] (channels_last memory by default: the layout whose
@@ -115,6 +117,7 @@ def roi_align_backward(grad, rois, spatial_scale, pooled_height, pooled_width, b
     return gi
 
 
+@_lib.on_device
 def roi_pool_backward(grad, rois, argmax, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width, channels_last=False):
     """torch.ops.torchvision._roi_pool_backward schema -> grad_input [B,C,H,W]"""
     _lib.require_cuda(grad, rois, argmax)
@@ -214,6 +217,7 @@ class RoIPool(nn.Module):
         return f"{self.__class__.__name__}(output_size={self.output_size}, spatial_scale={self.spatial_scale})"
 
 
+@_lib.on_device
 def level_map(boxes_xyxy, k_min=2, k_max=5, canonical_scale=224.0, canonical_level=4, eps=1e-6, style="torchvision"):
     """FPN level of each box [K,4] -> int64 [K] (poolers.py:73-84; style 'mmdet': eps inside the log)."""
     _lib.require_cuda(boxes_xyxy)
@@ -224,6 +228,7 @@ def level_map(boxes_xyxy, k_min=2, k_max=5, canonical_scale=224.0, canonical_lev
     return out
 
 
+@_lib.on_device
 def multilevel_roi_align(features, rois, output_size, spatial_scales, sampling_ratio=2, aligned=False, op="align",
                          levels=None, layout="auto", k_min=2, k_max=5, canonical_scale=224.0, canonical_level=4,
                          eps=1e-6, style="torchvision"):

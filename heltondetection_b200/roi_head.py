@@ -40,6 +40,7 @@ class RoIHeadPostprocessor:
             self.count = torch.zeros((B,), dtype=torch.int32, device=dev)
             self._key = key
 
+    @_lib.on_device
     def __call__(self, class_logits, box_regression, rois, roi_count=None, B=None):
         _lib.require_cuda(class_logits, box_regression, rois, roi_count)
         class_logits, box_regression, rois = _lib.f32c(class_logits), _lib.f32c(box_regression), _lib.f32c(rois)
@@ -161,6 +162,7 @@ def _letterbox_meta(img1_shape, img0_shapes, device):
     return torch.tensor(rows, dtype=torch.float32, device=device)
 
 
+@_lib.on_device
 def scale_coords(img1_shape, det, img0_shapes, count=None, xywh=False, out=None):
     """padded detections [B,max_det,6] in letterboxed pixels -> original-image pixels (clipped); xywh=True gives COCO boxes"""
     _lib.require_cuda(det, count)

@@ -55,10 +55,13 @@ class RpnProposals:
     """raw RPN heads -> (rois [B*n_post,5], count [B], scores [B,n_post], idx [B,n_post]); no host sync."""
 
     def __init__(self, anchor_bases, strides, img_size, nms_iou=0.7, n_pre_nms=12000, n_post_nms=2000, min_size=16.0,
-                 score_mode="sigmoid", clamp_dwh=None):
+                 score_mode="sigmoid", clamp_dwh=None, exact_math=False):
+        """exact_math: sigmoid / softmax / exp in fp64 rounded once to fp32 (HD_RPN_EXACT_MATH) -- the proposals are then
+        bit-reproducible against a CPU doing the same (oracle.rpn exact_math=True); default fp32 expf like the reference."""
         self.anchor_bases, self.strides, self.img_size = anchor_bases, strides, img_size
         self.nms_iou, self.n_pre, self.n_post, self.min_size = float(nms_iou), int(n_pre_nms), int(n_post_nms), float(min_size)
-        self.flags = (_lib.RPN_SOFTMAX if score_mode == "softmax" else 0) | (_lib.RPN_CLAMP_DWH if clamp_dwh is not None else 0)
+        self.flags = ((_lib.RPN_SOFTMAX if score_mode == "softmax" else 0) | (_lib.RPN_CLAMP_DWH if clamp_dwh is not None else 0)
+                      | (_lib.RPN_EXACT_MATH if exact_math else 0))
         self.clamp = float(clamp_dwh) if clamp_dwh is not None else 0.0
         self._key = None
 
@@ -74,6 +77,7 @@ class RpnProposals:
             self.count = torch.zeros((B,), dtype=torch.int32, device=dev)
             self._key = key
 
+    @_lib.on_device
     def __call__(self, objectness, deltas):
         arr, keep, B, A = _levels(objectness, deltas, self.anchor_bases, self.strides, bool(self.flags & _lib.RPN_SOFTMAX))
         L = _lib.lib()
@@ -85,6 +89,7 @@ class RpnProposals:
                                       self.ws_bytes, _lib.stream()))
         return self.rois.view(B * self.n_post, 5), self.count, self.scores, self.idx
 
+    @_lib.on_device
     def decode(self, objectness, deltas):
         """stage 1 only -> (boxes [B,N,4], scores [B,N], keys [B,N] int32 view of the sortable bits)."""
         arr, keep, B, A = _levels(objectness, deltas, self.anchor_bases, self.strides, bool(self.flags & _lib.RPN_SOFTMAX))
@@ -99,6 +104,7 @@ class RpnProposals:
         return boxes, scores, keys
 
 
+@_lib.on_device
 def select_nms(boxes, scores, valid, n_pre, n_post, nms_iou):
     """stage 2 on explicit arrays: boxes [B,N,4], scores [B,N], valid [B,N] bool -> (rois [B,n_post,5], scores, idx, count)."""
     _lib.require_cuda(boxes, scores, valid)
@@ -137,6 +143,7 @@ class ProposalCreator:
         self.n_train_pre_nms, self.n_train_post_nms = n_train_pre_nms, n_train_post_nms
         self.n_test_pre_nms, self.n_test_post_nms = n_test_pre_nms, n_test_post_nms
 
+    @_lib.on_device
     def __call__(self, loc, score, anchor, img_size, scale=1.0, return_index=False):
         _lib.require_cuda(loc, score)
         n_pre, n_post = ((self.n_train_pre_nms, self.n_train_post_nms) if self.mode == "training"
@@ -178,6 +185,7 @@ class RpnProposalsPerLevel:
         boxes, scores, keys = self.dec.decode(objectness, deltas)
         return self.filter_proposals(boxes, scores, keys, [d.shape[1] // 4 * d.shape[2] * d.shape[3] for d in deltas])
 
+    @_lib.on_device
     def filter_proposals(self, boxes, scores, keys, num_anchors_per_level):
         """stage 2 on the decoded arrays: boxes [B,N,4], scores [B,N] (probabilities), keys [B,N] int32 (sortable logit bits)"""
         L = _lib.lib()

@@ -39,6 +39,7 @@ def plant_yolo(heads, b, gt, cls, rng, nc, anchors=YOLO_ANCHORS, strides=YOLO_ST
     """Overwrite head logits of image b so anchors near each gt decode to it (inverse of A.1)."""
     flat = [(l, a, aw, ah) for l, lv in enumerate(anchors) for a, (aw, ah) in enumerate(lv)]
     no = 5 + nc
+    heads = [t.numpy() if isinstance(t, torch.Tensor) else t for t in heads]   # views: element writes without dispatcher overhead
     for (cx, cy, w, h), c in zip(gt, cls):
         ratios = [max(w / aw, aw / w, h / ah, ah / h) for (_, _, aw, ah) in flat]
         order = np.argsort(ratios)[:max_anchors]

@@ -34,6 +34,7 @@ class WbfBatched:
             self.oc = torch.zeros((B,), dtype=torch.int32, device=dev)
             self._key = key
 
+    @_lib.on_device
     def __call__(self, boxes, scores, labels, counts):
         _lib.require_cuda(boxes, scores, labels, counts)
         B, V, M = scores.shape
@@ -43,8 +44,11 @@ class WbfBatched:
             if len(self.weights) != V:
                 raise RuntimeError(f"Incorrect number of weights {len(self.weights)}. Must be: {V}")
             w = (C.c_double * V)(*[float(x) for x in self.weights])
-        _lib.check(_lib.lib().hd_wbf(_lib.ptr(_lib.f32c(boxes)), _lib.ptr(_lib.f32c(scores)), _lib.ptr(_lib.f32c(labels)),
-                                     _lib.ptr(counts.to(torch.int32).contiguous()), B, V, M, self.num_labels, w, self.iou_thr, self.skip,
+        # converted copies are bound to locals so that they outlive the launch (a temporary's block could be handed to the
+        # next conversion by the caching allocator before the kernel has read it)
+        bx, sc, lb, cn = _lib.f32c(boxes), _lib.f32c(scores), _lib.f32c(labels), counts.to(torch.int32).contiguous()
+        _lib.check(_lib.lib().hd_wbf(_lib.ptr(bx), _lib.ptr(sc), _lib.ptr(lb),
+                                     _lib.ptr(cn), B, V, M, self.num_labels, w, self.iou_thr, self.skip,
                                      self.conf, self.overflow, _lib.ptr(self.ob), _lib.ptr(self.os), _lib.ptr(self.ol), _lib.ptr(self.oc),
                                      _lib.ptr(self.ws), self.ws_bytes, _lib.stream()))
         return self.ob, self.os, self.ol, self.oc
@@ -93,12 +97,14 @@ class TTAFusion:
             self.cnt = torch.zeros((B, V), dtype=torch.int32, device=dev)
             self._key = (B, dev)
 
+    @_lib.on_device
     def map_back(self, v, det, count):
         """det [B,max_det,6] / count [B] of view v (device) -> written into the WBF input slot v."""
         B = det.shape[0]
         self._alloc(B, det.device)
         scale, hflip, view_w = self.views[v]
-        _lib.check(_lib.lib().hd_tta_map_back(_lib.ptr(_lib.f32c(det)), _lib.ptr(count), B, det.shape[1], float(scale), int(bool(hflip)),
+        det, count = _lib.f32c(det), count.to(torch.int32).contiguous()   # locals: alive until the launch is queued
+        _lib.check(_lib.lib().hd_tta_map_back(_lib.ptr(det), _lib.ptr(count), B, det.shape[1], float(scale), int(bool(hflip)),
                                               float(view_w), self.img_w, self.img_h, _lib.ptr(self.bx), _lib.ptr(self.sc), _lib.ptr(self.lb),
                                               _lib.ptr(self.cnt), len(self.views), v, self.M, _lib.stream()))
 

@@ -66,6 +66,7 @@ def _levels(outputs, anchors, strides, host_ok=False, half_ok=False):
     return arr, keep, B, A, nc, total
 
 
+@_lib.on_device
 def decode_box(outputs, anchors=DEFAULT_ANCHORS, strides=DEFAULT_STRIDES):
     """list of [B, A*(5+nc), H, W] -> [B, sum(A*H*W), 5+nc] (cx,cy,w,h,obj,cls..) px (A.1)."""
     arr, keep, B, A, nc, total = _levels(outputs, anchors, strides)
@@ -160,22 +161,27 @@ class YoloPostprocessor:
     def __call__(self, outputs, peer=None, slot=0):
         """peer: a dist.PeerDetectionBuffers -- the NMS kernels then store every kept row into this rank's slice of the
         gather buffer of EVERY rank (posted NVLink stores), i.e. the all-gather is fused into the kernel epilogue."""
-        # the level table only depends on the pointers/shapes: rebuild it when they change
-        sig = tuple((x.data_ptr(), tuple(x.shape), x.dtype, x.is_contiguous()) for x in outputs)
+        # The level table only depends on the pointers/shapes, so it is reused while they do not change -- but ONLY when the
+        # kernel reads every level in place.  A level that had to be converted (non-contiguous view, mixed layouts) points at
+        # a private copy, which a later call with the same pointer and shape would read stale: those are converted every call.
+        sig = tuple((x.data_ptr(), tuple(x.shape), x.dtype, tuple(x.stride())) for x in outputs)
         if getattr(self, "_sig", None) != sig:
             self._lv = _levels(outputs, self.anchors, self.strides, host_ok=True, half_ok=True)
-            self._sig = sig
+            self._in_place = all(k is o for k, o in zip(self._lv[1], outputs))
+            self._sig = sig if self._in_place else None
         arr, keep, B, A, nc, total = self._lv
         self._dflag = _dtype_flag(keep)
         if self.one_call:
             return self._one_call(arr, keep, B, A, nc, total, peer, slot)
         if peer is not None:
             raise RuntimeError("replicated (peer) outputs need the one-call path")
-        buf = self.buffers(B, total, self._out_device(keep))
-        _lib.check(_lib.lib().hd_yolo_decode_filter(
-            arr, len(keep), B, A, nc, self.conf_thres, self.flags | self._dflag, _lib.ptr(buf.box), _lib.ptr(buf.score),
-            _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))
-        _run_nms(buf, self.iou_thres, self.class_mode, self.max_wh, self.max_nms)
+        dev = self._out_device(keep)
+        buf = self.buffers(B, total, dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().hd_yolo_decode_filter(
+                arr, len(keep), B, A, nc, self.conf_thres, self.flags | self._dflag, _lib.ptr(buf.box), _lib.ptr(buf.score),
+                _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))
+            _run_nms(buf, self.iou_thres, self.class_mode, self.max_wh, self.max_nms)
         return buf.det, buf.out_count, buf.idx
 
     def graph(self, outputs, warmup=3, peer=None, slot=0):
@@ -183,12 +189,16 @@ class YoloPostprocessor:
         replay() re-runs the captured kernels on whatever the input buffers hold -- no per-call host work."""
         for _ in range(warmup):
             self(outputs, peer, slot)
+        if not self._in_place:
+            raise RuntimeError("graph() needs heads the kernel reads in place (contiguous NCHW, channels_last fp32 or contiguous 16-bit): "
+                               "a converted copy would be frozen into the graph")
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             det, count, idx = self(outputs, peer, slot)
         return g.replay, det, count, idx
 
+    @_lib.on_device
     def candidates(self, outputs):
         """decode+filter only -> per image (cand [n,6], anchor idx [n]) sorted by anchor index (test helper)."""
         arr, keep, B, A, nc, total = _levels(outputs, self.anchors, self.strides, half_ok=True)
@@ -229,6 +239,7 @@ def postprocess(outputs, conf_thres=0.25, iou_thres=0.45, return_index=False, gr
     return _slice(det, count, idx, group_by_class) if return_index else _slice(det, count, None, group_by_class)
 
 
+@_lib.on_device
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000,
                         max_wh=7680.0, class_mode="offset", ge=False, return_index=False):
     """Lineage signature: decoded prediction [B, N, 5+nc] -> list of [k,6] (xyxy, conf, cls) (A.2)."""
@@ -245,3 +256,66 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, agnostic=Fa
     mode = _lib.NMS_AGNOSTIC if agnostic else _CLASS_MODES[class_mode]
     _run_nms(buf, iou_thres, mode, max_wh, max_nms)
     return _slice(buf.det, buf.out_count, buf.idx) if return_index else _slice(buf.det, buf.out_count)
+
+
+class PostprocessPipeline:
+    """Throughput mode: a `depth`-deep software pipeline of YoloPostprocessor steps over CUDA streams.
+
+    Step k runs on stream k % depth with its own workspace and output buffers, so the (latency-bound, few-SM) NMS kernels of
+    step k overlap the (HBM-bound) decode kernel of step k+1, and the drain of one decode grid is filled by the head of the next.
+    Every step is one CUDA-graph replay of the single C-ABI call.  `pool` is a list of input sets (each the list of head tensors of
+    one batch); step k reads pool[k % len(pool)].  With `peer` (dist.PeerDetectionBuffers with >= depth slots) the NMS kernels
+    store their rows into every rank's gather buffer and a cross-GPU barrier follows each step on the step's own stream.
+
+        pipe = PostprocessPipeline(pool, depth=2, conf_thres=0.25)
+        pipe.fork(); [pipe.step(k) for k in range(K)]; pipe.join()      # outputs of step k: pipe.outputs(k)
+    """
+
+    def __init__(self, pool, depth=2, peer=None, device=None, **pp_kwargs):
+        import math
+        self.pool, self.depth, self.peer = list(pool), int(depth), peer
+        first = self.pool[0][0]
+        self.device = torch.device(device) if device is not None else first.device
+        if peer is not None and peer.slots < self.depth:
+            raise RuntimeError("peer buffers need one slot per pipeline stage")
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(self.depth)]
+        self.pps = [YoloPostprocessor(device=self.device, **pp_kwargs) for _ in range(self.depth)]
+        self.n_graphs = len(self.pool) * self.depth // math.gcd(len(self.pool), self.depth)
+        self.replays, self.outs = [], []
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            for g in range(self.n_graphs):
+                c0 = L.hd_debug_launch_count()
+                rp, det, cnt, idx = self.pps[g % self.depth].graph(self.pool[g % len(self.pool)], warmup=2, peer=peer, slot=g % self.depth)
+                # launches of one step = what one capture recorded (2 warm-up calls + 1 captured call were counted)
+                self.launches_per_step = (L.hd_debug_launch_count() - c0) // 3
+                self.replays.append(rp)
+                self.outs.append((det, cnt, idx))
+        self._ev = torch.cuda.Event()
+
+    def fork(self):
+        """the pipeline streams wait for the work queued so far on the current stream"""
+        self._ev.record()
+        for s in self.streams:
+            s.wait_event(self._ev)
+
+    def step(self, k):
+        g = k % self.n_graphs
+        s = self.streams[g % self.depth]
+        with torch.cuda.stream(s):
+            self.replays[g]()
+            if self.peer is not None:
+                self.peer.barrier(channel=g % self.depth)
+        return self.outs[g]
+
+    def outputs(self, k):
+        return self.outs[k % self.n_graphs]
+
+    def stream_of(self, k):
+        return self.streams[(k % self.n_graphs) % self.depth]
+
+    def join(self):
+        """the current stream waits for every pipeline stream"""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)

@@ -62,6 +62,9 @@ HD_API int hd_version(void);
  * rpn_select_nms_kernel (which=1); host array of 16; synchronises the device */
 HD_API int hd_debug_phases(int which, long long* out16 /*host*/);
 HD_API const char* hd_last_error(void);
+/* kernels launched (or captured into a CUDA graph) by this library since it was loaded, over all threads and devices;
+ * callers take differences (bench.py reports the launches of one step as `gpu_launches`) */
+HD_API unsigned long long hd_debug_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * YOLOv5 head (README.md:9; lineage `decode_box` / `non_max_suppression`)
@@ -266,6 +269,10 @@ HD_API int hd_match(const float* gt_boxes, const int32_t* gt_count, int B, int G
 #define HD_RPN_SOFTMAX 1   /* 2-channel softmax objectness instead of 1-channel sigmoid */
 #define HD_RPN_CLAMP_DWH 2 /* clamp dw,dh to clamp_dwh before exp (torchvision bbox_xform_clip) */
 #define HD_RPN_KEY_LOGIT 4 /* sigmoid mode: keys[] order the raw logits instead of the probabilities (torchvision's per-level top-k) */
+#define HD_RPN_EXACT_MATH 8 /* sigmoid / softmax / exp(dw), exp(dh) are evaluated in fp64 and rounded once to fp32, i.e. the correctly
+                             * rounded fp32 value (up to ~1e-8 of the inputs): scores and boxes then do not depend on which libm /
+                             * SIMD exp produced them, so the whole decode -> top-k -> NMS chain is bit-reproducible against a CPU
+                             * that does the same (oracle `exact_math=True`).  Default (flag clear): fp32 expf, as the reference. */
 typedef struct {
     const float* objectness; /* device */
     const float* deltas;     /* device */

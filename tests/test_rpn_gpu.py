@@ -104,6 +104,23 @@ def test_end_to_end_agreement_with_oracle(cfg):
             assert close(rois[b, :n, 1:], r_roi)
 
 
+def test_end_to_end_bit_exact_with_exact_math(cfg):
+    """HD_RPN_EXACT_MATH on the device vs exact_math=True in the oracle: sigmoid / softmax / exp are the correctly rounded fp32
+    values on both sides, so decode -> top-k -> NMS -> top-n agrees in every index and every bit (both score modes)."""
+    import oracle
+    from heltondetection_b200 import rpn
+    obj, dlt, bases, mode = cfg
+    ref = oracle.rpn.rpn_proposals(obj, dlt, bases, (4, 8, 16, 32), (416, 416), score_mode=mode, exact_math=True, n_pre_nms=6000, n_post_nms=1000)
+    pr = rpn.RpnProposals(bases, (4, 8, 16, 32), (416, 416), score_mode=mode, n_pre_nms=6000, n_post_nms=1000, exact_math=True)
+    rois, cnt, osc, idx = pr([o.cuda() for o in obj], [d.cuda() for d in dlt])
+    rois = rois.view(2, 1000, 5)
+    for b in range(2):
+        r_roi, r_sc, r_idx = ref[b]
+        n = int(cnt[b].item())
+        assert torch.equal(idx[b, :n].cpu(), r_idx)
+        assert torch.equal(rois[b, :n, 1:].cpu(), r_roi) and torch.equal(osc[b, :n].cpu(), r_sc)
+
+
 def test_proposal_creator_lineage_signature(cfg):
     import oracle
     from heltondetection_b200 import rpn
