@@ -47,8 +47,9 @@ extern "C" HD_API int hd_version(void) { return 100; }
 
 int hd_phase_reader_nms(long long* out16);
 int hd_phase_reader_rpn(long long* out16);
+int hd_phase_reader_small(long long* out16);
 // developer aid: phase clocks of block 0 of the last sort_nms_kernel (which=0) / rpn_select_nms_kernel (which=1); synchronises
 extern "C" HD_API int hd_debug_phases(int which, long long* out16) {
     HD_CHECK_ARG(out16 != nullptr, "out16 is NULL");
-    return which == 1 ? hd_phase_reader_rpn(out16) : hd_phase_reader_nms(out16);
+    return which == 1 ? hd_phase_reader_rpn(out16) : (which == 2 ? hd_phase_reader_small(out16) : hd_phase_reader_nms(out16));
 }

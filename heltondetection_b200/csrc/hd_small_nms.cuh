@@ -65,6 +65,9 @@ __device__ __forceinline__ void hd_zero_tail(float* out_det, long long* out_idx,
 }
 __device__ __forceinline__ void hd_small_zero_tail(const HdNmsTail& q, int b, int kc) { hd_zero_tail(q.out_det, q.out_idx, q.rep, q.max_det, b, kc); }
 
+static __device__ long long hd_dbg_small[16];   // phase clocks of block 0 (developer aid, hd_debug_phases(2, ..))
+#define HD_SPHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) hd_dbg_small[i] = clock64(); } while (0)
+
 // returns false if the image is not handled here (n > HD_SMALL_N); all 256 threads must call
 __device__ __forceinline__ bool hd_small_nms_image(HdSmallSmem& sm, const HdNmsTail& q, int b, int cap, int n, const float4* cand_box,
                                                    const float* cand_score, const int* cand_cls, const int* cand_tie) {
@@ -77,6 +80,7 @@ __device__ __forceinline__ bool hd_small_nms_image(HdSmallSmem& sm, const HdNmsT
         return true;
     }
     const size_t off = (size_t)b * cap;
+    HD_SPHASE(0);
     // ---- 1. load (all loads independent)
     float4 bx[HD_SMALL_PER]; float sc[HD_SMALL_PER]; int cl[HD_SMALL_PER], tb[HD_SMALL_PER];
     unsigned long long key[HD_SMALL_PER];
@@ -97,16 +101,19 @@ __device__ __forceinline__ bool hd_small_nms_image(HdSmallSmem& sm, const HdNmsT
         if (i < n) sm.key[i] = key[u];
     }
     __syncthreads();
+    HD_SPHASE(1);
     // ---- 2. enumeration sort: composites are unique, rank = number of smaller composites
     int rank[HD_SMALL_PER];
 #pragma unroll
     for (int u = 0; u < HD_SMALL_PER; ++u) rank[u] = 0;
     const bool two = n > HD_SMALL_NT;   // block-uniform: does any thread own a second candidate
     if (!two) {
-        int r0 = 0;
-#pragma unroll 8
-        for (int j = 0; j < n; ++j) r0 += (sm.key[j] < key[0]);
-        rank[0] = r0;
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0, j = 0;   // four independent counters: the adds are not one dependency chain
+        for (; j + 4 <= n; j += 4) {
+            c0 += (sm.key[j] < key[0]); c1 += (sm.key[j + 1] < key[0]); c2 += (sm.key[j + 2] < key[0]); c3 += (sm.key[j + 3] < key[0]);
+        }
+        for (; j < n; ++j) c0 += (sm.key[j] < key[0]);
+        rank[0] = (c0 + c1) + (c2 + c3);
     } else {
         int r0 = 0, r1 = 0;
 #pragma unroll 8
@@ -114,7 +121,9 @@ __device__ __forceinline__ bool hd_small_nms_image(HdSmallSmem& sm, const HdNmsT
         rank[0] = r0; rank[1] = r1;
     }
     const int n_use = (q.max_nms > 0) ? min(n, q.max_nms) : n;
+    HD_SPHASE(2);
     // ---- 3. scatter the class-offset boxes to their rank, then the bitmask row of every rank
+    bool improper = false;
 #pragma unroll
     for (int u = 0; u < HD_SMALL_PER; ++u) {
         const int i = tid + u * HD_SMALL_NT;
@@ -126,13 +135,17 @@ __device__ __forceinline__ bool hd_small_nms_image(HdSmallSmem& sm, const HdNmsT
         if (i < n && rank[u] < n_use) {
             sm.box[rank[u]] = ob; sm.area[rank[u]] = hd_area(ob);
             sm.cls[rank[u]] = (q.class_mode == HD_NMS_CLASS_EXACT) ? cl[u] : 0;
+            improper |= !(fabsf(ob.x) < 3.0e38f && fabsf(ob.y) < 3.0e38f && fabsf(ob.z) < 3.0e38f && fabsf(ob.w) < 3.0e38f);   // NaN / inf
         }
     }
-    __syncthreads();
-    // mask words.  Warp `wid` owns the rows r = wid (mod 8); for word w its lanes hold the 32 boxes of rank 32w..32w+31 and
-    // every row costs one broadcast read + a branch-free overlap pre-test + a ballot; the exact IoU test (hd_iou_gt) only
-    // runs for the words in which some pair overlaps at all.  The pre-test is the kernel's own "inter == 0 -> not
-    // suppressed" rule (same fp32 subtraction), so it only rejects pairs the exact test rejects (NaN boxes included).
+    // (barrier + vote) any NaN/inf coordinate in the image -> the generic IoU test, whose min/max follow the CPU kernel's NaN rules
+    const bool generic = __syncthreads_or(improper) != 0;
+    HD_SPHASE(3);
+    // mask words.  Warp `wid` owns the rows r = wid (mod 8); for word w its lanes hold the 32 boxes of rank 32w..32w+31.  Per
+    // (row, word): one broadcast read, a branch-free overlap test and a ballot; only words in which some pair overlaps go on to
+    // the IoU test.  With finite coordinates fminf/fmaxf equal the CPU kernel's std::min/max, so the overlap extents ARE the
+    // intersection sides and the IoU test is inter, union, inter - thr*union against +-1e-5*union (hd_iou_gt's two-sided
+    // filter, same fp32 operations in the same order); the IEEE division only runs for borderline pairs.  Four rows per step.
     const bool exact = q.class_mode == HD_NMS_CLASS_EXACT;
     const bool pre = q.thr >= 0.0f;      // a negative threshold lets disjoint boxes (IoU 0) suppress: no pre-test then
     const int nwords = (n_use + 31) >> 5;
@@ -140,44 +153,74 @@ __device__ __forceinline__ bool hd_small_nms_image(HdSmallSmem& sm, const HdNmsT
         const int qr = w * 32 + lane;
         float4 qb = make_float4(0.f, 0.f, 0.f, 0.f); float qa = 0.f; int qc = 0;
         if (qr < n_use) { qb = sm.box[qr]; qa = sm.area[qr]; qc = sm.cls[qr]; }
-        for (int r = w * 32 + ((wid - w * 32) & 7); r < n_use; r += HD_SMALL_NT / 32) {
-            const float4 rb = sm.box[r];
-            bool ov = qr < r;
-            if (pre) ov = ov && (__fsub_rn(fminf(qb.z, rb.z), fmaxf(qb.x, rb.x)) > 0.0f) && (__fsub_rn(fminf(qb.w, rb.w), fmaxf(qb.y, rb.y)) > 0.0f);
-            if (exact) ov = ov && (qc == sm.cls[r]);
-            uint32_t m = __ballot_sync(HD_FULL, ov);
-            if (m) m = __ballot_sync(HD_FULL, ov && hd_iou_gt(qb, qa, rb, sm.area[r], q.thr));
-            if (lane == 0) sm.mask[w][r] = m;
+        for (int r0 = w * 32 + wid; r0 < n_use; r0 += 4 * (HD_SMALL_NT / 32)) {
+            float4 rb[4]; float ix[4], iy[4]; uint32_t m[4]; bool ov[4];
+            int rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                rr[u] = r0 + u * (HD_SMALL_NT / 32);
+                rb[u] = sm.box[min(rr[u], n_use - 1)];   // clamped duplicate rows are not stored
+            }
+            uint32_t any = 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ix[u] = __fsub_rn(fminf(qb.z, rb[u].z), fmaxf(qb.x, rb[u].x));
+                iy[u] = __fsub_rn(fminf(qb.w, rb[u].w), fmaxf(qb.y, rb[u].y));
+                bool o = qr < rr[u] && rr[u] < n_use;
+                if (pre && !generic) o = o && ix[u] > 0.0f && iy[u] > 0.0f;
+                if (exact) o = o && (qc == sm.cls[min(rr[u], n_use - 1)]);
+                ov[u] = o;
+                m[u] = __ballot_sync(HD_FULL, o);
+                any |= m[u];
+            }
+            if (any) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float ra = sm.area[min(rr[u], n_use - 1)];
+                    bool hit;
+                    if (generic) {
+                        hit = ov[u] && hd_iou_gt(qb, qa, rb[u], ra, q.thr);
+                    } else {
+                        const float inter = __fmul_rn(fmaxf(ix[u], 0.0f), fmaxf(iy[u], 0.0f));
+                        const float uni = __fsub_rn(__fadd_rn(qa, ra), inter);
+                        const float d = __fsub_rn(inter, __fmul_rn(q.thr, uni));
+                        const float tol = 1.0e-5f * uni;
+                        const bool ranged = uni > 0.0f && uni < 3.0e38f;
+                        hit = ov[u] && ranged && d > tol;
+                        const bool border = ov[u] && !(ranged && (d > tol || d < -tol));
+                        if (__any_sync(HD_FULL, border)) { if (border) hit = __fdiv_rn(inter, uni) > q.thr; }
+                    }
+                    m[u] = __ballot_sync(HD_FULL, hit);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (lane == u && rr[u] < n_use) sm.mask[w][rr[u]] = m[u];
         }
     }
     __syncthreads();
+    HD_SPHASE(4);
     // ---- 4. warp 0: greedy keep set, 32 ranks per round
     const int max_det = q.max_det > 0 ? q.max_det : n_use;
     if (wid == 0) {
-        uint32_t kw[HD_SMALL_W];
-#pragma unroll
-        for (int w = 0; w < HD_SMALL_W; ++w) kw[w] = 0u;
         const int rounds = (n_use + 31) >> 5;
         int total = 0;
         for (int rd = 0; rd < rounds; ++rd) {
             const int r = rd * 32 + lane;
             const bool valid = r < n_use;
-            bool dead = false;
-#pragma unroll
-            for (int w = 0; w < HD_SMALL_W; ++w)
-                if (w < rd && valid) dead |= (sm.mask[w][r] & kw[w]) != 0u;
+            uint32_t hit = 0u;
+            if (valid)
+                for (int w = 0; w < rd; ++w) hit |= sm.mask[w][r] & sm.kept[w];   // kept words of the earlier rounds (broadcast reads)
             const uint32_t self = valid ? sm.mask[rd][r] : 0u;
-            const bool alive = valid && !dead;
+            const bool alive = valid && hit == 0u;
             uint32_t k = __ballot_sync(HD_FULL, alive);
             for (int it = 0; it < 32; ++it) {
                 const uint32_t nk = __ballot_sync(HD_FULL, alive && !(self & k));
                 if (nk == k) break;
                 k = nk;
             }
-#pragma unroll
-            for (int w = 0; w < HD_SMALL_W; ++w)
-                if (w == rd) kw[w] = k;
             if (lane == 0) sm.kept[rd] = k;
+            __syncwarp();
             total += __popc(k);
             if (total >= max_det) {   // later ranks cannot be output: stop (their kept words read as zero)
                 for (int w = rd + 1 + lane; w < HD_SMALL_W; w += 32) sm.kept[w] = 0u;
@@ -187,6 +230,7 @@ __device__ __forceinline__ bool hd_small_nms_image(HdSmallSmem& sm, const HdNmsT
         if (lane == 0) sm.kc = min(total, max_det);
     }
     __syncthreads();
+    HD_SPHASE(5);
     const int kc = sm.kc;
     // ---- 5. kept candidates write their row from registers
 #pragma unroll
@@ -214,6 +258,8 @@ __device__ __forceinline__ bool hd_small_nms_image(HdSmallSmem& sm, const HdNmsT
     }
     if (tid == 0) q.out_count[b] = kc;
     if (tid < q.rep.n) q.rep.cnt[tid][b] = kc;
+    HD_SPHASE(6);
     hd_small_zero_tail(q, b, kc);
+    HD_SPHASE(7);
     return true;
 }

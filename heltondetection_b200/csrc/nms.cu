@@ -34,11 +34,19 @@ struct NmsParams {
     int sort_off, bitonic_cap;  // dynamic smem: word offset of the in-smem sort area and its capacity (0 = disabled)
     HdRep rep;
     const int* only;            // nullable: run only the images whose flag is set (images the cluster kernel hands back)
+    unsigned* hint;             // nullable: mapped host word that receives `call_id` when some image takes this (large) path
+    unsigned call_id;
 };
 
-__global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_constant__ NmsParams p) {
+// NT = 1024: one whole SM per image (64 K registers, ~190 KB shared memory) -- the fast configuration for dense scenes.
+// NT = 256 ("light"): the same algorithm in a CTA that fits beside the decode kernel's CTAs.  Launching the 1024-thread variant
+// for a batch that has no large image still needs B empty SMs, i.e. it drains whatever else is running -- fatal for the
+// software-pipelined small-batch steps -- so the host launches the light variant while recent calls saw no large image
+// (see nms_large_recent below); either variant returns the same bits.
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) sort_nms_kernel(const __grid_constant__ NmsParams p) {
     extern __shared__ uint32_t removed[];  // ceil(cap/32)+4 words, (+pad)
-    __shared__ HdSortSmem<NMS_NT> ssm;
+    __shared__ HdSortSmem<NT> ssm;
     __shared__ HdNmsSmem nsm;
     __shared__ HdGridSmem gsm;
 
@@ -53,6 +61,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
         hd_zero_tail(p.out_det, p.out_idx, p.rep, p.max_det, b, 0);
         return;
     }
+    if (p.hint && tid == 0) *reinterpret_cast<volatile unsigned*>(p.hint) = p.call_id;   // "this call had a large image"
     const size_t off = (size_t)b * p.cap;
     uint64_t* k0 = p.k0 + off; uint64_t* k1 = p.k1 + off;
     uint32_t* v0 = p.v0 + off; uint32_t* v1 = p.v1 + off;
@@ -67,7 +76,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
         unsigned long long* skey = reinterpret_cast<unsigned long long*>(removed + p.sort_off);
         uint32_t* sval = reinterpret_cast<uint32_t*>(skey + p.bitonic_cap);
         const int N = hd_bitonic_padded(n);
-        for (int i = tid; i < N; i += NMS_NT) {
+        for (int i = tid; i < N; i += NT) {
             if (i < n) {
                 const uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + i] : (uint32_t)i;
                 skey[i] = ((uint64_t)(~hd_orderable(p.scores[off + i])) << 32) | tb;
@@ -79,26 +88,28 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
         }
         __syncthreads();
         HD_PHASE(2);
-        if (N == 2048) hd_cta_bitonic_reg<2, true>(skey, sval);
-        else if (N == 4096) hd_cta_bitonic_reg<4, true>(skey, sval);
-        else hd_cta_bitonic_reg<8, true>(skey, sval);
+        if (NT == 1024) {   // (bitonic_cap is 0 for the light variant: the register-blocked network needs 1024 threads)
+            if (N == 2048) hd_cta_bitonic_reg<2, true>(skey, sval);
+            else if (N == 4096) hd_cta_bitonic_reg<4, true>(skey, sval);
+            else hd_cta_bitonic_reg<8, true>(skey, sval);
+        }
         order = sval;
     } else {
-        for (int i = tid; i < n; i += NMS_NT) {
+        for (int i = tid; i < n; i += NT) {
             uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + i] : (uint32_t)i;
             k0[i] = ((uint64_t)(~hd_orderable(p.scores[off + i])) << 32) | tb;
             v0[i] = (uint32_t)i;
         }
         __syncthreads();
         HD_PHASE(2);
-        const int res = hd_cta_radix_sort<NMS_NT>(k0, v0, k1, v1, n, ssm);
+        const int res = hd_cta_radix_sort<NT>(k0, v0, k1, v1, n, ssm);
         order = res ? v1 : v0;
     }
     HD_PHASE(3);
 
     const int n_use = (p.max_nms > 0) ? min(n, p.max_nms) : n;
     const int max_det = (p.max_det > 0) ? p.max_det : n_use;
-    for (int r = tid; r < n_use; r += NMS_NT) {
+    for (int r = tid; r < n_use; r += NT) {
         const uint32_t slot = order[r];
         float4 bx = p.boxes[off + slot];
         int c = p.cls ? p.cls[off + slot] : 0;
@@ -115,14 +126,15 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_kernel(const __grid_consta
     int kc;
     if (n_use > HD_GRID_MIN_N && p.thr > 0.05f) {
         // big segment: spatially pruned pass; buckets alias the (finished) sort scratch, items use the free key buffer
-        kc = hd_cta_greedy_nms_grid<NMS_NT, int>(sbox, clsp, n_use, max_det, p.thr, removed, keep_r, nsm, gsm, &ssm.warp_cnt[0][0], 12,
-                                                 p.gitem + off);
+        // buckets alias the sort scratch: (NT/32)*256 ints -> 4096 buckets for the 1024-thread CTA, 1024 for the light one
+        kc = hd_cta_greedy_nms_grid<NT, int>(sbox, clsp, n_use, max_det, p.thr, removed, keep_r, nsm, gsm, &ssm.warp_cnt[0][0],
+                                                 NT == 1024 ? 12 : 10, p.gitem + off);
     } else {
-        kc = hd_cta_greedy_nms<NMS_NT, int>(sbox, clsp, n_use, max_det, p.thr, removed, keep_r, nsm);
+        kc = hd_cta_greedy_nms<NT, int>(sbox, clsp, n_use, max_det, p.thr, removed, keep_r, nsm);
     }
 
     HD_PHASE(5);
-    for (int q = tid; q < kc; q += NMS_NT) {
+    for (int q = tid; q < kc; q += NT) {
         const int r = keep_r[q];
         const uint32_t slot = order[r];
         if (p.out_det) {
@@ -161,6 +173,12 @@ struct NmsClParams {
 };
 
 __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_cluster_kernel(const __grid_constant__ NmsClParams q) {
+    if (q.s.hint && threadIdx.x == 0 && blockIdx.x == 0) {   // any image beyond the small kernel's range -> the call was "large"
+        for (int b = 0; b < q.s.B; ++b) {
+            const int nb = q.s.counts ? min(q.s.counts[b], q.s.cap) : q.s.n_fixed;
+            if (nb > HD_SMALL_N) { *reinterpret_cast<volatile unsigned*>(q.s.hint) = q.s.call_id; break; }
+        }
+    }
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ HdClSmem csm;
     cg::cluster_group cluster = cg::this_cluster();
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(NMS_NT, 1) sort_nms_cluster_kernel(const __gri
 }
 
 // small-image variant: 256 threads, everything in shared memory, several images per SM at once
-__global__ void __launch_bounds__(HD_SMALL_NT) small_nms_kernel(const __grid_constant__ NmsParams p, const __grid_constant__ HdNmsTail q) {
+__global__ void __launch_bounds__(HD_SMALL_NT, 2) small_nms_kernel(const __grid_constant__ NmsParams p, const __grid_constant__ HdNmsTail q) {
     __shared__ HdSmallSmem ssm;
     const int b = blockIdx.x;
     const int n = p.counts ? min(__ldcg(p.counts + b), p.cap) : p.n_fixed;
@@ -294,7 +312,41 @@ __global__ void __launch_bounds__(256) box_iou_kernel(const float4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ host
-// developer/test knob (process-wide, atomic): 0 auto, 1 one CTA per image only, 2 cluster kernel whenever the batch allows
+// ---- "did a recent call have a large image?"  One mapped host word per (device, workspace-hash slot): the large-path kernels
+// store the call id there (a posted write over PCIe), the host reads it at the next call without synchronising.  The answer only
+// selects between kernels that return identical bits, so a stale value costs time, never correctness.
+#include <mutex>
+#define NMS_HINT_SLOTS 256
+static unsigned* g_hint_host[HD_MAX_DEVICES];
+static unsigned* g_hint_dev[HD_MAX_DEVICES];
+static unsigned g_hint_calls[HD_MAX_DEVICES][NMS_HINT_SLOTS];
+static std::mutex g_hint_mutex;
+static bool nms_hint_slot(const void* workspace, cudaStream_t st, unsigned** dev_word, unsigned* call_id, bool* large_recent) {
+    const int d = hd_current_device();
+    if (d < 0 || d >= HD_MAX_DEVICES) return false;
+    std::lock_guard<std::mutex> lock(g_hint_mutex);
+    if (!g_hint_host[d]) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
+        void* h = nullptr; void* dv = nullptr;
+        if (cudaHostAlloc(&h, NMS_HINT_SLOTS * sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+            cudaHostGetDevicePointer(&dv, h, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+        memset(h, 0, NMS_HINT_SLOTS * sizeof(unsigned));
+        for (int i = 0; i < NMS_HINT_SLOTS; ++i) g_hint_calls[d][i] = 1000u;
+        g_hint_dev[d] = (unsigned*)dv;
+        g_hint_host[d] = (unsigned*)h;
+    }
+    const unsigned slot = (unsigned)((((uintptr_t)workspace) >> 8) * 2654435761u) % NMS_HINT_SLOTS;
+    const unsigned last_big = *reinterpret_cast<volatile unsigned*>(g_hint_host[d] + slot);
+    const unsigned prev = g_hint_calls[d][slot];
+    *large_recent = (prev - last_big) < 8u;          // one of the last 8 calls through this workspace reported a large image
+    *call_id = ++g_hint_calls[d][slot];
+    *dev_word = g_hint_dev[d] + slot;
+    return true;
+}
+
+// developer/test knob (process-wide, atomic): 0 auto, 1 one CTA per image only, 2 cluster kernel whenever the batch allows,
+// 3 light (256-thread) large-image kernel always, 4 heavy (1024-thread, no clusters unless the batch allows) always
 static int g_nms_mode = 0;
 extern "C" HD_API int hd_nms_set_mode(int mode) { return __atomic_exchange_n(&g_nms_mode, mode, __ATOMIC_ACQ_REL); }
 static int nms_cluster_capacity(int CL) {
@@ -415,7 +467,17 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
     p.sort_off = (int)words;
     p.bitonic_cap = 8192;
     size_t smem = words * 4 + (size_t)p.bitonic_cap * 12;
-    HD_ENSURE_SMEM(sort_nms_kernel, 186 * 1024);
+    HD_ENSURE_SMEM(sort_nms_kernel<1024>, 186 * 1024);
+    // heavy or light large-image kernels?  (auto: light until a recent call through this workspace saw a large image)
+    const int mode = __atomic_load_n(&g_nms_mode, __ATOMIC_ACQUIRE);
+    bool heavy = true;
+    p.hint = nullptr; p.call_id = 0;
+    if (counts != nullptr && min_n < 0) {   // variable-length segments: worth remembering what the data looks like
+        bool recent = true;
+        if (nms_hint_slot(workspace, st, &p.hint, &p.call_id, &recent)) heavy = recent;
+    }
+    if (mode == 3) heavy = false;
+    else if (mode != 0) heavy = true;
     if (min_n < 0 && (counts != nullptr || n_fixed <= HD_SMALL_N)) {
         // images with <= HD_SMALL_N candidates: shared-memory kernel; the radix-sort kernel below then only
         // works on the larger ones (it returns at once for the rest)
@@ -429,6 +491,13 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
         if (counts == nullptr) return HD_OK;
     }
     p.only = nullptr;
+    if (!heavy) {
+        // light variant: 256 threads, radix sort through the global scratch, 1024-bucket pruning grid; co-resident with other kernels
+        p.bitonic_cap = 0;
+        sort_nms_kernel<256><<<B, 256, words * 4, st>>>(p);
+        HD_CUDA_LAUNCH_CHECK("sort_nms_kernel<256>");
+        return HD_OK;
+    }
     const int CL = nms_cluster_size(B);
     if (CL) {
         NmsClParams q;
@@ -452,7 +521,7 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
         hd_count_launch();
         p.only = q.fallback;
     }
-    sort_nms_kernel<<<B, NMS_NT, smem, st>>>(p);
+    sort_nms_kernel<1024><<<B, NMS_NT, smem, st>>>(p);
     HD_CUDA_LAUNCH_CHECK("sort_nms_kernel");
     return HD_OK;
 }
@@ -475,3 +544,4 @@ extern "C" HD_API int hd_box_iou(const float* boxes1, int64_t N, const float* bo
 }
 
 HD_DEFINE_PHASE_READER(hd_phase_reader_nms)
+int hd_phase_reader_small(long long* out16) { HD_CUDA_CALL(cudaDeviceSynchronize()); HD_CUDA_CALL(cudaMemcpyFromSymbol(out16, hd_dbg_small, sizeof(long long) * 16)); return HD_OK; }
