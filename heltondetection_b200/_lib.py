@@ -83,6 +83,8 @@ SIGNATURES = {
     "hd_wbf": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_double), _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hd_tta_map_back": (_i, [_vp, _vp, _i, _i, _f, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hd_roi_align": (_i, [C.POINTER(RoiLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
+    "hd_roi_align_workspace_size": (_sz, [C.POINTER(RoiLevel), _i, _i, _i, _i64, _i, _i, _i]),
+    "hd_roi_align_ws": (_i, [C.POINTER(RoiLevel), _i, _i, _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "hd_roi_pool": (_i, [C.POINTER(RoiLevel), _i, _i, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "hd_roi_set_mode": (_i, [_i]),
     "hd_roi_pool_backward": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -9,53 +9,8 @@
 // 16*grid^2/4 corner reads of the sample-by-sample form.  The [C,PH,PW] result tile is assembled in
 // shared memory in exactly the output layout and leaves with ONE TMA bulk store (cp.async.bulk).
 #include "hd_common.cuh"
-
-#define ROI_MAX_LEVELS HD_MAX_LEVELS
-#define ROI_TAB 1024  // table entries per axis
-
-struct RoiParams {
-    const float* data[ROI_MAX_LEVELS];
-    int H[ROI_MAX_LEVELS], W[ROI_MAX_LEVELS];
-    float scale[ROI_MAX_LEVELS];
-    int n_levels, C, PH, PW, sampling_ratio, aligned;
-    const float* rois;       // [K,5]
-    const int* level_ids;    // [K] or NULL (level 0)
-    long long K;
-    float* out;              // [K,C,PH,PW]
-    int* argmax;             // roi_pool only, nullable
-};
-
-struct AxisEntry { int off; float w; };  // off = cell index premultiplied by the element stride of the axis
-
-// Per-axis table of one RoI: bin b owns entries [b*stride, b*stride + cnt[b]).  Sample positions grow
-// monotonically inside a bin, so a cell that was already emitted is one of the last two entries.
-__device__ __forceinline__ void build_axis(AxisEntry* tab, int* cnt, int b, int stride, float start, float bin_size, int grid,
-                                           int extent, int elem_stride, int pad_to) {
-    int n = 0;
-    AxisEntry* t = tab + b * stride;
-    auto add = [&](int cell, float w) {
-        const int off = cell * elem_stride;
-        if (n >= 1 && t[n - 1].off == off) t[n - 1].w = __fadd_rn(t[n - 1].w, w);
-        else if (n >= 2 && t[n - 2].off == off) t[n - 2].w = __fadd_rn(t[n - 2].w, w);
-        else { t[n].off = off; t[n].w = w; ++n; }
-    };
-    for (int i = 0; i < grid; ++i) {
-        // y = roi_start + ph*bin_size + (iy + .5f) * bin_size / grid   (fp32, left to right)
-        float y = __fadd_rn(__fadd_rn(start, __fmul_rn((float)b, bin_size)),
-                            __fdiv_rn(__fmul_rn(__fadd_rn((float)i, 0.5f), bin_size), (float)grid));
-        if (y < -1.0f || y > (float)extent) continue;  // sample contributes 0 (C++/CUDA kernel rule)
-        if (y <= 0.0f) y = 0.0f;
-        int lo = (int)y, hi;
-        if (lo >= extent - 1) { hi = lo = extent - 1; y = (float)lo; } else hi = lo + 1;
-        const float l = __fsub_rn(y, (float)lo), h = __fsub_rn(1.0f, l);
-        add(lo, h);
-        add(hi, l);
-    }
-    cnt[b] = n;
-    // pad with zero-weight duplicates of a real cell so the consumer can run fixed-trip-count loops
-    const int dup = n > 0 ? t[n - 1].off : 0;
-    for (int i = n; i < pad_to; ++i) { t[i].off = dup; t[i].w = 0.0f; }
-}
+#include "hd_roi_axis.cuh"
+#include "hd_roi_internal.cuh"
 
 // one bin row with compile-time entry counts: all E*E loads of a bin are independent and issued together
 template <int E>
@@ -265,7 +220,10 @@ __global__ void __launch_bounds__(256, EFIX == 4 ? 4 : 3) roi_align_nhwc_quad_ke
     AxisEntry* xtab = ytab + tab;                           // tab entries per axis (host: small when sampling_ratio is fixed)
     __shared__ int ycnt[64], xcnt[64];
 
-    const long long k = blockIdx.x;
+    // one RoI per CTA, or (p.list) a grid-stride walk over a device-side list of RoI indices
+    const long long nk = p.list ? (long long)*p.list_count : p.K;
+    for (long long kk = blockIdx.x; kk < nk; kk += gridDim.x) {
+    const long long k = p.list ? (long long)p.list[kk] : kk;
     const float* roi = p.rois + k * 5;
     const int lvl = p.level_ids ? p.level_ids[k] : 0;
     const int H = p.H[lvl], W = p.W[lvl];
@@ -369,6 +327,8 @@ __global__ void __launch_bounds__(256, EFIX == 4 ? 4 : 3) roi_align_nhwc_quad_ke
         }
     }
     tile_store(p.out + (size_t)k * p.C * nb, tile, p.C * nb, use_tma != 0);
+    __syncthreads();   // the tile and the tables are rewritten by the next RoI of the walk
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ RoIAlign NHWC, staged rows
@@ -903,6 +863,8 @@ static int fill_roi(RoiParams& p, const hd_roi_level* levels, int n_levels, int 
 static int g_roi_mode_ = 0;   // developer/test knob (process-wide, atomic)
 extern "C" HD_API int hd_roi_set_mode(int mode) { return __atomic_exchange_n(&g_roi_mode_, mode, __ATOMIC_ACQ_REL); }
 
+int hd_roi_mode(void) { return __atomic_load_n(&g_roi_mode_, __ATOMIC_ACQUIRE); }
+
 static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st) {
     if (p.K == 0) return HD_OK;
     const int g_roi_mode = __atomic_load_n(&g_roi_mode_, __ATOMIC_ACQUIRE);
@@ -965,6 +927,26 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
     } else {
         HD_FAIL(HD_ERR_INVALID, "layout must be HD_LAYOUT_NCHW or HD_LAYOUT_NHWC, got %d", layout);
     }
+    return HD_OK;
+}
+
+int hd_roi_align_launch_list(const RoiParams& p0, const int* list, const int* list_count, int ctas, cudaStream_t st) {
+    RoiParams p = p0;
+    p.list = list; p.list_count = list_count;
+    const size_t tile = (size_t)p.C * p.PH * p.PW * 4;
+    const int mx = p.PH > p.PW ? p.PH : p.PW;
+    int tab = (p.sampling_ratio > 0 && p.sampling_ratio <= 8) ? 16 * mx : ROI_TAB;
+    if (tab > ROI_TAB) tab = ROI_TAB;
+    const size_t smem_quad = tile + 2 * (size_t)tab * sizeof(AxisEntry);
+    HD_CHECK_ARG(p.C % 4 == 0 && smem_quad <= 220 * 1024, "list launch needs C %% 4 == 0 and a tile that fits shared memory");
+    const int use_tma = (tile % 16 == 0) && (((uintptr_t)p.out & 15) == 0);
+    int nq = p.C / 4, QT = 8;
+    while (QT < nq && QT < 256) QT <<= 1;
+    HD_ENSURE_SMEM(roi_align_nhwc_quad_kernel<4>, 220 * 1024);
+    HD_ENSURE_SMEM(roi_align_nhwc_quad_kernel<0>, 220 * 1024);
+    if (tab < ROI_TAB && p.sampling_ratio >= 1 && p.sampling_ratio <= 2) roi_align_nhwc_quad_kernel<4><<<(unsigned)ctas, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+    else roi_align_nhwc_quad_kernel<0><<<(unsigned)ctas, 256, tile + 2 * (size_t)ROI_TAB * sizeof(AxisEntry), st>>>(p, use_tma, QT, ROI_TAB);
+    HD_CUDA_LAUNCH_CHECK("roi_align_nhwc_quad_kernel (list)");
     return HD_OK;
 }
 

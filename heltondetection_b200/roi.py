@@ -54,6 +54,20 @@ def _prepare_level(x, K, layout):
     return _lib.f32c(x), _lib.LAYOUT_NCHW
 
 
+_WS = {}
+
+
+def _workspace(device, nbytes):
+    """scratch for hd_roi_align_ws, one buffer per (device, stream): calls on different streams must not share it"""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        if len(_WS) > 16:
+            _WS.clear()
+        buf = _WS[key] = torch.empty((max(int(nbytes), 256),), dtype=torch.uint8, device=device)
+    return buf
+
+
 def _levels_struct(tensors, scales):
     arr = (_lib.RoiLevel * len(tensors))()
     for l, (t, s) in enumerate(zip(tensors, scales)):
@@ -90,8 +104,12 @@ def _run(features, scales, rois, level_ids, output_size, sampling_ratio, aligned
         _lib.check(L.hd_roi_pool(arr, len(prepared), lay, C, _lib.ptr(rois), _lib.ptr(lid), K, PH, PW, _lib.ptr(out),
                                  _lib.ptr(argmax), _lib.stream()))
     else:
-        _lib.check(L.hd_roi_align(arr, len(prepared), lay, C, _lib.ptr(rois), _lib.ptr(lid), K, PH, PW, int(sampling_ratio),
-                                  int(bool(aligned)), _lib.ptr(out), _lib.stream()))
+        # batch size + workspace: many RoIs on NHWC features take the streamed (TMA ring) kernel, everything else the per-RoI kernels
+        B = int(features[0].shape[0])
+        ws_bytes = L.hd_roi_align_workspace_size(arr, len(prepared), C, B, K, PH, PW, int(sampling_ratio))
+        ws = _workspace(out.device, ws_bytes)
+        _lib.check(L.hd_roi_align_ws(arr, len(prepared), lay, C, B, _lib.ptr(rois), _lib.ptr(lid), K, PH, PW, int(sampling_ratio),
+                                     int(bool(aligned)), _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream()))
     return (out, argmax) if return_argmax else out
 
 

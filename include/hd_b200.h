@@ -172,6 +172,18 @@ typedef struct {
 HD_API int hd_roi_align(const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, const float* rois,
                         const int32_t* level_ids, int64_t K, int pooled_h, int pooled_w, int sampling_ratio, int aligned,
                         float* out, void* stream);
+
+/* The same operation with the batch size and a caller workspace (hd_roi_align_workspace_size bytes; the answer depends only on
+ * the shapes).  For many RoIs on NHWC features (C % 32 == 0, output <= 7x7, 1 <= sampling_ratio <= 2) this runs the STREAMED
+ * kernel (csrc/roi_strip.cu): RoIs are bucketed by (image, level, x-strip) and sorted by their first feature row on the device, and
+ * every bucket's rows cross L2->SM once through a TMA-fed shared-memory ring, instead of once per RoI.  Every other case (and any
+ * RoI the strips cannot take) is computed by the per-RoI kernels of hd_roi_align; results are the same values either way.
+ * Replaces: torchvision MultiScaleRoIAlign / roi_align call site (poolers.py:147-227, roi_align.py:204-260; README.md:65). */
+HD_API size_t hd_roi_align_workspace_size(const hd_roi_level* levels /*host*/, int n_levels, int C, int batch, int64_t K, int pooled_h,
+                                          int pooled_w, int sampling_ratio);
+HD_API int hd_roi_align_ws(const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, int batch, const float* rois,
+                           const int32_t* level_ids, int64_t K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, float* out,
+                           void* workspace, size_t workspace_bytes, void* stream);
 /* argmax (int32 [K,C,PH,PW], index h*W+w inside the channel plane, -1 for an empty bin) may be NULL. */
 HD_API int hd_roi_pool(const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, const float* rois,
                        const int32_t* level_ids, int64_t K, int pooled_h, int pooled_w, float* out, int32_t* argmax,
