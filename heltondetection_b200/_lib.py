@@ -15,12 +15,13 @@ HD_MAX_LEVELS = 8
 HD_MAX_ANCHORS = 8
 FLAG_CONF_GE = 1
 FLAG_DENSE_READ = 2
+FLAG_MULTI_LABEL = 256
 NMS_AGNOSTIC, NMS_CLASS_EXACT, NMS_CLASS_OFFSET = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 RPN_SOFTMAX, RPN_CLAMP_DWH, RPN_KEY_LOGIT, RPN_EXACT_MATH = 1, 2, 4, 8
 ROIHEAD_MUL_STD, ROIHEAD_CLAMP_DWH, ROIHEAD_LABEL_MINUS1 = 16, 32, 64
 BOX_XYWH = 1
-WBF_AVG, WBF_MAX = 0, 1
+WBF_AVG, WBF_MAX, WBF_BOX_AND_MODEL_AVG, WBF_ABSENT_MODEL_AWARE_AVG, WBF_RESCALE_SUM_WEIGHTS = 0, 1, 2, 3, 256
 
 
 class YoloLevel(C.Structure):
@@ -52,6 +53,7 @@ SIGNATURES = {
     "hd_last_error": (C.c_char_p, []),
     "hd_debug_phases": (_i, [_i, C.POINTER(C.c_longlong)]),
     "hd_debug_launch_count": (C.c_ulonglong, []),
+    "hd_debug_roi_profile": (_i, [_i, C.POINTER(C.c_ulonglong)]),
     "hd_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _vp, _vp]),
     "hd_yolo_decode_filter": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "hd_yolo_postprocess_workspace_size": (_sz, [_i, _i]),

@@ -18,7 +18,7 @@
 #include "hd_roi_internal.cuh"
 #include <cuda.h>
 
-#define RS_NCW 8                       // consumer warps
+#define RS_NCW 11                      // consumer warps (13 warps x 152 registers fill the register file)
 #define RS_THREADS ((RS_NCW + 1) * 32)
 #define RS_CS 32                       // channels per slice (= lanes)
 #define RS_P 7                         // PH, PW <= 7
@@ -28,15 +28,16 @@
 #define RS_MAXH 1024                   // feature-map height bound of the per-bucket counting sort
 
 struct RsLevel { int H, W, SW, S, RW, unit_base; float scale; };
-struct RsItem { int k, pr, y0, y1; };  // RoI index, bin rows [pr & 255, pr >> 8), first / last feature row
+struct RsItem { int k, pr, y0, y1; };  // RoI index, bin rows [pr & 255, (pr >> 8) & 255) and bucket << 16, first / last feature row
 
 struct RsParams {
     RsLevel lv[HD_MAX_LEVELS];
     int n_levels, C, PH, PW, sr, aligned, B, NR, units_per_img, n_units;
     const float* rois; const int* level_ids; long long K; float* out;
     int* unit_count; int* unit_start; int* unit_cursor; int* unit_ymax;
-    RsItem* tmp; int* tmp_unit; RsItem* scat; RsItem* items;
+    RsItem* tmp; int* tmp_unit; RsItem* scat; RsItem* items; int* tables;
     int* n_tmp; int* fb_count; int* fb_list;
+    unsigned long long* prof;   // nullable developer counters: [0] table cycles [1] wait cycles [2] row-loop cycles [3] output cycles [4] items [5] producer wait
 };
 struct RsMaps { CUtensorMap m[HD_MAX_LEVELS]; };
 
@@ -110,10 +111,10 @@ __global__ void __launch_bounds__(256) rs_prep_kernel(const __grid_constant__ Rs
     atomicMax(p.unit_ymax + unit, split ? max(yb, yd) : yb);
     RsItem it;
     it.k = (int)k;
-    it.pr = split ? (split << 8) : (p.PH << 8); it.y0 = ya; it.y1 = yb;
+    it.pr = (split ? (split << 8) : (p.PH << 8)) | (unit << 16); it.y0 = ya; it.y1 = yb;
     p.tmp[at] = it; p.tmp_unit[at] = unit;
     if (split) {
-        it.pr = split | (p.PH << 8); it.y0 = yc; it.y1 = yd;
+        it.pr = split | (p.PH << 8) | (unit << 16); it.y0 = yc; it.y1 = yd;
         p.tmp[at + 1] = it; p.tmp_unit[at + 1] = unit;
     }
 }
@@ -190,13 +191,57 @@ __device__ __forceinline__ void rs_tma_row(void* sdst, const CUtensorMap* map, i
                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-struct RsWarpTab {
-    AxisEntry xt[RS_P * RS_E], yt[RS_P * RS_E];
-    int xc[8], yc[8];
-    float rec_w[RS_MAXROWS][RS_P];
-    unsigned char rec_ph[RS_MAXROWS][8];
-    unsigned char rec_n[RS_MAXROWS];
-};
+// Per-item table (RS_TABW words, built once per item by rs_table_kernel and shared by the C/32 slice CTAs):
+//   [0,28)   xo   ring-row float offset of x entry (pw*4 + e): (cell - strip start) * 32        (0 for unused entries)
+//   [28,56)  wx   merged weight of that entry                                                    (0 for unused entries)
+//   [56,63)  nx   entries of bin column pw;   [63] number of (row, bin-row) pairs
+//   [64,92)  code (row - y0) << 8 | ph, sorted by row;   [92,120) weight of the pair
+//   [120,124) k, p0 | p1 << 8, y0, y1
+#define RS_TABW 128
+#define RS_NTILE 6                     // output tiles shared by the consumer warps (taken with a shared-memory lock)
+
+// one warp per item: the separable tables of roi.cu (build_axis) turned into the layout above
+__global__ void __launch_bounds__(256) rs_table_kernel(const __grid_constant__ RsParams p) {
+    __shared__ AxisEntry xt[8][RS_P * RS_E], yt[8][RS_P * RS_E];
+    __shared__ int xc[8][8], yc[8][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 8 + w;
+    if (i >= *p.n_tmp) return;
+    const RsItem it = p.items[i];
+    const int p0 = it.pr & 255, p1 = (it.pr >> 8) & 255, unit = it.pr >> 16;
+    const RsGeom G = rs_geom(p, it.k);
+    const RsLevel& L = p.lv[G.lvl];
+    const int xs = (unit % p.units_per_img - L.unit_base) * L.SW;
+    if (lane < p.PH) build_axis(yt[w], yc[w], lane, RS_E, G.sh, G.bh, G.g, L.H, 1, 0);
+    else if (lane >= 8 && lane < 8 + p.PW) build_axis(xt[w], xc[w], lane - 8, RS_E, G.sw, G.bw, G.g, L.W, 1, 0);
+    __syncwarp();
+    int* tab = p.tables + (size_t)i * RS_TABW;
+    if (lane < RS_P * RS_E) {
+        const int pw = lane / RS_E, e = lane - pw * RS_E;
+        const bool on = pw < p.PW && e < xc[w][pw];
+        tab[lane] = on ? (xt[w][lane].off - xs) * RS_CS : 0;
+        tab[28 + lane] = on ? __float_as_int(xt[w][lane].w) : 0;
+    }
+    if (lane < RS_P) tab[56 + lane] = lane < p.PW ? xc[w][lane] : 0;
+    // lane rr gathers the pairs of feature row y0 + rr; a warp scan puts them in row order
+    int cnt = 0, code[RS_P]; float wt[RS_P];
+    const int nrows = it.y1 - it.y0 + 1;
+    if (lane < nrows) {
+        const int row = it.y0 + lane;
+        for (int ph = p0; ph < p1; ++ph)
+            for (int a = 0; a < yc[w][ph]; ++a)
+                if (yt[w][ph * RS_E + a].off == row && cnt < RS_P) { code[cnt] = (lane << 8) | ph; wt[cnt] = yt[w][ph * RS_E + a].w; ++cnt; }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
+    const int total = __shfl_sync(HD_FULL, incl, 31);
+    int at = incl - cnt;
+#pragma unroll
+    for (int j = 0; j < RS_P; ++j)
+        if (j < cnt && at + j < RS_P * RS_E) { tab[64 + at + j] = code[j]; tab[92 + at + j] = __float_as_int(wt[j]); }
+    if (lane == 0) { tab[63] = min(total, RS_P * RS_E); tab[120] = it.k; tab[121] = p0 | (p1 << 8); tab[122] = it.y0; tab[123] = it.y1; }
+}
 
 __global__ void __launch_bounds__(RS_THREADS, 1) roi_align_strip_kernel(const __grid_constant__ RsParams p, const __grid_constant__ RsMaps maps,
                                                                         int ring_off, int tab_off) {
@@ -204,6 +249,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) roi_align_strip_kernel(const __
     __shared__ unsigned long long full[RS_MAXROWS];
     __shared__ int prog[RS_NCW];           // first row of the item each consumer warp is working on (INT_MAX: finished)
     __shared__ int issued;                 // rows the producer has issued so far (a barrier's 1-bit phase says nothing before that)
+    __shared__ int tile_lock[RS_NTILE];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int u = blockIdx.y, c0 = blockIdx.x * RS_CS;
     const int s0 = p.unit_start[u], n = p.unit_start[u + 1] - s0;
@@ -217,18 +263,19 @@ __global__ void __launch_bounds__(RS_THREADS, 1) roi_align_strip_kernel(const __
     const RsLevel L = p.lv[lvl];
     const int xs = (rem - L.unit_base) * L.SW;
     const RsItem* items = p.items + s0;
+    const int* tables = p.tables + (size_t)s0 * RS_TABW;
     const int ya = max(items[0].y0, 0), yb = p.unit_ymax[u];
     const int NR = p.NR, row_floats = L.RW * RS_CS;
     const int nb = p.PH * p.PW, tstride = nb | 1;                 // odd tile stride: lane-per-channel writes hit 32 banks
     float* ring = reinterpret_cast<float*>(smem + ring_off);
-    float* tile = reinterpret_cast<float*>(smem) + (size_t)(wid < RS_NCW ? wid : 0) * RS_CS * tstride;
-    RsWarpTab& T = *reinterpret_cast<RsWarpTab*>(smem + tab_off + (size_t)(wid < RS_NCW ? wid : 0) * sizeof(RsWarpTab));
+    int* T = reinterpret_cast<int*>(smem + tab_off) + (size_t)(wid < RS_NCW ? wid : 0) * RS_TABW;
     if (tid == 0) {
         for (int s = 0; s < NR; ++s) rs_mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issued = 0;
     }
+    if (tid < RS_NTILE) tile_lock[tid] = 0;
     if (wid < RS_NCW && lane == 0) prog[wid] = wid < n ? items[wid].y0 : 0x7fffffff;
-    if (tid == 0) issued = 0;
     __syncthreads();
 
     if (wid == RS_NCW) {
@@ -240,16 +287,19 @@ __global__ void __launch_bounds__(RS_THREADS, 1) roi_align_strip_kernel(const __
             for (int idx = 0; idx < total; ++idx) {
                 const int slot = idx % NR, r = ya + idx;
                 if (idx >= NR) {
+                    const long long tp0 = clock64();
                     // the slot holds row r - NR: free once every unfinished item starts below it ...
                     for (unsigned spin = 0;; ++spin) {
                         int m = 0x7fffffff;
 #pragma unroll
                         for (int w = 0; w < RS_NCW; ++w) m = min(m, *reinterpret_cast<volatile int*>(&prog[w]));
                         if (m > r - NR) break;
-                        if (spin > (1u << 26)) __trap();
+                        __nanosleep(128);
+                        if (spin > (1u << 23)) __trap();
                     }
                     // ... and its previous load must have landed before the barrier is re-armed (rows nobody waited for)
                     rs_mbar_wait(&full[slot], (unsigned)(((idx / NR) - 1) & 1));
+                    if (p.prof) atomicAdd(p.prof + 5, (unsigned long long)(clock64() - tp0));
                 }
                 rs_mbar_expect_tx(&full[slot], row_bytes);
                 rs_tma_row(ring + (size_t)slot * row_floats, map, c0, xs, r, img, &full[slot]);
@@ -265,90 +315,113 @@ __global__ void __launch_bounds__(RS_THREADS, 1) roi_align_strip_kernel(const __
     // ==================================================================== consumers: lane = channel c0 + lane
     const float inv = 1.0f / (float)max(p.sr * p.sr, 1);
     const bool pow2 = ((p.sr * p.sr) & (p.sr * p.sr - 1)) == 0;
+    int4 nxt = make_int4(0, 0, 0, 0);
+    if (wid < n) nxt = __ldg(reinterpret_cast<const int4*>(tables + (size_t)wid * RS_TABW) + lane);   // table of the first item
     for (int i = wid; i < n; i += RS_NCW) {
-        const RsItem it = items[i];
-        if (lane == 0) *reinterpret_cast<volatile int*>(&prog[wid]) = it.y0;   // rows below it.y0 are no longer needed by this warp
-        const int p0 = it.pr & 255, p1 = it.pr >> 8;
-        const RsGeom G = rs_geom(p, it.k);
+        const unsigned tc0 = (unsigned)clock();
         __syncwarp();
-        if (lane < p.PH) build_axis(T.yt, T.yc, lane, RS_E, G.sh, G.bh, G.g, L.H, 1, 0);
-        else if (lane >= 8 && lane < 8 + p.PW) build_axis(T.xt, T.xc, lane - 8, RS_E, G.sw, G.bw, G.g, L.W, 1, 0);
+        reinterpret_cast<int4*>(T)[lane] = nxt;                                   // this item's table -> shared memory
+        if (i + RS_NCW < n) nxt = __ldg(reinterpret_cast<const int4*>(tables + (size_t)(i + RS_NCW) * RS_TABW) + lane);   // prefetch the next
         __syncwarp();
-        const int nrows = it.y1 - it.y0 + 1;
-        {   // lane rr: which bin rows does feature row y0 + rr feed, and with what weight
-            int cnt = 0;
-            if (lane < nrows) {
-                const int row = it.y0 + lane;
-                for (int ph = p0; ph < p1; ++ph)
-                    for (int a = 0; a < T.yc[ph]; ++a)
-                        if (T.yt[ph * RS_E + a].off == row) { T.rec_ph[lane][cnt] = (unsigned char)ph; T.rec_w[lane][cnt] = T.yt[ph * RS_E + a].w; ++cnt; }
-            }
-            T.rec_n[lane] = (unsigned char)cnt;
+        const int k = T[120], pr = T[121], y0 = T[122], y1 = T[123], np = T[63];
+        if (lane == 0) *reinterpret_cast<volatile int*>(&prog[wid]) = y0;         // rows below y0 are no longer needed by this warp
+        const int p0 = pr & 255, p1 = pr >> 8;
+        // Lane = (channel quad q, bin-column pair g): 8 quads x 4 pairs.  A quarter warp reads one cell's 32 channels as 128
+        // contiguous bytes (conflict free), and every instruction of the warp serves all 32 channels of the item -- the
+        // one-channel-per-lane form of this loop executed 2 900 instructions per item and was issue bound.
+        const int q = lane & 7, pwA = 2 * (lane >> 3), pwB = pwA + 1;
+        int xoA[RS_E], xoB[RS_E]; float wA[RS_E], wB[RS_E];
+        const int nA = T[56 + pwA], nB = pwB < RS_P ? T[56 + pwB] : 0;
+        {
+            const int4 o4 = reinterpret_cast<const int4*>(T)[pwA];
+            const float4 w4 = reinterpret_cast<const float4*>(T + 28)[pwA];
+            xoA[0] = (o4.x >> 2) + q; xoA[1] = (o4.y >> 2) + q; xoA[2] = (o4.z >> 2) + q; xoA[3] = (o4.w >> 2) + q;   // float4 units
+            wA[0] = w4.x; wA[1] = w4.y; wA[2] = w4.z; wA[3] = w4.w;
+            const int4 p4 = reinterpret_cast<const int4*>(T)[pwB < RS_P ? pwB : pwA];
+            const float4 v4 = reinterpret_cast<const float4*>(T + 28)[pwB < RS_P ? pwB : pwA];
+            xoB[0] = (p4.x >> 2) + q; xoB[1] = (p4.y >> 2) + q; xoB[2] = (p4.z >> 2) + q; xoB[3] = (p4.w >> 2) + q;
+            wB[0] = v4.x; wB[1] = v4.y; wB[2] = v4.z; wB[3] = v4.w;
         }
-        // x tables into registers (warp-uniform values): offset of the cell inside a ring row, merged weight
-        int xo[RS_P][RS_E]; float wx[RS_P][RS_E]; int nx[RS_P];
-#pragma unroll
-        for (int pw = 0; pw < RS_P; ++pw) {
-            nx[pw] = pw < p.PW ? T.xc[pw] : 0;
-#pragma unroll
-            for (int e = 0; e < RS_E; ++e) {
-                const bool on = e < nx[pw];
-                xo[pw][e] = on ? (T.xt[pw * RS_E + e].off - xs) * RS_CS + lane : lane;
-                wx[pw][e] = on ? T.xt[pw * RS_E + e].w : 0.0f;
-            }
-        }
-        __syncwarp();
+        const unsigned tc1 = (unsigned)clock();
         // The rows of this item must have landed.  A consumer can be many ring revolutions ahead of the producer (buckets with few,
         // scattered RoIs), where the 1-bit phase parity of a slot's barrier would alias: first wait until the last row has been
         // ISSUED -- from then on each of the item's slots is in, or one past, exactly the phase of its row.
-        for (unsigned spin = 0; *reinterpret_cast<volatile int*>(&issued) <= it.y1 - ya; ++spin)
-            if (spin > (1u << 26)) __trap();
+        for (unsigned spin = 0; *reinterpret_cast<volatile int*>(&issued) <= y1 - ya; ++spin) {
+            __nanosleep(256);                                                      // do not take issue slots from the working warps
+            if (spin > (1u << 22)) __trap();
+        }
         __threadfence_block();
-        for (int r = it.y0; r <= it.y1; ++r) {
+        for (int r = y0; r <= y1; ++r) {
             const int idx = r - ya;
             rs_mbar_wait(&full[idx % NR], (unsigned)((idx / NR) & 1));
         }
-        float acc[RS_P][RS_P];
+        const unsigned tc2 = (unsigned)clock();
+        float4 acc[RS_P][2];
 #pragma unroll
-        for (int a = 0; a < RS_P; ++a)
+        for (int a = 0; a < RS_P; ++a) { acc[a][0] = make_float4(0.f, 0.f, 0.f, 0.f); acc[a][1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        // pairs (row, bin row, weight) in row order: the x-interpolated values of a row are formed once, when the row changes
+        const int base_slot = (y0 - ya) % NR;
+        int cur = -1;
+        float4 tA = make_float4(0.f, 0.f, 0.f, 0.f), tB = tA;
+        int code = np > 0 ? T[64] : 0;
+        float wy = np > 0 ? __int_as_float(T[92]) : 0.0f;
+        for (int j = 0; j < np; ++j) {
+            const int ncode = j + 1 < np ? T[64 + j + 1] : 0;                     // next pair: in flight while this one is used
+            const float nwy = j + 1 < np ? __int_as_float(T[92 + j + 1]) : 0.0f;
+            const int rr = code >> 8;
+            if (rr != cur) {
+                cur = rr;
+                int slot = base_slot + rr;
+                if (slot >= NR) slot -= NR;
+                const float4* __restrict__ row = reinterpret_cast<const float4*>(ring + (size_t)slot * row_floats);
+                tA = make_float4(0.f, 0.f, 0.f, 0.f); tB = tA;
 #pragma unroll
-            for (int b = 0; b < RS_P; ++b) acc[a][b] = 0.0f;
-        int slot = (it.y0 - ya) % NR;
-        for (int rr = 0; rr < nrows; ++rr) {
-            const float* __restrict__ row = ring + (size_t)slot * row_floats;
-            slot = slot + 1 == NR ? 0 : slot + 1;
-            float t[RS_P];
-#pragma unroll
-            for (int pw = 0; pw < RS_P; ++pw) {
-                float r = 0.0f;
-#pragma unroll
-                for (int e = 0; e < RS_E; ++e)
-                    if (e < nx[pw]) r = fmaf(wx[pw][e], row[xo[pw][e]], r);
-                t[pw] = r;
-            }
-            const int cn = T.rec_n[rr];
-            for (int j = 0; j < cn; ++j) {
-                const float wy = T.rec_w[rr][j];
-                switch (T.rec_ph[rr][j]) {   // warp-uniform: the accumulators stay in statically indexed registers
-#define RS_ROW(q) case q: _Pragma("unroll") for (int pw = 0; pw < RS_P; ++pw) acc[q][pw] = fmaf(wy, t[pw], acc[q][pw]); break;
-                    RS_ROW(0) RS_ROW(1) RS_ROW(2) RS_ROW(3) RS_ROW(4) RS_ROW(5) RS_ROW(6)
-#undef RS_ROW
-                    default: break;
+                for (int e = 0; e < RS_E; ++e) {
+                    if (e < nA) { const float4 v = row[xoA[e]]; tA.x = fmaf(wA[e], v.x, tA.x); tA.y = fmaf(wA[e], v.y, tA.y); tA.z = fmaf(wA[e], v.z, tA.z); tA.w = fmaf(wA[e], v.w, tA.w); }
+                    if (e < nB) { const float4 v = row[xoB[e]]; tB.x = fmaf(wB[e], v.x, tB.x); tB.y = fmaf(wB[e], v.y, tB.y); tB.z = fmaf(wB[e], v.z, tB.z); tB.w = fmaf(wB[e], v.w, tB.w); }
                 }
             }
+            switch (code & 255) {   // warp-uniform: the accumulators stay in statically indexed registers
+#define RS_ROW(k_) case k_: acc[k_][0].x = fmaf(wy, tA.x, acc[k_][0].x); acc[k_][0].y = fmaf(wy, tA.y, acc[k_][0].y); acc[k_][0].z = fmaf(wy, tA.z, acc[k_][0].z); acc[k_][0].w = fmaf(wy, tA.w, acc[k_][0].w); \
+                       acc[k_][1].x = fmaf(wy, tB.x, acc[k_][1].x); acc[k_][1].y = fmaf(wy, tB.y, acc[k_][1].y); acc[k_][1].z = fmaf(wy, tB.z, acc[k_][1].z); acc[k_][1].w = fmaf(wy, tB.w, acc[k_][1].w); break;
+                RS_ROW(0) RS_ROW(1) RS_ROW(2) RS_ROW(3) RS_ROW(4) RS_ROW(5) RS_ROW(6)
+#undef RS_ROW
+                default: break;
+            }
+            code = ncode; wy = nwy;
         }
-        // scale, then out: full items through the shared tile (contiguous [32, PH*PW] block, 128-bit stores), split items directly
-        float* __restrict__ dst = p.out + ((size_t)it.k * p.C + c0) * nb;
+        const unsigned tc3 = (unsigned)clock();
+        // scale, then out: full items through a shared tile (contiguous [32, PH*PW] block, 128-bit stores), split items directly
+        float* __restrict__ dst = p.out + ((size_t)k * p.C + c0) * nb;
         const bool whole = p0 == 0 && p1 == p.PH;
+        float* tile = nullptr;
+        int ts = 0;
+        if (whole) {   // take one of the RS_NTILE tiles (the output phase is ~10% of an item, so the tiles are rarely all busy)
+            if (lane == 0) {
+                ts = wid % RS_NTILE;
+                for (unsigned spin = 0; atomicCAS(&tile_lock[ts], 0, 1) != 0; ++spin) {
+                    ts = ts + 1 == RS_NTILE ? 0 : ts + 1;
+                    if (spin > (1u << 26)) __trap();
+                }
+            }
+            ts = __shfl_sync(HD_FULL, ts, 0);
+            tile = reinterpret_cast<float*>(smem) + (size_t)ts * RS_CS * tstride;
+        }
 #pragma unroll
         for (int ph = 0; ph < RS_P; ++ph) {
             if (ph < p0 || ph >= p1) continue;
 #pragma unroll
-            for (int pw = 0; pw < RS_P; ++pw) {
+            for (int h = 0; h < 2; ++h) {
+                const int pw = pwA + h;
                 if (pw >= p.PW) continue;
-                const float v = pow2 ? acc[ph][pw] * inv : __fdiv_rn(acc[ph][pw], (float)(p.sr * p.sr));
-                if (whole) tile[lane * tstride + ph * p.PW + pw] = v;
-                else dst[(size_t)lane * nb + ph * p.PW + pw] = v;
+                const float4 a4 = acc[ph][h];
+                const float v[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float o = pow2 ? v[c] * inv : __fdiv_rn(v[c], (float)(p.sr * p.sr));
+                    if (whole) tile[(4 * q + c) * tstride + ph * p.PW + pw] = o;
+                    else dst[(size_t)(4 * q + c) * nb + ph * p.PW + pw] = o;
+                }
             }
         }
         if (whole) {
@@ -365,6 +438,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1) roi_align_strip_kernel(const __
                 }
             }
             __syncwarp();
+            if (lane == 0) { __threadfence_block(); atomicExch(&tile_lock[ts], 0); }
+        }
+        if (p.prof && lane == 0) {
+            const unsigned tc4 = (unsigned)clock();
+            atomicAdd(p.prof + 0, (unsigned long long)(tc1 - tc0)); atomicAdd(p.prof + 1, (unsigned long long)(tc2 - tc1));
+            atomicAdd(p.prof + 2, (unsigned long long)(tc3 - tc2)); atomicAdd(p.prof + 3, (unsigned long long)(tc4 - tc3));
+            atomicAdd(p.prof + 4, 1ull);
         }
     }
     if (lane == 0) *reinterpret_cast<volatile int*>(&prog[wid]) = 0x7fffffff;
@@ -384,7 +464,15 @@ static RsEncodeFn rs_encode_fn() {
     return fn;
 }
 
-static const int RS_NR = 20;
+static unsigned long long* g_rs_prof = nullptr;   // developer aid (hd_debug_roi_profile): device counters of the streamed kernel
+extern "C" HD_API int hd_debug_roi_profile(int enable, unsigned long long* out8 /*host, nullable*/) {
+    if (enable && !g_rs_prof) { HD_CUDA_CALL(cudaMalloc(&g_rs_prof, 64)); HD_CUDA_CALL(cudaMemset(g_rs_prof, 0, 64)); }
+    if (out8 && g_rs_prof) { HD_CUDA_CALL(cudaDeviceSynchronize()); HD_CUDA_CALL(cudaMemcpy(out8, g_rs_prof, 64, cudaMemcpyDeviceToHost)); HD_CUDA_CALL(cudaMemset(g_rs_prof, 0, 64)); }
+    if (!enable && g_rs_prof) { cudaFree(g_rs_prof); g_rs_prof = nullptr; }
+    return HD_OK;
+}
+
+static const int RS_NR = 24;
 static void rs_ws_layout(int n_units, long long K, size_t* offs, size_t* total) {
     size_t o = 0;
     const size_t nu = (size_t)n_units, k2 = (size_t)K * 2;
@@ -395,6 +483,7 @@ static void rs_ws_layout(int n_units, long long K, size_t* offs, size_t* total) 
     offs[4] = o; o = hd_align_up(o + k2 * sizeof(RsItem), 256);   // scat
     offs[5] = o; o = hd_align_up(o + k2 * sizeof(RsItem), 256);   // items
     offs[6] = o; o = hd_align_up(o + (size_t)K * 4, 256);         // fb_list
+    offs[7] = o; o = hd_align_up(o + k2 * RS_TABW * 4, 256);      // per-item tables
     *total = o;
 }
 
@@ -403,10 +492,10 @@ static bool rs_plan(RsParams& p, const hd_roi_level* levels, int n_levels, int C
                     int* ring_off, int* tab_off) {
     if (C % RS_CS != 0 || PH < 1 || PW < 1 || PH > RS_P || PW > RS_P || sr < 1 || sr > 2 || batch < 1 || K < 512 || K >= (1ll << 30)) return false;
     const int nb = PH * PW, tstride = nb | 1;
-    const size_t tiles = hd_align_up((size_t)RS_NCW * RS_CS * tstride * 4, 128);
-    const size_t tabs = hd_align_up((size_t)RS_NCW * sizeof(RsWarpTab), 128);
+    const size_t tiles = hd_align_up((size_t)RS_NTILE * RS_CS * tstride * 4, 128);
+    const size_t tabs = hd_align_up((size_t)RS_NCW * RS_TABW * 4, 128);
     const size_t budget = 224 * 1024;   // dynamic shared memory; the 227 KB of an SM also hold this kernel's static barriers
-    if (tiles + tabs + (size_t)RS_NR * 64 * RS_CS * 4 > budget) return false;
+    if (tiles + tabs + (size_t)RS_NR * (RS_HALO + 8) * RS_CS * 4 > budget) return false;
     const int rw_cap = (int)((budget - tiles - tabs) / ((size_t)RS_NR * RS_CS * 4));
     int units = 0, rw_max = 0;
     for (int l = 0; l < n_levels; ++l) {
@@ -437,7 +526,7 @@ extern "C" HD_API size_t hd_roi_align_workspace_size(const hd_roi_level* levels,
     size_t smem; int ro, to;
     if (!levels || n_levels < 1 || n_levels > HD_MAX_LEVELS || K < 0) return 0;
     if (!rs_plan(p, levels, n_levels, C, batch, pooled_h, pooled_w, sampling_ratio, K, &smem, &ro, &to)) return 256;
-    size_t offs[7], total;
+    size_t offs[8], total;
     rs_ws_layout(p.n_units, K, offs, &total);
     return total + 256;
 }
@@ -452,7 +541,7 @@ extern "C" HD_API int hd_roi_align_ws(const hd_roi_level* levels, int n_levels, 
     RsEncodeFn enc = rs_encode_fn();
     bool ok = layout == HD_LAYOUT_NHWC && (hd_roi_mode() & 15) != 1 && enc != nullptr && workspace != nullptr && (n_levels == 1 || level_ids != nullptr) &&
               rs_plan(p, levels, n_levels, C, batch, pooled_h, pooled_w, sampling_ratio, K, &smem, &ring_off, &tab_off);
-    size_t offs[7], total = 0;
+    size_t offs[8], total = 0;
     uintptr_t w0 = hd_align_up((uintptr_t)workspace, 256);
     if (ok) {
         rs_ws_layout(p.n_units, K, offs, &total);
@@ -481,7 +570,8 @@ extern "C" HD_API int hd_roi_align_ws(const hd_roi_level* levels, int n_levels, 
     p.unit_count = zero; p.unit_cursor = zero + nu; p.unit_ymax = zero + 2 * nu; p.n_tmp = zero + 3 * nu; p.fb_count = zero + 3 * nu + 1;
     p.unit_start = (int*)(w0 + offs[1]);
     p.tmp = (RsItem*)(w0 + offs[2]); p.tmp_unit = (int*)(w0 + offs[3]); p.scat = (RsItem*)(w0 + offs[4]); p.items = (RsItem*)(w0 + offs[5]);
-    p.fb_list = (int*)(w0 + offs[6]);
+    p.fb_list = (int*)(w0 + offs[6]); p.tables = (int*)(w0 + offs[7]);
+    p.prof = g_rs_prof;
     HD_CUDA_CALL(cudaMemsetAsync(zero, 0, (nu * 3 + 4) * 4, st));
     rs_prep_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(p);
     HD_CUDA_LAUNCH_CHECK("rs_prep_kernel");
@@ -491,6 +581,8 @@ extern "C" HD_API int hd_roi_align_ws(const hd_roi_level* levels, int n_levels, 
     HD_CUDA_LAUNCH_CHECK("rs_scatter_kernel");
     rs_sort_kernel<<<(unsigned)p.n_units, 256, 0, st>>>(p);
     HD_CUDA_LAUNCH_CHECK("rs_sort_kernel");
+    rs_table_kernel<<<(unsigned)((2 * K + 7) / 8), 256, 0, st>>>(p);
+    HD_CUDA_LAUNCH_CHECK("rs_table_kernel");
     HD_ENSURE_SMEM(roi_align_strip_kernel, 226 * 1024);
     roi_align_strip_kernel<<<dim3((unsigned)(C / RS_CS), (unsigned)p.n_units), RS_THREADS, smem, st>>>(p, maps, ring_off, tab_off);
     HD_CUDA_LAUNCH_CHECK("roi_align_strip_kernel");

@@ -1,5 +1,5 @@
 // TTA map-back (a10) and Weighted Boxes Fusion (a11).  Reference feature: README.md:19; semantics SURVEY.md A.6
-// (ZFTurbo ensemble-boxes `weighted_boxes_fusion`, conf types 'avg' and 'max').
+// (ZFTurbo ensemble-boxes `weighted_boxes_fusion`, conf types 'avg', 'max', 'box_and_model_avg', 'absent_model_aware_avg').
 //
 // One CTA per image.  The whole CTA prefilters the V views into records, orders them with the CTA radix
 // sort (three stable passes: position desc, weighted score desc, label first-appearance asc -- the order
@@ -21,6 +21,8 @@ struct WbfParams {
     double wsum, wmax;
     double iou_thr, skip_thr;
     int conf_max, allow_overflow;
+    int conf_type;       // HD_WBF_AVG / MAX / BOX_AND_MODEL_AVG / ABSENT_MODEL_AWARE_AVG
+    int rescale_sum;     // 'avg' without overflow: min(cluster size, sum(weights)) (ensemble-boxes <= 1.0.4) instead of min(.., len(weights))
     float* out_boxes;   // [B, cap, 4]
     double* out_scores; // [B, cap]
     float* out_labels;  // [B, cap]
@@ -31,6 +33,7 @@ struct WbfParams {
     int* first_pos;  // [B, num_labels]
     double* c_box; double* c_score; double* c_conf; double* c_w; double* c_max; float* c_acc; int* c_cnt; int* c_label;
     int* seg_start;
+    int* c_models;       // bit t: view/model t contributed a box to the cluster
 };
 
 __device__ __forceinline__ uint64_t orderable64(double d) {
@@ -53,6 +56,7 @@ __global__ void __launch_bounds__(WBF_NT) wbf_kernel(const __grid_constant__ Wbf
     double* c_box = p.c_box + off * 4; double* c_score = p.c_score + off; double* c_conf = p.c_conf + off;
     double* c_w = p.c_w + off; double* c_max = p.c_max + off; float* c_acc = p.c_acc + off * 4;
     int* c_cnt = p.c_cnt + off; int* c_label = p.c_label + off; int* seg_start = p.seg_start + off;
+    int* c_models = p.c_models + off;
 
     if (tid == 0) { s_n = 0; s_nseg = 0; s_next = 0; s_nclu = 0; }
     for (int i = tid; i < p.num_labels; i += WBF_NT) first_pos[i] = 0x7fffffff;
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(WBF_NT) wbf_kernel(const __grid_constant__ Wbf
             const bool match = (nclu > 0) && (best > p.iou_thr);
             if (lane == 0) {
                 const double ws = r_ws[rec], w = r_w[rec];
+                const int model_bit = 1 << (r_pos[rec] / p.M);
                 const int c = match ? bi : nclu;
                 const size_t ci = (size_t)(seg0 + c);
                 float* acc = c_acc + ci * 4;
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(WBF_NT) wbf_kernel(const __grid_constant__ Wbf
                     // new cluster: weighted row is a copy of the box; accumulators start as get_weighted_box would
                     acc[0] = (float)__dmul_rn(ws, bx1); acc[1] = (float)__dmul_rn(ws, by1);
                     acc[2] = (float)__dmul_rn(ws, bx2); acc[3] = (float)__dmul_rn(ws, by2);
-                    c_conf[ci] = ws; c_w[ci] = w; c_max[ci] = ws; c_cnt[ci] = 1; c_label[ci] = label;
+                    c_conf[ci] = ws; c_w[ci] = w; c_max[ci] = ws; c_cnt[ci] = 1; c_label[ci] = label; c_models[ci] = model_bit;
                     cb[0] = bx1; cb[1] = by1; cb[2] = bx2; cb[3] = by2;
                     c_score[ci] = ws;
                 } else {
@@ -158,6 +163,7 @@ __global__ void __launch_bounds__(WBF_NT) wbf_kernel(const __grid_constant__ Wbf
                     const double conf = __dadd_rn(c_conf[ci], ws);
                     c_conf[ci] = conf; c_w[ci] = __dadd_rn(c_w[ci], w);
                     c_max[ci] = fmax(c_max[ci], ws);
+                    c_models[ci] |= model_bit;
                     const int cnt = ++c_cnt[ci];
                     c_score[ci] = p.conf_max ? (double)(float)c_max[ci] : (double)(float)__ddiv_rn(conf, (double)cnt);
                     cb[0] = (double)(float)__ddiv_rn((double)acc[0], conf); cb[1] = (double)(float)__ddiv_rn((double)acc[1], conf);
@@ -173,8 +179,19 @@ __global__ void __launch_bounds__(WBF_NT) wbf_kernel(const __grid_constant__ Wbf
     for (int i = tid; i < n; i += WBF_NT) {
         if (c_cnt[i] > 0) {
             double sc = c_score[i];
+            // weighted_boxes[i, 2]: the exact weight of a single-box cluster (the row is a copy of the box), the float32 sum otherwise
+            const double w_row = c_cnt[i] == 1 ? c_w[i] : (double)(float)c_w[i];
             if (p.conf_max) sc = __ddiv_rn(sc, p.wmax);
-            else if (!p.allow_overflow) sc = __ddiv_rn(__dmul_rn(sc, fmin((double)c_cnt[i], p.wsum)), p.wsum);
+            else if (p.conf_type == HD_WBF_BOX_AND_MODEL_AVG) {
+                double uniq = 0.0;   // weights of the distinct models in the cluster, ascending model index (np.unique order)
+                for (int t = 0; t < p.V; ++t) if ((c_models[i] >> t) & 1) uniq = __dadd_rn(uniq, p.weights[t]);
+                sc = __ddiv_rn(__dmul_rn(sc, (double)c_cnt[i]), w_row);
+                sc = __ddiv_rn(__dmul_rn(sc, uniq), p.wsum);
+            } else if (p.conf_type == HD_WBF_ABSENT_MODEL_AWARE_AVG) {
+                double absent = 0.0;  // weights of the models that have no box in the cluster
+                for (int t = 0; t < p.V; ++t) if (!((c_models[i] >> t) & 1)) absent = __dadd_rn(absent, p.weights[t]);
+                sc = __ddiv_rn(__dmul_rn(sc, (double)c_cnt[i]), __dadd_rn(w_row, absent));
+            } else if (!p.allow_overflow) sc = __ddiv_rn(__dmul_rn(sc, fmin((double)c_cnt[i], p.rescale_sum ? p.wsum : (double)p.V)), p.wsum);
             else sc = __ddiv_rn(__dmul_rn(sc, (double)c_cnt[i]), p.wsum);
             c_score[i] = sc;
             const int slot = atomicAdd(&s_nclu, 1);
@@ -232,6 +249,7 @@ static WbfWs wbf_layout(int B, int cap, int num_labels) {
     put((size_t)B * num_labels * 4);                                       // first_pos
     put(n * 32); put(n * 8); put(n * 8); put(n * 8); put(n * 8); put(n * 16); put(n * 4); put(n * 4);  // c_*
     put(n * 4);                                                            // seg_start
+    put(n * 4);                                                            // c_models
     w.total = o;
     return w;
 }
@@ -247,7 +265,9 @@ extern "C" HD_API int hd_wbf(const float* boxes, const float* scores, const floa
                              void* workspace, size_t workspace_bytes, void* stream) {
     HD_CHECK_ARG(B >= 0 && V >= 1 && V <= 16 && M >= 1, "bad shape B=%d V=%d (max 16) M=%d", B, V, M);
     HD_CHECK_ARG(num_labels >= 1, "num_labels must be >= 1");
-    HD_CHECK_ARG(conf_type == HD_WBF_AVG || conf_type == HD_WBF_MAX, "conf_type must be HD_WBF_AVG or HD_WBF_MAX");
+    const int ctype = conf_type & 255;
+    HD_CHECK_ARG(ctype >= HD_WBF_AVG && ctype <= HD_WBF_ABSENT_MODEL_AWARE_AVG && (conf_type & ~(255 | HD_WBF_RESCALE_SUM_WEIGHTS)) == 0,
+                 "conf_type must be HD_WBF_AVG, _MAX, _BOX_AND_MODEL_AVG or _ABSENT_MODEL_AWARE_AVG (| HD_WBF_RESCALE_SUM_WEIGHTS), got %d", conf_type);
     HD_CHECK_ARG((long long)V * M < (1ll << 24), "V*M too large");
     if (B == 0) return HD_OK;
     HD_CHECK_ARG(boxes && scores && labels && counts && out_boxes && out_scores && out_labels && out_count, "null pointer");
@@ -264,7 +284,8 @@ extern "C" HD_API int hd_wbf(const float* boxes, const float* scores, const floa
         p.wsum += p.weights[v];
         if (p.weights[v] > p.wmax) p.wmax = p.weights[v];
     }
-    p.iou_thr = iou_thr; p.skip_thr = skip_box_thr; p.conf_max = conf_type == HD_WBF_MAX; p.allow_overflow = allows_overflow;
+    p.iou_thr = iou_thr; p.skip_thr = skip_box_thr; p.conf_max = ctype == HD_WBF_MAX; p.allow_overflow = allows_overflow;
+    p.conf_type = ctype; p.rescale_sum = (conf_type & HD_WBF_RESCALE_SUM_WEIGHTS) ? 1 : 0;
     p.out_boxes = out_boxes; p.out_scores = out_scores; p.out_labels = out_labels; p.out_count = out_count;
     int i = 0;
     p.r_label = (int*)(w0 + w.o[i++]); p.r_pos = (int*)(w0 + w.o[i++]); p.r_ws = (double*)(w0 + w.o[i++]); p.r_w = (double*)(w0 + w.o[i++]);
@@ -273,7 +294,7 @@ extern "C" HD_API int hd_wbf(const float* boxes, const float* scores, const floa
     p.first_pos = (int*)(w0 + w.o[i++]);
     p.c_box = (double*)(w0 + w.o[i++]); p.c_score = (double*)(w0 + w.o[i++]); p.c_conf = (double*)(w0 + w.o[i++]); p.c_w = (double*)(w0 + w.o[i++]);
     p.c_max = (double*)(w0 + w.o[i++]); p.c_acc = (float*)(w0 + w.o[i++]); p.c_cnt = (int*)(w0 + w.o[i++]); p.c_label = (int*)(w0 + w.o[i++]);
-    p.seg_start = (int*)(w0 + w.o[i++]);
+    p.seg_start = (int*)(w0 + w.o[i++]); p.c_models = (int*)(w0 + w.o[i++]);
     wbf_kernel<<<B, WBF_NT, 0, (cudaStream_t)stream>>>(p);
     HD_CUDA_LAUNCH_CHECK("wbf_kernel");
     return HD_OK;

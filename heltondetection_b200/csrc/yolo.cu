@@ -53,6 +53,7 @@ struct YoloParams {
     float thr;   // (float) conf_thres: torch compares the fp32 tensor with the scalar cast to fp32
     float gate;  // conservative logit-domain pre-test for sigmoid(obj) > thr
     int ge, dense, cap;
+    int multi;   // HD_FLAG_MULTI_LABEL: every (anchor, class) pair with obj*cls > thr is a candidate (ultralytics multi_label)
     int items_per_image;
     long long total_items;
 };
@@ -238,6 +239,128 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// multi_label variant (ultralytics non_max_suppression with multi_label=True, the evaluation setting conf 0.001 / iou 0.6 when
+// nc > 1): after `x[:, 5:] *= x[:, 4:5]` EVERY class with obj*cls > conf_thres yields a candidate (box, obj*cls, class), in
+// (anchor, class) order.  Same tile walk as above; per group of class planes the lanes count their hits (logit gate first, then the
+// exact fp32 product), a warp scan claims the slots with one atomicAdd, and each hit decodes its box.  The candidate's tie-break /
+// reported index is anchor * nc + class.
+// ------------------------------------------------------------------------------------------------
+template <bool VEC, typename T>
+__device__ __forceinline__ void yolo_decode_item_multi(const YoloParams& p, const long long item, const int lane,
+                                                       float4* __restrict__ cand_box, float* __restrict__ cand_score,
+                                                       int* __restrict__ cand_cls, int* __restrict__ cand_anchor,
+                                                       int* __restrict__ cand_count) {
+    const int b = (int)(item / p.items_per_image);
+    int r = (int)(item - (long long)b * p.items_per_image);
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < HD_MAX_LEVELS; ++q)
+        if (q < p.n_levels && r >= p.A * p.tile_start[q]) l = q;
+    r -= p.A * p.tile_start[l];
+    const int tiles_l = p.tile_start[l + 1] - p.tile_start[l];
+    const int a = r / tiles_l;
+    const int t = r - a * tiles_l;
+    const int HW = p.HW[l];
+    const int cell0 = t * 128 + lane * 4;
+    const T* __restrict__ base = reinterpret_cast<const T*>(p.data[l]) + ((size_t)(b * p.A + a) * p.no) * HW + cell0;
+    bool valid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) valid[k] = (cell0 + k) < HW;
+    auto load4 = [&](int plane, float* v, bool need) {
+        const T* q = base + (size_t)plane * HW;
+        if (VEC) {
+            if (valid[0] && need) hd_load4<T>(q, v);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (valid[k] && need) v[k] = hd_load1<T>(q + k);
+        }
+    };
+    float o[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    load4(4, o, true);
+    bool live[4];
+    float po[4];
+    bool any_live = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        live[k] = false; po[k] = 0.0f;
+        if (valid[k] && o[k] > p.gate) {
+            po[k] = hd_sigmoid(o[k]);
+            live[k] = p.ge ? (po[k] >= p.thr) : (po[k] > p.thr);
+        }
+        any_live |= live[k];
+    }
+    if (!p.dense && !__any_sync(HD_FULL, any_live)) return;
+    const bool need = p.dense || any_live;
+    float bx[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bx[c][k] = 0.0f;
+        load4(c, bx[c], need);
+    }
+    const float s = p.stride[l];
+    const float aw = p.anchor[l][2 * a], ah = p.anchor[l][2 * a + 1];
+    const int W = p.W[l];
+    constexpr int U = 8;
+    for (int c0 = 0; c0 < p.nc; c0 += U) {
+        float v[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[u][k] = -INFINITY;
+            if (c0 + u < p.nc) load4(5 + c0 + u, v[u], need);
+        }
+        // hits of this lane in the group: bit (k * U + u); conf recomputed at emission (hits are rare next to the planes streamed)
+        unsigned hits = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (live[k] && v[u][k] > p.gate) {
+                    const float cf = __fmul_rn(hd_sigmoid(v[u][k]), po[k]);
+                    if (p.ge ? (cf >= p.thr) : (cf > p.thr)) hits |= 1u << (k * U + u);
+                }
+        if (!__any_sync(HD_FULL, hits != 0u)) continue;
+        const int nh = __popc(hits);
+        int incl = nh;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(HD_FULL, incl, d); if (lane >= d) incl += y; }
+        const int total = __shfl_sync(HD_FULL, incl, 31);
+        int slot0 = 0;
+        if (lane == 31) slot0 = atomicAdd(cand_count + b, total);
+        slot0 = __shfl_sync(HD_FULL, slot0, 31);
+        int slot = slot0 + incl - nh;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!((hits >> (k * U)) & ((1u << U) - 1u))) continue;
+            const int cell = cell0 + k;
+            const int gi = cell / W, gj = cell - gi * W;
+            const float px = __fmul_rn(hd_sigmoid(bx[0][k]), 2.0f), py = __fmul_rn(hd_sigmoid(bx[1][k]), 2.0f);
+            const float pw = __fmul_rn(hd_sigmoid(bx[2][k]), 2.0f), ph = __fmul_rn(hd_sigmoid(bx[3][k]), 2.0f);
+            const float cx = __fmul_rn(__fadd_rn(__fsub_rn(px, 0.5f), (float)gj), s);
+            const float cy = __fmul_rn(__fadd_rn(__fsub_rn(py, 0.5f), (float)gi), s);
+            const float w = __fmul_rn(__fmul_rn(pw, pw), aw), h = __fmul_rn(__fmul_rn(ph, ph), ah);
+            const float hw2 = __fmul_rn(w, 0.5f), hh2 = __fmul_rn(h, 0.5f);
+            const float4 box = make_float4(__fsub_rn(cx, hw2), __fsub_rn(cy, hh2), __fadd_rn(cx, hw2), __fadd_rn(cy, hh2));
+            const int anchor = p.level_off[l] + a * HW + cell;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!((hits >> (k * U + u)) & 1u)) continue;
+                if (slot < p.cap) {
+                    const size_t g = (size_t)b * p.cap + slot;
+                    cand_box[g] = box;
+                    cand_score[g] = __fmul_rn(hd_sigmoid(v[u][k]), po[k]);
+                    cand_cls[g] = c0 + u;
+                    cand_anchor[g] = anchor * p.nc + c0 + u;
+                }
+                ++slot;
+            }
+        }
+    }
+}
+
 template <bool VEC, typename T = float>
 __global__ void __launch_bounds__(256, 4) yolo_decode_filter_kernel(const __grid_constant__ YoloParams p,
                                                                  float4* __restrict__ cand_box,
@@ -248,6 +371,15 @@ __global__ void __launch_bounds__(256, 4) yolo_decode_filter_kernel(const __grid
     const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (item >= p.total_items) return;
     yolo_decode_item<VEC, T>(p, item, threadIdx.x & 31, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
+}
+
+template <bool VEC, typename T = float>
+__global__ void __launch_bounds__(256, 2) yolo_decode_filter_multi_kernel(const __grid_constant__ YoloParams p, float4* __restrict__ cand_box,
+                                                                          float* __restrict__ cand_score, int* __restrict__ cand_cls,
+                                                                          int* __restrict__ cand_anchor, int* __restrict__ cand_count) {
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= p.total_items) return;
+    yolo_decode_item_multi<VEC, T>(p, item, threadIdx.x & 31, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -638,7 +770,14 @@ extern "C" HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels, int n_l
     p.gate = conf_gate(conf_thres);
     p.ge = (flags & HD_FLAG_CONF_GE) ? 1 : 0;
     p.dense = (flags & HD_FLAG_DENSE_READ) ? 1 : 0;
+    p.multi = (flags & HD_FLAG_MULTI_LABEL) ? 1 : 0;
     p.cap = cap;
+    if (p.multi) {
+        HD_CHECK_ARG(!(flags & HD_FLAG_IN_NHWC), "HD_FLAG_MULTI_LABEL needs NCHW heads");
+        long long tot = 0;
+        for (int l = 0; l < n_levels; ++l) tot += (long long)A * p.HW[l];
+        HD_CHECK_ARG(tot * nc < (1ll << 31), "anchors * classes must be < 2^31 for the multi_label candidate index");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0) return HD_OK;
     HD_CUDA_CALL(cudaMemsetAsync(cand_count, 0, sizeof(int) * (size_t)B, st));
@@ -690,7 +829,11 @@ extern "C" HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels, int n_l
     const int warps = 8;
     long long blocks = (p.total_items + warps - 1) / warps;
     HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
-#define HD_YOLO_LAUNCH(V, T) yolo_decode_filter_kernel<V, T><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count)
+#define HD_YOLO_LAUNCH(V, T)                                                                                                                     \
+    do {                                                                                                                                         \
+        if (p.multi) yolo_decode_filter_multi_kernel<V, T><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count); \
+        else yolo_decode_filter_kernel<V, T><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count);                \
+    } while (0)
     if (dt == 0) { if (vec) HD_YOLO_LAUNCH(true, float); else HD_YOLO_LAUNCH(false, float); }
     else if (dt == 1) { if (vec) HD_YOLO_LAUNCH(true, HdF16); else HD_YOLO_LAUNCH(false, HdF16); }
     else { if (vec) HD_YOLO_LAUNCH(true, HdBF16); else HD_YOLO_LAUNCH(false, HdBF16); }

@@ -108,3 +108,37 @@ _LIB.impl("roi_align", lambda input, rois, s, ph, pw, sr, al: roi_align(input, r
 _LIB.impl("roi_pool", lambda input, rois, s, ph, pw: roi_pool_with_argmax(input, rois, (ph, pw), s), "CUDA")
 _LIB.impl("roi_align", _cpu_refuse, "CPU")
 _LIB.impl("roi_pool", _cpu_refuse, "CPU")
+
+
+# ----------------------------------------------------------------------------- fake (meta) implementations
+# Shapes/dtypes without data, so that the four ops trace under FakeTensorMode / torch.compile / torch.export exactly like the
+# torchvision ops they replace (torchvision registers the same abstract impls in torchvision/_meta_registrations.py).
+@torch.library.register_fake("hd_b200::nms")
+def _nms_fake(dets, scores, iou_threshold):
+    torch._check(dets.dim() == 2, lambda: f"boxes should be a 2d tensor, got {dets.dim()}D")
+    torch._check(dets.size(1) == 4, lambda: f"boxes should have 4 elements in dimension 1, got {dets.size(1)}")
+    torch._check(scores.dim() == 1, lambda: f"scores should be a 1d tensor, got {scores.dim()}D")
+    torch._check(dets.size(0) == scores.size(0),
+                 lambda: f"boxes and scores should have same number of elements in dimension 0, got {dets.size(0)} and {scores.size(0)}")
+    n = torch.library.get_ctx().new_dynamic_size()      # data-dependent number of kept boxes
+    return dets.new_empty((n,), dtype=torch.int64)
+
+
+@torch.library.register_fake("hd_b200::box_iou")
+def _box_iou_fake(boxes1, boxes2):
+    torch._check(boxes1.dim() == 2 and boxes1.size(1) == 4 and boxes2.dim() == 2 and boxes2.size(1) == 4,
+                 lambda: "box_iou expects Tensor[N, 4] and Tensor[M, 4]")
+    return boxes1.new_empty((boxes1.size(0), boxes2.size(0)))
+
+
+@torch.library.register_fake("hd_b200::roi_align")
+def _roi_align_fake(input, rois, spatial_scale, pooled_height, pooled_width, sampling_ratio, aligned):
+    torch._check(rois.dim() == 2 and rois.size(1) == 5, lambda: "rois must have shape as Tensor[K, 5]")
+    return input.new_empty((rois.size(0), input.size(1), pooled_height, pooled_width))
+
+
+@torch.library.register_fake("hd_b200::roi_pool")
+def _roi_pool_fake(input, rois, spatial_scale, pooled_height, pooled_width):
+    torch._check(rois.dim() == 2 and rois.size(1) == 5, lambda: "rois must have shape as Tensor[K, 5]")
+    shape = (rois.size(0), input.size(1), pooled_height, pooled_width)
+    return input.new_empty(shape), input.new_empty(shape, dtype=torch.int32)

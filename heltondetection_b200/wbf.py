@@ -8,18 +8,25 @@ import numpy as np
 import torch
 from . import _lib
 
-_CONF = {"avg": _lib.WBF_AVG, "max": _lib.WBF_MAX}
+_CONF = {"avg": _lib.WBF_AVG, "max": _lib.WBF_MAX, "box_and_model_avg": _lib.WBF_BOX_AND_MODEL_AVG,
+         "absent_model_aware_avg": _lib.WBF_ABSENT_MODEL_AWARE_AVG}
 
 
 class WbfBatched:
     """boxes [B,V,M,4], scores [B,V,M], labels [B,V,M] (float), counts [B,V] int32 ->
     (boxes [B,V*M,4] f32, scores [B,V*M] f64, labels [B,V*M] f32, count [B] int32)."""
 
-    def __init__(self, num_labels, weights=None, iou_thr=0.55, skip_box_thr=0.0, conf_type="avg", allows_overflow=False):
+    def __init__(self, num_labels, weights=None, iou_thr=0.55, skip_box_thr=0.0, conf_type="avg", allows_overflow=False,
+                 rescale="len_weights"):
+        """rescale: the 'avg' confidence rescale of ensemble-boxes >= 1.0.5, min(n, len(weights)) ("len_weights", default), or of
+        older releases, min(n, sum(weights)) ("sum_weights"); identical for unit weights."""
         if conf_type not in _CONF:
-            raise RuntimeError(f'Unknown conf_type: {conf_type}. Must be "avg" or "max" (hd_b200 implements these two)')
+            raise RuntimeError(f'Unknown conf_type: {conf_type}. Must be "avg", "max", "box_and_model_avg" or "absent_model_aware_avg"')
+        if rescale not in ("len_weights", "sum_weights"):
+            raise RuntimeError('rescale must be "len_weights" or "sum_weights"')
         self.num_labels, self.weights = int(num_labels), weights
-        self.iou_thr, self.skip, self.conf, self.overflow = float(iou_thr), float(skip_box_thr), _CONF[conf_type], int(allows_overflow)
+        self.iou_thr, self.skip, self.overflow = float(iou_thr), float(skip_box_thr), int(allows_overflow)
+        self.conf = _CONF[conf_type] | (_lib.WBF_RESCALE_SUM_WEIGHTS if rescale == "sum_weights" else 0)
         self._key = None
 
     def _alloc(self, B, V, M, dev):
@@ -55,7 +62,7 @@ class WbfBatched:
 
 
 def weighted_boxes_fusion(boxes_list, scores_list, labels_list, weights=None, iou_thr=0.55, skip_box_thr=0.0,
-                          conf_type="avg", allows_overflow=False, device="cuda"):
+                          conf_type="avg", allows_overflow=False, device="cuda", rescale="len_weights"):
     """ensemble-boxes signature, one image: lists (one entry per model/view) of boxes [n,4] in [0,1], scores, labels
     -> (boxes [m,4], scores [m], labels [m]) numpy float64, sorted by fused score."""
     V = len(boxes_list)
@@ -74,7 +81,7 @@ def weighted_boxes_fusion(boxes_list, scores_list, labels_list, weights=None, io
             lab = torch.as_tensor(np.asarray(labels_list[v], np.float32))
             lb[0, v, :n] = lab
             mx = max(mx, int(lab.max().item()))
-    f = WbfBatched(mx + 1, weights, iou_thr, skip_box_thr, conf_type, allows_overflow)
+    f = WbfBatched(mx + 1, weights, iou_thr, skip_box_thr, conf_type, allows_overflow, rescale)
     ob, os_, ol, oc = f(bx.to(device), sc.to(device), lb.to(device), cnt.to(device))
     m = int(oc.item())
     return ob[0, :m].double().cpu().numpy(), os_[0, :m].cpu().numpy(), ol[0, :m].double().cpu().numpy()

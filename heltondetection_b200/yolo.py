@@ -110,7 +110,7 @@ class YoloPostprocessor:
 
     def __init__(self, anchors=DEFAULT_ANCHORS, strides=DEFAULT_STRIDES, conf_thres=0.25, iou_thres=0.45,
                  agnostic=False, max_det=300, max_nms=30000, max_wh=7680.0, class_mode="offset", ge=False,
-                 dense_read=False, one_call=True, device=None):
+                 dense_read=False, one_call=True, device=None, multi_label=False):
         """one_call: a single C-ABI call (hd_yolo_postprocess, internal workspace); False issues the decode and the
         NMS entry points separately (same kernels, candidate buffers visible).  device: where the outputs live;
         needed when `outputs` are pinned HOST tensors, which the kernel then reads directly over PCIe (zero-copy:
@@ -121,7 +121,9 @@ class YoloPostprocessor:
         self.conf_thres, self.iou_thres = float(conf_thres), float(iou_thres)
         self.max_det, self.max_nms, self.max_wh = int(max_det), int(max_nms), float(max_wh)
         self.class_mode = _lib.NMS_AGNOSTIC if agnostic else _CLASS_MODES[class_mode]
-        self.flags = (_lib.FLAG_CONF_GE if ge else 0) | (_lib.FLAG_DENSE_READ if dense_read else 0)
+        # multi_label (ultralytics eval setting): every (anchor, class) pair over the threshold is a candidate; idx = anchor*nc + class
+        self.flags = ((_lib.FLAG_CONF_GE if ge else 0) | (_lib.FLAG_DENSE_READ if dense_read else 0)
+                      | (_lib.FLAG_MULTI_LABEL if multi_label else 0))
         self._buf = None
 
     def buffers(self, B, cap, device):

@@ -49,6 +49,8 @@ extern "C" {
 #define HD_FLAG_DENSE_READ 2  /* stream every head element (no objectness-tile skip) */
 #define HD_FLAG_IN_F16 4      /* hd_yolo_decode_filter / hd_yolo_postprocess*: levels[].data points to IEEE half heads */
 #define HD_FLAG_IN_BF16 8     /* ... to bfloat16 heads.  Elements are widened to fp32 on load (exact); all arithmetic is fp32 */
+#define HD_FLAG_MULTI_LABEL 256 /* ultralytics multi_label: every (anchor, class) with obj*cls > thr is a candidate; index = anchor*nc + class.
+                                 * Candidates of an image beyond the buffer capacity (= anchors per image) are dropped. NCHW heads only. */
 #define HD_FLAG_IN_NHWC 128   /* ... to fp32 heads stored [B, H, W, A*(5+nc)] (torch channels_last of the NCHW head): the layout the
                                * final 1x1 conv produces; same candidates as the NCHW path */
 
@@ -65,6 +67,9 @@ HD_API const char* hd_last_error(void);
 /* kernels launched (or captured into a CUDA graph) by this library since it was loaded, over all threads and devices;
  * callers take differences (bench.py reports the launches of one step as `gpu_launches`) */
 HD_API unsigned long long hd_debug_launch_count(void);
+/* developer aid: cycle counters of the streamed RoIAlign kernel (enable != 0 allocates them on the current device; out8 != NULL
+ * synchronises, copies the 8 counters {tables, waits, row loop, output, items, producer waits, -, -} to the host and clears them) */
+HD_API int hd_debug_roi_profile(int enable, unsigned long long* out8 /*host, nullable*/);
 
 /* ---------------------------------------------------------------------------------------------
  * YOLOv5 head (README.md:9; lineage `decode_box` / `non_max_suppression`)
@@ -329,6 +334,11 @@ HD_API int hd_rpn_proposals(const hd_rpn_level* levels /*host*/, int n_levels, i
  * ------------------------------------------------------------------------------------------- */
 #define HD_WBF_AVG 0
 #define HD_WBF_MAX 1
+#define HD_WBF_BOX_AND_MODEL_AVG 2       /* score * n / sum(w of the boxes) * sum(w of the distinct models in the cluster) / sum(weights) */
+#define HD_WBF_ABSENT_MODEL_AWARE_AVG 3  /* score * n / (sum(w of the boxes) + sum(w of the models absent from the cluster)) */
+/* OR-ed into conf_type: the 'avg' rescale uses min(n, sum(weights)) (ensemble-boxes <= 1.0.4) instead of min(n, len(weights))
+ * (ensemble-boxes >= 1.0.5, the default).  The two agree for unit weights. */
+#define HD_WBF_RESCALE_SUM_WEIGHTS 256
 HD_API size_t hd_wbf_workspace_size(int B, int V, int M, int num_labels);
 HD_API int hd_wbf(const float* boxes, const float* scores, const float* labels, const int32_t* counts, int B, int V, int M,
                   int num_labels, const double* weights /*host, nullable*/, double iou_thr, double skip_box_thr, int conf_type,

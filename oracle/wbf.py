@@ -3,7 +3,9 @@
 Reference feature: README.md:19 (TTA fused by WBF).  The dependency is presumably
 ZFTurbo ``ensemble-boxes`` (PyPI; version unknown; NOT installed here) -- PARITY
 UNPINNED.  This is a restatement of its published ``weighted_boxes_fusion``
-('avg' / 'max' conf types), keeping its dtype conventions: rows are float64,
+(conf types 'avg', 'max', 'box_and_model_avg', 'absent_model_aware_avg'; the 'avg' rescale of
+releases >= 1.0.5, ``min(len(weights), n)``, with ``rescale="sum_weights"`` for the older
+``min(weights.sum(), n)``), keeping its dtype conventions: rows are float64,
 the fused box is accumulated in a float32 ``np.zeros(8)`` from float64 products,
 the confidence sum is float64, IoU matching is float64 with a strict ``>``.
 One deliberate fix-point: the original sorts with ``argsort()[::-1]`` (unstable);
@@ -80,7 +82,7 @@ def _find_matching_box(weighted, new_box, match_iou):
 
 
 def weighted_boxes_fusion(boxes_list, scores_list, labels_list, weights=None, iou_thr=0.55,
-                          skip_box_thr=0.0, conf_type="avg", allows_overflow=False):
+                          skip_box_thr=0.0, conf_type="avg", allows_overflow=False, rescale="len_weights"):
     """-> (boxes [m,4] f64, scores [m] f64, labels [m] f64), sorted by score desc."""
     if weights is None:
         weights = np.ones(len(boxes_list))
@@ -102,10 +104,22 @@ def weighted_boxes_fusion(boxes_list, scores_list, labels_list, weights=None, io
                 clusters.append([boxes[j].copy()])
                 weighted = np.vstack((weighted, boxes[j].copy()))
         for i in range(len(clusters)):
-            if conf_type == "max":
+            if conf_type == "box_and_model_avg":
+                cb = np.array(clusters[i])
+                weighted[i, 1] = weighted[i, 1] * len(cb) / weighted[i, 2]
+                _, idx = np.unique(cb[:, 3], return_index=True)
+                weighted[i, 1] = weighted[i, 1] * cb[idx, 2].sum() / weights.sum()
+            elif conf_type == "absent_model_aware_avg":
+                cb = np.array(clusters[i])
+                models = np.unique(cb[:, 3]).astype(int)
+                mask = np.ones(len(weights), dtype=bool)
+                mask[models] = False
+                weighted[i, 1] = weighted[i, 1] * len(cb) / (weighted[i, 2] + weights[mask].sum())
+            elif conf_type == "max":
                 weighted[i, 1] = weighted[i, 1] / weights.max()
             elif not allows_overflow:
-                weighted[i, 1] = weighted[i, 1] * min(len(clusters[i]), weights.sum()) / weights.sum()
+                cap = weights.sum() if rescale == "sum_weights" else len(weights)
+                weighted[i, 1] = weighted[i, 1] * min(len(clusters[i]), cap) / weights.sum()
             else:
                 weighted[i, 1] = weighted[i, 1] * len(clusters[i]) / weights.sum()
         overall.append(weighted)

@@ -65,8 +65,26 @@ def filter_candidates(pred_img, conf_thres, ge=False):
     return torch.cat((box, conf, j.float()), 1)[m], idx[m]
 
 
+def filter_candidates_multi_label(pred_img, conf_thres, ge=False):
+    """ultralytics multi_label=True: ``x[:, 5:] *= x[:, 4:5]``; ``i, j = (x[:, 5:] > conf_thres).nonzero().T``;
+    candidates = (box[i], x[i, 5 + j], j) in (anchor, class) order.  Returned index = anchor * nc + class."""
+    x = pred_img
+    obj = x[:, 4]
+    xc = (obj >= conf_thres) if ge else (obj > conf_thres)
+    idx = torch.nonzero(xc).flatten()
+    x = x[xc]
+    nc = x.shape[1] - 5
+    if x.shape[0] == 0:
+        return x.new_zeros((0, 6)), idx
+    cls = x[:, 5:] * x[:, 4:5]
+    box = xywh2xyxy(x[:, :4])
+    hit = (cls >= conf_thres) if ge else (cls > conf_thres)
+    i, j = hit.nonzero(as_tuple=False).T
+    return torch.cat((box[i], cls[i, j, None], j[:, None].float()), 1), idx[i] * nc + j
+
+
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, agnostic=False, max_det=300,
-                        max_nms=30000, max_wh=7680.0, class_mode="offset", ge=False, return_index=False):
+                        max_nms=30000, max_wh=7680.0, class_mode="offset", ge=False, return_index=False, multi_label=False):
     """A.2: per image filter -> (cap max_nms by conf) -> class-aware NMS -> first max_det.
 
     class_mode "offset": nms(boxes + cls*max_wh) (ultralytics);
@@ -75,7 +93,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, agnostic=Fa
     prediction = prediction.detach().cpu().float()
     out, out_idx = [], []
     for xi in range(prediction.shape[0]):
-        x, aidx = filter_candidates(prediction[xi], conf_thres, ge)
+        x, aidx = (filter_candidates_multi_label if multi_label else filter_candidates)(prediction[xi], conf_thres, ge)
         n = x.shape[0]
         if n > max_nms:
             o = torch.sort(x[:, 4], descending=True, stable=True)[1][:max_nms]

@@ -36,6 +36,33 @@ def test_wbf_matches_oracle(conf_type, weights, seed):
     assert np.array_equal(gb, rb) and np.array_equal(gs, rs)      # same dtype conventions -> identical bits
 
 
+@pytest.mark.parametrize("conf_type", ["box_and_model_avg", "absent_model_aware_avg"])
+@pytest.mark.parametrize("weights", [None, [2, 1, 1, 0.5]])
+def test_wbf_model_aware_conf_types(conf_type, weights):
+    """ensemble-boxes >= 1.0.5 conf types: the cluster's distinct models (views) enter the confidence rescale"""
+    import oracle
+    from heltondetection_b200 import wbf
+    bl, sl, ll = _views(3)
+    rb, rs, rl = oracle.wbf.weighted_boxes_fusion(bl, sl, ll, weights, 0.55, 0.1, conf_type)
+    gb, gs, gl = wbf.weighted_boxes_fusion(bl, sl, ll, weights, 0.55, 0.1, conf_type)
+    assert gb.shape == rb.shape and np.array_equal(gl, rl) and np.array_equal(gb, rb)
+    assert np.allclose(gs, rs, rtol=1e-12, atol=0)
+
+
+def test_wbf_rescale_rules_differ_only_for_non_unit_weights():
+    import oracle
+    from heltondetection_b200 import wbf
+    bl, sl, ll = _views(4)
+    for weights in (None, [2, 1, 1, 0.5]):
+        for rule in ("len_weights", "sum_weights"):
+            rb, rs, rl = oracle.wbf.weighted_boxes_fusion(bl, sl, ll, weights, 0.55, 0.1, "avg", False, rule)
+            gb, gs, gl = wbf.weighted_boxes_fusion(bl, sl, ll, weights, 0.55, 0.1, "avg", False, rescale=rule)
+            assert np.array_equal(gl, rl) and np.array_equal(gb, rb) and np.array_equal(gs, rs)
+    a = wbf.weighted_boxes_fusion(bl, sl, ll, None, 0.55, 0.1, rescale="len_weights")
+    b = wbf.weighted_boxes_fusion(bl, sl, ll, None, 0.55, 0.1, rescale="sum_weights")
+    assert np.array_equal(a[1], b[1])
+
+
 def test_wbf_edge_cases():
     import oracle
     from heltondetection_b200 import wbf

@@ -201,3 +201,27 @@ def test_bubbliiiing_per_class_output_order():
         assert got[b].shape == ref[b].shape
         assert torch.equal(got[b][:, 5].cpu(), ref[b][:, 5])
         assert torch.allclose(got[b].cpu(), ref[b], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("cfg", [(2, 640, 80, 20, 0.001, 0.6, False), (2, 1280, 10, 300, 0.001, 0.6, True), (2, 640, 80, 20, 0.25, 0.45, False)])
+def test_multi_label_matches_oracle(cfg):
+    """ultralytics multi_label=True (its evaluation setting): every (anchor, class) pair over the threshold is a candidate;
+    kept (anchor*nc + class) indices bit-exact, boxes/scores within 1e-5"""
+    import oracle
+    from heltondetection_b200 import synth, yolo
+    from _tol import close, boxes_close
+    B, img, nc, G, conf, iou, dense = cfg
+    heads, _ = synth.yolo_heads(B, img, nc, G, 77, dense=dense)
+    pred = oracle.yolo.decode_box(heads)
+    ref, ridx = oracle.yolo.non_max_suppression(pred, conf, iou, return_index=True, multi_label=True)
+    ref1 = oracle.yolo.non_max_suppression(pred, conf, iou)
+    for dense_read in (True, False):
+        pp = yolo.YoloPostprocessor(conf_thres=conf, iou_thres=iou, multi_label=True, dense_read=dense_read)
+        det, cnt, idx = pp([h.cuda() for h in heads])
+        for b in range(B):
+            n = int(cnt[b])
+            assert n == ridx[b].numel() and torch.equal(idx[b, :n].cpu(), ridx[b]), f"image {b}"
+            assert boxes_close(det[b, :n, :4], ref[b][:, :4]) and close(det[b, :n, 4], ref[b][:, 4], scale=1e-3)
+            assert torch.equal(det[b, :n, 5].cpu(), ref[b][:, 5])
+    if conf < 0.01:
+        assert any(r.shape[0] != s.shape[0] or not torch.equal(r, s) for r, s in zip(ref, ref1)), "multi_label should change the low-threshold result"
