@@ -37,6 +37,7 @@ struct RsParams {
     int* unit_count; int* unit_start; int* unit_cursor; int* unit_ymax;
     RsItem* tmp; int* tmp_unit; RsItem* scat; RsItem* items; int* tables;
     int* n_tmp; int* fb_count; int* fb_list;
+    int dbg;                    // developer switches (hd_roi_set_mode bits 4..): 1 no prefetch, 2 no row walk, 4 no tile store
     unsigned long long* prof;   // nullable developer counters: [0] table cycles [1] wait cycles [2] row-loop cycles [3] output cycles [4] items [5] producer wait
 };
 struct RsMaps { CUtensorMap m[HD_MAX_LEVELS]; };
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) rs_prep_kernel(const __grid_constant__ Rs
     if (strip) {
         const RsLevel& L = p.lv[G.lvl];
         strip = rs_axis_range(G.sw, G.bw, G.g, L.W, 0, p.PW, &x0, &x1) && rs_axis_range(G.sh, G.bh, G.g, L.H, 0, p.PH, &ya, &yb);
-        strip = strip && (L.S == 1 || x1 - x0 <= RS_HALO);
+        strip = strip && (L.S == 1 || x1 - x0 <= RS_HALO) && (p.NR <= RS_MAXROWS || yb - ya + 1 <= RS_MAXROWS);   // the item table holds <= 32 rows
         if (strip && yb - ya + 1 > p.NR - 3) {   // tall: two bin-row ranges, each with its own (shorter) row span
             split = (p.PH + 1) / 2;
             const bool a = rs_axis_range(G.sh, G.bh, G.g, L.H, 0, split, &ya, &yb);
@@ -106,9 +107,23 @@ __global__ void __launch_bounds__(256) rs_prep_kernel(const __grid_constant__ Rs
         return;
     }
     const int n = split ? 2 : 1;
-    const int at = atomicAdd(p.n_tmp, n);
-    atomicAdd(p.unit_count + unit, n);
-    atomicMax(p.unit_ymax + unit, split ? max(yb, yd) : yb);
+    // a few hundred buckets take all K updates: aggregate per warp (lanes of one bucket elect a leader) before touching memory
+    const unsigned peers = __match_any_sync(__activemask(), unit);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    int nsum = 0, ymx = -1, rank = 0;
+    for (unsigned m = peers; m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const int on = __shfl_sync(peers, n, src), oy = __shfl_sync(peers, split ? max(yb, yd) : yb, src);
+        if (src < lane) rank += on;
+        nsum += on; ymx = max(ymx, oy);
+    }
+    int base = 0;
+    if (lane == leader) {
+        base = atomicAdd(p.n_tmp, nsum);
+        atomicAdd(p.unit_count + unit, nsum);
+        atomicMax(p.unit_ymax + unit, ymx);
+    }
+    const int at = __shfl_sync(peers, base, leader) + rank;
     RsItem it;
     it.k = (int)k;
     it.pr = (split ? (split << 8) : (p.PH << 8)) | (unit << 16); it.y0 = ya; it.y1 = yb;
@@ -450,6 +465,111 @@ __global__ void __launch_bounds__(RS_THREADS, 1) roi_align_strip_kernel(const __
     if (lane == 0) *reinterpret_cast<volatile int*>(&prog[wid]) = 0x7fffffff;
 }
 
+// ------------------------------------------------------------------------------------------------ row-walk kernel
+// One CTA per RoI (in the bucketed order, so neighbouring CTAs work on neighbouring rows of one feature map), thread = (channel quad,
+// bin-column pair).  The RoI's feature rows are walked ONCE: per row a thread forms the x-interpolated value of its two bin columns
+// from at most 2x4 128-bit loads, then adds it into the bin rows that row feeds (the (row, bin row, weight) pairs of the item table).
+// The per-RoI gather kernel of roi.cu visits every row once per bin row it feeds (~1.8x the loads, ~4x the instructions); the sums
+// are formed in the same order, so the results are identical.  Output through the [C, PH*PW] shared tile + one TMA bulk store.
+__global__ void __launch_bounds__(512, 2) roi_align_rowwalk_kernel(const __grid_constant__ RsParams p, const __grid_constant__ RoiParams g) {
+    extern __shared__ __align__(128) float tile[];           // [C][PH*PW]
+    __shared__ __align__(16) int T[RS_TABW];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    if (i >= *p.n_tmp) return;
+    if (tid < 32) reinterpret_cast<int4*>(T)[tid] = __ldg(reinterpret_cast<const int4*>(p.tables + (size_t)i * RS_TABW) + tid);
+    __syncthreads();
+    const int k = T[120], y0 = T[122], np = T[63];
+    const int unit = p.items[i].pr >> 16;
+    const int img = unit / p.units_per_img, rem = unit - img * p.units_per_img;
+    int lvl = 0;
+#pragma unroll
+    for (int q = 1; q < HD_MAX_LEVELS; ++q)
+        if (q < p.n_levels && rem >= p.lv[q].unit_base) lvl = q;
+    const int W = p.lv[lvl].W, nq = p.C >> 2, nb = p.PH * p.PW;
+    const float4* __restrict__ f = reinterpret_cast<const float4*>(g.data[lvl]) + (size_t)img * p.lv[lvl].H * W * nq;
+    const float inv = 1.0f / (float)max(p.sr * p.sr, 1);
+    const bool pow2 = ((p.sr * p.sr) & (p.sr * p.sr - 1)) == 0;
+    // thread = (channel quad, bin column): 64 quads x 8 column slots (PW <= 7 of them used); 2 CTAs = 32 warps per SM, because the
+    // walk is a chain of dependent row loads and only many warps hide its latency
+    const int groups = 64;
+    const int pw = tid / groups;
+    const bool on = pw < p.PW;
+    int xo[RS_E]; float wx[RS_E];
+    const int nx = on ? T[56 + pw] : 0;
+    {   // table x offsets are (cell - strip start) * 32 with strip start 0 here: cell = off / 32
+        const int4 o4 = reinterpret_cast<const int4*>(T)[on ? pw : 0];
+        const float4 w4 = reinterpret_cast<const float4*>(T + 28)[on ? pw : 0];
+        xo[0] = (o4.x >> 5) * nq; xo[1] = (o4.y >> 5) * nq; xo[2] = (o4.z >> 5) * nq; xo[3] = (o4.w >> 5) * nq;
+        wx[0] = w4.x; wx[1] = w4.y; wx[2] = w4.z; wx[3] = w4.w;
+    }
+    // The walk below is a chain of dependent row loads, and on a pyramid larger than L2 every link would pay a full DRAM round
+    // trip (~1 us loaded: measured 15 us per RoI).  So every thread first asks L2 for all the lines it is going to read.
+    {
+        const int nrows = (p.dbg & 1) ? 0 : T[123] - y0 + 1;
+        for (int q = tid % groups; q < nq && on; q += groups)
+            for (int rr = 0; rr < nrows; ++rr) {
+                const float4* row = f + (size_t)(y0 + rr) * W * nq + q;
+#pragma unroll
+                for (int e = 0; e < RS_E; ++e)
+                    if (e < nx) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + xo[e]));
+            }
+    }
+    for (int q = tid % groups; q < nq && on; q += groups) {
+        float4 acc[RS_P];
+#pragma unroll
+        for (int a = 0; a < RS_P; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cur = -1;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < ((p.dbg & 2) ? 0 : np); ++j) {
+            const int code = T[64 + j];
+            const float wy = __int_as_float(T[92 + j]);
+            const int rr = code >> 8;
+            if (rr != cur) {
+                cur = rr;
+                const float4* __restrict__ row = f + (size_t)(y0 + rr) * W * nq + q;
+                float4 v[RS_E];
+#pragma unroll
+                for (int e = 0; e < RS_E; ++e) v[e] = e < nx ? __ldg(row + xo[e]) : make_float4(0.f, 0.f, 0.f, 0.f);   // up to 4 requests in flight
+                t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int e = 0; e < RS_E; ++e)
+                    if (e < nx) { t.x = fmaf(wx[e], v[e].x, t.x); t.y = fmaf(wx[e], v[e].y, t.y); t.z = fmaf(wx[e], v[e].z, t.z); t.w = fmaf(wx[e], v[e].w, t.w); }
+            }
+            switch (code & 255) {   // CTA-uniform: the accumulators stay in statically indexed registers
+#define RS_ROW(k_) case k_: acc[k_].x = fmaf(wy, t.x, acc[k_].x); acc[k_].y = fmaf(wy, t.y, acc[k_].y); acc[k_].z = fmaf(wy, t.z, acc[k_].z); acc[k_].w = fmaf(wy, t.w, acc[k_].w); break;
+                RS_ROW(0) RS_ROW(1) RS_ROW(2) RS_ROW(3) RS_ROW(4) RS_ROW(5) RS_ROW(6)
+#undef RS_ROW
+                default: break;
+            }
+        }
+        const int rot = (tid & 31) >> 3;                      // lane-rotated store order: the 32 lanes of a step hit 32 banks
+#pragma unroll
+        for (int ph = 0; ph < RS_P; ++ph) {
+            if (ph >= p.PH) continue;
+            const float4 a4 = acc[ph];
+            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = pow2 ? v[c] * inv : __fdiv_rn(v[c], (float)(p.sr * p.sr));
+            float* tq = tile + (size_t)(4 * q) * nb + ph * p.PW + pw;
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2) {
+                const int c = (s2 + rot) & 3;
+                tq[c * nb] = c == 0 ? v[0] : (c == 1 ? v[1] : (c == 2 ? v[2] : v[3]));
+            }
+        }
+    }
+    // tile -> out[k]: one TMA bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0 && !(p.dbg & 4)) {
+        const unsigned saddr = (unsigned)__cvta_generic_to_shared(tile);
+        float* gdst = p.out + (size_t)k * p.C * nb;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(p.C * nb * 4) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 typedef CUresult (*RsEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -489,20 +609,20 @@ static void rs_ws_layout(int n_units, long long K, size_t* offs, size_t* total) 
 
 // levels -> strips; returns false when the streamed kernel does not apply to this call
 static bool rs_plan(RsParams& p, const hd_roi_level* levels, int n_levels, int C, int batch, int PH, int PW, int sr, int64_t K, size_t* smem_out,
-                    int* ring_off, int* tab_off) {
+                    int* ring_off, int* tab_off, bool streamed) {
     if (C % RS_CS != 0 || PH < 1 || PW < 1 || PH > RS_P || PW > RS_P || sr < 1 || sr > 2 || batch < 1 || K < 512 || K >= (1ll << 30)) return false;
     const int nb = PH * PW, tstride = nb | 1;
     const size_t tiles = hd_align_up((size_t)RS_NTILE * RS_CS * tstride * 4, 128);
     const size_t tabs = hd_align_up((size_t)RS_NCW * RS_TABW * 4, 128);
     const size_t budget = 224 * 1024;   // dynamic shared memory; the 227 KB of an SM also hold this kernel's static barriers
     if (tiles + tabs + (size_t)RS_NR * (RS_HALO + 8) * RS_CS * 4 > budget) return false;
-    const int rw_cap = (int)((budget - tiles - tabs) / ((size_t)RS_NR * RS_CS * 4));
+    const int rw_cap = streamed ? (int)((budget - tiles - tabs) / ((size_t)RS_NR * RS_CS * 4)) : 65535;   // row-walk: no strips
     int units = 0, rw_max = 0;
     for (int l = 0; l < n_levels; ++l) {
         RsLevel& L = p.lv[l];
         L.H = levels[l].H; L.W = levels[l].W; L.scale = levels[l].spatial_scale;
         if (L.H > RS_MAXH || L.W > 65535 || (((uintptr_t)levels[l].data) & 15) != 0) return false;
-        if (L.W <= rw_cap && L.W <= 256) { L.S = 1; L.SW = L.W; L.RW = L.W; }
+        if (L.W <= rw_cap && (L.W <= 256 || !streamed)) { L.S = 1; L.SW = L.W; L.RW = L.W; }
         else {
             const int rw = rw_cap < 256 ? rw_cap : 256;
             if (rw - RS_HALO < 8) return false;
@@ -512,10 +632,11 @@ static bool rs_plan(RsParams& p, const hd_roi_level* levels, int n_levels, int C
         if (L.RW > rw_max) rw_max = L.RW;
     }
     if ((long long)units * batch > 65535) return false;
-    p.n_levels = n_levels; p.C = C; p.PH = PH; p.PW = PW; p.sr = sr; p.B = batch; p.NR = RS_NR;
+    p.n_levels = n_levels; p.C = C; p.PH = PH; p.PW = PW; p.sr = sr; p.B = batch; p.NR = streamed ? RS_NR : (1 << 20);   // row-walk: never split
     p.units_per_img = units; p.n_units = units * batch; p.K = K;
     *ring_off = (int)tiles; *tab_off = (int)(tiles + hd_align_up((size_t)RS_NR * rw_max * RS_CS * 4, 128));
     *smem_out = (size_t)*tab_off + tabs;
+    if (!streamed) { *smem_out = (size_t)C * nb * 4; return C % 4 == 0 && (C * nb * 4) % 16 == 0 && *smem_out <= 200 * 1024; }
     return *smem_out <= 226 * 1024;
 }
 
@@ -525,7 +646,9 @@ extern "C" HD_API size_t hd_roi_align_workspace_size(const hd_roi_level* levels,
     memset(&p, 0, sizeof(p));
     size_t smem; int ro, to;
     if (!levels || n_levels < 1 || n_levels > HD_MAX_LEVELS || K < 0) return 0;
-    if (!rs_plan(p, levels, n_levels, C, batch, pooled_h, pooled_w, sampling_ratio, K, &smem, &ro, &to)) return 256;
+    const int mode = hd_roi_mode() & 15;
+    if (mode != 2 && mode != 3) return 256;   // the default per-RoI gather kernels need no workspace
+    if (!rs_plan(p, levels, n_levels, C, batch, pooled_h, pooled_w, sampling_ratio, K, &smem, &ro, &to, mode == 2)) return 256;
     size_t offs[8], total;
     rs_ws_layout(p.n_units, K, offs, &total);
     return total + 256;
@@ -539,8 +662,14 @@ extern "C" HD_API int hd_roi_align_ws(const hd_roi_level* levels, int n_levels, 
     memset(&p, 0, sizeof(p));
     size_t smem = 0; int ring_off = 0, tab_off = 0;
     RsEncodeFn enc = rs_encode_fn();
-    bool ok = layout == HD_LAYOUT_NHWC && (hd_roi_mode() & 15) != 1 && enc != nullptr && workspace != nullptr && (n_levels == 1 || level_ids != nullptr) &&
-              rs_plan(p, levels, n_levels, C, batch, pooled_h, pooled_w, sampling_ratio, K, &smem, &ring_off, &tab_off);
+    // hd_roi_set_mode: 0 / 1 per-RoI gather kernels (the fastest measured on B200: 1.25 ms on cfg3), 2 streamed (TMA ring) kernel
+    // (2.46 ms), 3 row-walk kernel over the bucketed RoIs (1.80 ms).  2 and 3 are bit-identical to the gather kernels and kept as
+    // tested, opt-in experiments; DESIGN.md section 3 has the measurements and why they lose.
+    const int mode = hd_roi_mode() & 15;
+    const bool streamed = mode == 2;
+    bool ok = layout == HD_LAYOUT_NHWC && (mode == 2 || mode == 3) && (enc != nullptr || !streamed) && workspace != nullptr &&
+              (n_levels == 1 || level_ids != nullptr) && (((uintptr_t)out) & 15) == 0 &&
+              rs_plan(p, levels, n_levels, C, batch, pooled_h, pooled_w, sampling_ratio, K, &smem, &ring_off, &tab_off, streamed);
     size_t offs[8], total = 0;
     uintptr_t w0 = hd_align_up((uintptr_t)workspace, 256);
     if (ok) {
@@ -548,7 +677,7 @@ extern "C" HD_API int hd_roi_align_ws(const hd_roi_level* levels, int n_levels, 
         ok = w0 + total <= (uintptr_t)workspace + workspace_bytes;
     }
     RsMaps maps;
-    if (ok) {
+    if (ok && streamed) {
         memset(&maps, 0, sizeof(maps));
         for (int l = 0; l < n_levels && ok; ++l) {
             const RsLevel& L = p.lv[l];
@@ -571,7 +700,7 @@ extern "C" HD_API int hd_roi_align_ws(const hd_roi_level* levels, int n_levels, 
     p.unit_start = (int*)(w0 + offs[1]);
     p.tmp = (RsItem*)(w0 + offs[2]); p.tmp_unit = (int*)(w0 + offs[3]); p.scat = (RsItem*)(w0 + offs[4]); p.items = (RsItem*)(w0 + offs[5]);
     p.fb_list = (int*)(w0 + offs[6]); p.tables = (int*)(w0 + offs[7]);
-    p.prof = g_rs_prof;
+    p.prof = g_rs_prof; p.dbg = hd_roi_mode() >> 4;
     HD_CUDA_CALL(cudaMemsetAsync(zero, 0, (nu * 3 + 4) * 4, st));
     rs_prep_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(p);
     HD_CUDA_LAUNCH_CHECK("rs_prep_kernel");
@@ -583,15 +712,21 @@ extern "C" HD_API int hd_roi_align_ws(const hd_roi_level* levels, int n_levels, 
     HD_CUDA_LAUNCH_CHECK("rs_sort_kernel");
     rs_table_kernel<<<(unsigned)((2 * K + 7) / 8), 256, 0, st>>>(p);
     HD_CUDA_LAUNCH_CHECK("rs_table_kernel");
-    HD_ENSURE_SMEM(roi_align_strip_kernel, 226 * 1024);
-    roi_align_strip_kernel<<<dim3((unsigned)(C / RS_CS), (unsigned)p.n_units), RS_THREADS, smem, st>>>(p, maps, ring_off, tab_off);
-    HD_CUDA_LAUNCH_CHECK("roi_align_strip_kernel");
-    // hand-back list (device-side count): gather kernel, grid-stride over the list
     RoiParams g;
     memset(&g, 0, sizeof(g));
     for (int l = 0; l < n_levels; ++l) { g.data[l] = levels[l].data; g.H[l] = levels[l].H; g.W[l] = levels[l].W; g.scale[l] = levels[l].spatial_scale; }
     g.n_levels = n_levels; g.C = C; g.PH = pooled_h; g.PW = pooled_w; g.sampling_ratio = sampling_ratio; g.aligned = p.aligned;
     g.rois = rois; g.level_ids = level_ids; g.K = K; g.out = out;
+    if (streamed) {
+        HD_ENSURE_SMEM(roi_align_strip_kernel, 226 * 1024);
+        roi_align_strip_kernel<<<dim3((unsigned)(C / RS_CS), (unsigned)p.n_units), RS_THREADS, smem, st>>>(p, maps, ring_off, tab_off);
+        HD_CUDA_LAUNCH_CHECK("roi_align_strip_kernel");
+    } else {
+        HD_ENSURE_SMEM(roi_align_rowwalk_kernel, 200 * 1024);
+        roi_align_rowwalk_kernel<<<(unsigned)K, 512, smem, st>>>(p, g);   // items <= K (never split); CTAs beyond the item count exit
+        HD_CUDA_LAUNCH_CHECK("roi_align_rowwalk_kernel");
+    }
+    // hand-back list (device-side count): gather kernel, grid-stride over the list
     long long ctas = K < 4 * (long long)hd_num_sms() ? K : 4 * (long long)hd_num_sms();
     return hd_roi_align_launch_list(g, p.fb_list, p.fb_count, (int)ctas, st);
 }

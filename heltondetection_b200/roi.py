@@ -10,7 +10,8 @@ from . import _lib
 
 
 def set_mode(mode):
-    """RoIAlign kernel choice: 0 auto, 1 gather kernels only, 2 staged-row (TMA ring) kernel whenever eligible; returns the previous mode."""
+    """RoIAlign kernel choice for many RoIs on NHWC features: 0 / 1 per-RoI gather kernels (default: the fastest measured), 2 streamed
+    (TMA ring) kernel, 3 row-walk kernel over the device-bucketed RoIs -- 2 and 3 are bit-identical, slower, opt-in; returns the previous mode."""
     return _lib.lib().hd_roi_set_mode(int(mode))
 
 

@@ -110,12 +110,16 @@ class YoloPostprocessor:
 
     def __init__(self, anchors=DEFAULT_ANCHORS, strides=DEFAULT_STRIDES, conf_thres=0.25, iou_thres=0.45,
                  agnostic=False, max_det=300, max_nms=30000, max_wh=7680.0, class_mode="offset", ge=False,
-                 dense_read=False, one_call=True, device=None, multi_label=False):
+                 dense_read=False, one_call=True, device=None, multi_label=False, multi_label_cap=4):
         """one_call: a single C-ABI call (hd_yolo_postprocess, internal workspace); False issues the decode and the
         NMS entry points separately (same kernels, candidate buffers visible).  device: where the outputs live;
         needed when `outputs` are pinned HOST tensors, which the kernel then reads directly over PCIe (zero-copy:
         only the sectors of possible survivors are fetched)."""
-        self.one_call, self.device = bool(one_call), (torch.device(device) if device is not None else None)
+        # multi_label needs candidate buffers larger than one slot per anchor: up to multi_label_cap (anchor, class) pairs per anchor
+        # on average (an image with more is truncated arbitrarily -- `overflowed()` tells); that uses the two-call path, whose
+        # capacity the caller chooses, instead of the one-call entry point, which sizes its workspace for one slot per anchor
+        self.multi_label, self.multi_cap = bool(multi_label), max(1, int(multi_label_cap))
+        self.one_call, self.device = bool(one_call) and not multi_label, (torch.device(device) if device is not None else None)
         self._fkey = None
         self.anchors, self.strides = anchors, strides
         self.conf_thres, self.iou_thres = float(conf_thres), float(iou_thres)
@@ -178,13 +182,18 @@ class YoloPostprocessor:
         if peer is not None:
             raise RuntimeError("replicated (peer) outputs need the one-call path")
         dev = self._out_device(keep)
-        buf = self.buffers(B, total, dev)
+        buf = self.buffers(B, min(total * min(nc, self.multi_cap), 500000) if self.multi_label else total, dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().hd_yolo_decode_filter(
                 arr, len(keep), B, A, nc, self.conf_thres, self.flags | self._dflag, _lib.ptr(buf.box), _lib.ptr(buf.score),
                 _lib.ptr(buf.cls), _lib.ptr(buf.anchor), _lib.ptr(buf.count), buf.cap, _lib.stream()))
             _run_nms(buf, self.iou_thres, self.class_mode, self.max_wh, self.max_nms)
         return buf.det, buf.out_count, buf.idx
+
+    def overflowed(self):
+        """multi_label: True if some image of the last call had more candidates than the buffer holds (one host sync)"""
+        b = self._buf
+        return bool(b is not None and int(b.count.max()) > b.cap)
 
     def graph(self, outputs, warmup=3, peer=None, slot=0):
         """Capture one post-process of `outputs` (fixed buffers) into a CUDA graph; returns (replay, det, count, idx).

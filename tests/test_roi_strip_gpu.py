@@ -1,4 +1,4 @@
-"""Streamed (TMA ring) RoIAlign kernel against the per-RoI gather kernels and torchvision's CPU op."""
+"""Row-walk (default) and streamed (TMA ring, opt-in) RoIAlign kernels against the per-RoI gather kernels and torchvision's CPU op."""
 import pytest
 import torch
 import torchvision
@@ -20,16 +20,21 @@ def _rois(B, per_img, img, seed, big=0.15):
     return r
 
 
+@pytest.mark.parametrize("mode", [3, 2])
 @pytest.mark.parametrize("aligned", [False, True])
 @pytest.mark.parametrize("sr", [2, 1])
-def test_strip_equals_gather_multilevel(sr, aligned):
+def test_strip_equals_gather_multilevel(sr, aligned, mode):
     from heltondetection_b200 import ops, roi
     B, img, C = 3, 416, 64
     g = torch.Generator().manual_seed(5)
     feats = [torch.randn((B, C, img // s, img // s), generator=g).cuda().contiguous(memory_format=torch.channels_last) for s in (4, 8, 16, 32)]
     rois = _rois(B, 700, img, 11).cuda()
     scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
-    a, la = ops.multilevel_roi_align(feats, rois, 7, scales, sr, aligned)
+    old = roi.set_mode(mode)       # 3: row-walk kernel over the bucketed RoIs, 2: streamed kernel
+    try:
+        a, la = ops.multilevel_roi_align(feats, rois, 7, scales, sr, aligned)
+    finally:
+        roi.set_mode(old)
     old = roi.set_mode(1)
     try:
         b, lb = ops.multilevel_roi_align(feats, rois, 7, scales, sr, aligned)
@@ -39,15 +44,20 @@ def test_strip_equals_gather_multilevel(sr, aligned):
     assert torch.equal(a, b), f"max abs diff {(a - b).abs().max().item():.3e}, rows differing {(a != b).flatten(1).any(1).sum().item()}"
 
 
+@pytest.mark.parametrize("mode", [3, 2])
 @pytest.mark.parametrize("PH,PW", [(7, 7), (5, 3), (6, 6)])
-def test_strip_single_level_vs_torchvision_cpu(PH, PW):
-    from heltondetection_b200 import ops
+def test_strip_single_level_vs_torchvision_cpu(PH, PW, mode):
+    from heltondetection_b200 import ops, roi
     B, H, W, C = 2, 120, 300, 32            # W > one strip: exercises the strip halo
     g = torch.Generator().manual_seed(9)
     x = torch.randn((B, C, H, W), generator=g)
     rois = _rois(B, 600, 1200, 3)
     rois[:, 2] *= 0.4; rois[:, 4] *= 0.4
-    got = ops.roi_align(x.cuda().contiguous(memory_format=torch.channels_last), rois.cuda(), (PH, PW), 0.25, 2, False)
+    old = roi.set_mode(mode)
+    try:
+        got = ops.roi_align(x.cuda().contiguous(memory_format=torch.channels_last), rois.cuda(), (PH, PW), 0.25, 2, False)
+    finally:
+        roi.set_mode(old)
     ref = torchvision.ops.roi_align(x, rois, (PH, PW), 0.25, 2, False)
     d = (got.cpu().double() - ref.double()).abs()
     assert bool((d <= 1e-5 * ref.double().abs().clamp(min=1.0)).all()), float(d.max())

@@ -218,6 +218,7 @@ def test_multi_label_matches_oracle(cfg):
     for dense_read in (True, False):
         pp = yolo.YoloPostprocessor(conf_thres=conf, iou_thres=iou, multi_label=True, dense_read=dense_read)
         det, cnt, idx = pp([h.cuda() for h in heads])
+        assert not pp.overflowed()
         for b in range(B):
             n = int(cnt[b])
             assert n == ridx[b].numel() and torch.equal(idx[b, :n].cpu(), ridx[b]), f"image {b}"

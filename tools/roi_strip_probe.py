@@ -30,17 +30,18 @@ lv = ops.level_map(rois[:, 1:])
 print("rois per level:", [int((lv == l).sum()) for l in range(4)])
 w = (rois[:, 3] - rois[:, 1]); h = (rois[:, 4] - rois[:, 2])
 print("roi side px: mean %.1f  p50 %.1f  p90 %.1f  max %.1f" % (float(w.mean()), float(w.median()), float(w.kthvalue(int(0.9 * w.numel()))[0]), float(w.max())))
-for mode, name in ((0, "streamed"), (1, "gather")):
+for mode, name in ((3, "row-walk"), (2, "streamed"), (1, "gather")):
     roi.set_mode(mode)
     for sr in (2,):
         t = timed(lambda: roi.multilevel_roi_align(feats, rois, 7, scales, sr, False))
         print(f"{name:9s} sr={sr}: {t * 1e3:8.1f} us  {nbytes / t / 1e6:7.1f} GB/s ({nbytes / t / 1e6 / 6536.7 * 100:.1f}% of measured peak)")
-roi.set_mode(0)
-a = roi.multilevel_roi_align(feats, rois, 7, scales, 2, False)[0]
 roi.set_mode(1)
 b = roi.multilevel_roi_align(feats, rois, 7, scales, 2, False)[0]
-roi.set_mode(0)
-print("bit-equal:", bool(torch.equal(a, b)))
+for mode in (3, 2):
+    roi.set_mode(mode)
+    a = roi.multilevel_roi_align(feats, rois, 7, scales, 2, False)[0]
+    print("mode", mode, "bit-equal to gather:", bool(torch.equal(a, b)))
+roi.set_mode(2)
 import ctypes as C
 from heltondetection_b200 import _lib
 L = _lib.lib()
