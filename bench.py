@@ -41,7 +41,7 @@ def parse():
                     help="dense: every head byte is read (roofline-honest headline); sparse: objectness-tile skip")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the global batch is sharded over the ranks (the contracted config); weak: --batch images per rank")
-    ap.add_argument("--depth", type=int, default=2, help="software-pipeline depth (CUDA streams)")
+    ap.add_argument("--depth", type=int, default=3, help="software-pipeline depth (CUDA streams); 3 measured best at 32 images per step")
     ap.add_argument("--batch", type=int, default=BATCH, help="global batch (strong) / per-rank batch (weak)")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-sample", type=int, default=32)
@@ -342,7 +342,7 @@ def main():
     gather, peer, gather_mode, gather_parity = None, None, "none", None
     if world > 1:
         try:
-            peer = hd_dist.PeerDetectionBuffers(Bl, MAX_DET, dev, slots=depth)
+            peer = hd_dist.PeerDetectionBuffers(Bl, MAX_DET, dev, slots=2 * depth)
             gather_mode = "fused: NMS kernels write into every peer's gather buffer over NVLink (symmetric memory) + per-step device barrier"
         except Exception as e:  # noqa: BLE001
             peer = None
@@ -421,8 +421,8 @@ def main():
     # ---------------- e2e: public API with HOST (pinned) inputs; host<->device traffic inside the timed region, every step
     own_cpu = pool_cpu[0]
     pinned = [h.contiguous().pin_memory() for h in own_cpu]
-    det_h = [torch.empty((Bl, MAX_DET, 6), dtype=torch.float32).pin_memory() for _ in range(depth)]
-    cnt_h = [torch.empty((Bl,), dtype=torch.int32).pin_memory() for _ in range(depth)]
+    det_h = [torch.empty((Bl, MAX_DET, 6), dtype=torch.float32).pin_memory() for _ in range(2 * depth)]
+    cnt_h = [torch.empty((Bl,), dtype=torch.int32).pin_memory() for _ in range(2 * depth)]
     stages = [[torch.empty_like(h, device=dev) for h in own_cpu] for _ in range(depth)]
     pipe_copy = yolo.PostprocessPipeline(stages, depth=depth, peer=peer, device=dev, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=False)
     e2e_steps = max(args.e2e_steps, 2) * (world if strong else 1)
@@ -437,8 +437,8 @@ def main():
                         s_.copy_(p_, non_blocking=True)
             det, cnt, _ = p.step(k)
             with torch.cuda.stream(s):
-                det_h[k % depth].copy_(det, non_blocking=True)
-                cnt_h[k % depth].copy_(cnt, non_blocking=True)
+                det_h[k % (2 * depth)].copy_(det, non_blocking=True)
+                cnt_h[k % (2 * depth)].copy_(cnt, non_blocking=True)
         p.join()
         torch.cuda.synchronize()
 

@@ -494,6 +494,7 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
     if (!heavy) {
         // light variant: 256 threads, radix sort through the global scratch, 1024-bucket pruning grid; co-resident with other kernels
         p.bitonic_cap = 0;
+        HD_ENSURE_SMEM(sort_nms_kernel<256>, 80 * 1024);   // the removed-bitmap of a large cap exceeds the 48 KB default
         sort_nms_kernel<256><<<B, 256, words * 4, st>>>(p);
         HD_CUDA_LAUNCH_CHECK("sort_nms_kernel<256>");
         return HD_OK;

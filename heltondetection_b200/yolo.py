@@ -275,8 +275,9 @@ class PostprocessPipeline:
     Step k runs on stream k % depth with its own workspace and output buffers, so the (latency-bound, few-SM) NMS kernels of
     step k overlap the (HBM-bound) decode kernel of step k+1, and the drain of one decode grid is filled by the head of the next.
     Every step is one CUDA-graph replay of the single C-ABI call.  `pool` is a list of input sets (each the list of head tensors of
-    one batch); step k reads pool[k % len(pool)].  With `peer` (dist.PeerDetectionBuffers with >= depth slots) the NMS kernels
-    store their rows into every rank's gather buffer and a cross-GPU barrier follows each step on the step's own stream.
+    one batch); step k reads pool[k % len(pool)].  With `peer` (dist.PeerDetectionBuffers, slots a multiple of depth; 2*depth keeps
+    the barrier off the critical path) the NMS kernels store their rows into every rank's gather buffer; the cross-GPU barrier that
+    marks a step complete runs on a side stream, and a gather-buffer slot is only rewritten after the barrier of its previous use.
 
         pipe = PostprocessPipeline(pool, depth=2, conf_thres=0.25)
         pipe.fork(); [pipe.step(k) for k in range(K)]; pipe.join()      # outputs of step k: pipe.outputs(k)
@@ -287,17 +288,23 @@ class PostprocessPipeline:
         self.pool, self.depth, self.peer = list(pool), int(depth), peer
         first = self.pool[0][0]
         self.device = torch.device(device) if device is not None else first.device
-        if peer is not None and peer.slots < self.depth:
-            raise RuntimeError("peer buffers need one slot per pipeline stage")
+        if peer is not None and (peer.slots < self.depth or peer.slots % self.depth):
+            raise RuntimeError("peer buffers need a multiple of `depth` slots")
         self.streams = [torch.cuda.Stream(self.device) for _ in range(self.depth)]
         self.pps = [YoloPostprocessor(device=self.device, **pp_kwargs) for _ in range(self.depth)]
-        self.n_graphs = len(self.pool) * self.depth // math.gcd(len(self.pool), self.depth)
+        self.n_slots = peer.slots if peer is not None else self.depth
+        self.n_graphs = len(self.pool) * self.n_slots // math.gcd(len(self.pool), self.n_slots)
+        if peer is not None:
+            self.side = torch.cuda.Stream(self.device)
+            self._stepped = [torch.cuda.Event() for _ in range(self.n_slots)]
+            self._gathered = [torch.cuda.Event() for _ in range(self.n_slots)]
+            self._used = [False] * self.n_slots
         self.replays, self.outs = [], []
         L = _lib.lib()
         with torch.cuda.device(self.device):
             for g in range(self.n_graphs):
                 c0 = L.hd_debug_launch_count()
-                rp, det, cnt, idx = self.pps[g % self.depth].graph(self.pool[g % len(self.pool)], warmup=2, peer=peer, slot=g % self.depth)
+                rp, det, cnt, idx = self.pps[g % self.depth].graph(self.pool[g % len(self.pool)], warmup=2, peer=peer, slot=g % self.n_slots)
                 # launches of one step = what one capture recorded (2 warm-up calls + 1 captured call were counted)
                 self.launches_per_step = (L.hd_debug_launch_count() - c0) // 3
                 self.replays.append(rp)
@@ -314,9 +321,19 @@ class PostprocessPipeline:
         g = k % self.n_graphs
         s = self.streams[g % self.depth]
         with torch.cuda.stream(s):
-            self.replays[g]()
             if self.peer is not None:
-                self.peer.barrier(channel=g % self.depth)
+                slot = g % self.n_slots
+                if self._used[slot]:
+                    s.wait_event(self._gathered[slot])      # the slot's previous contents have been gathered everywhere
+                self.replays[g]()
+                self._stepped[slot].record(s)
+                with torch.cuda.stream(self.side):           # completion barrier off the compute streams
+                    self.side.wait_event(self._stepped[slot])
+                    self.peer.barrier(channel=slot)
+                    self._gathered[slot].record(self.side)
+                self._used[slot] = True
+            else:
+                self.replays[g]()
         return self.outs[g]
 
     def outputs(self, k):
@@ -330,3 +347,5 @@ class PostprocessPipeline:
         cur = torch.cuda.current_stream(self.device)
         for s in self.streams:
             cur.wait_stream(s)
+        if self.peer is not None:
+            cur.wait_stream(self.side)
