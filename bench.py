@@ -41,7 +41,8 @@ def parse():
                     help="dense: every head byte is read (roofline-honest headline); sparse: objectness-tile skip")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the global batch is sharded over the ranks (the contracted config); weak: --batch images per rank")
-    ap.add_argument("--depth", type=int, default=3, help="software-pipeline depth (CUDA streams); 3 measured best at 32 images per step")
+    ap.add_argument("--depth", type=int, default=0, help="software-pipeline depth (CUDA streams); 0 = auto: 4 for shards of >= 128 images, "
+                    "8 below (measured on B200: a 32-image shard runs 45.9 / 41.0 / 38.8 / 38.5 us per step at depth 3 / 4 / 6 / 8)")
     ap.add_argument("--batch", type=int, default=BATCH, help="global batch (strong) / per-rank batch (weak)")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-sample", type=int, default=32)
@@ -334,7 +335,7 @@ def main():
         pool_cpu = [heads_cpu]
     pool = [[h.to(dev) for h in hs] for hs in pool_cpu]
     dense = args.mode == "dense"
-    depth = max(1, args.depth)
+    depth = args.depth if args.depth > 0 else (4 if Bl >= 128 else 8)
 
     # multi-GPU: the NMS kernels store every kept row into every rank's gather buffer (symmetric memory, posted NVLink stores) --
     # the all-gather is fused into the kernel epilogue; one cross-GPU barrier per step on the step's stream.
@@ -348,8 +349,8 @@ def main():
             peer = None
             gather = hd_dist.DetectionGather(Bl, MAX_DET, dev)
             gather_mode = f"NCCL all_gather of padded detections on a side stream (symmetric memory unavailable: {type(e).__name__})"
-    pipe = yolo.PostprocessPipeline(pool, depth=depth, peer=peer, device=dev, cycle_graph=True, conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET,
-                                    dense_read=dense)
+    pipe = yolo.PostprocessPipeline(pool, depth=depth, peer=peer, device=dev, cycle_graph=True, min_cycle=min(max(args.steps // 2, 24), 192),
+                                    conf_thres=CONF, iou_thres=IOU, max_det=MAX_DET, dense_read=dense)
 
     def run_step(k):
         det, cnt, _ = pipe.step(k)
@@ -379,7 +380,10 @@ def main():
         ref_det, ref_cnt = ref.result(slot)
         torch.cuda.synchronize()
         got_det, got_cnt = peer.gathered(0)
-        ok = torch.tensor([int(torch.equal(got_det, ref_det.reshape(got_det.shape)) and torch.equal(got_cnt, ref_cnt))], device=dev)
+        # rows at and beyond an image's count are unspecified in the peers' copies: compare the counts and the valid rows
+        valid = (torch.arange(MAX_DET, device=dev)[None, :] < ref_cnt[:, None])[..., None]
+        same = torch.equal(got_cnt, ref_cnt) and torch.equal(torch.where(valid, got_det, 0.0), torch.where(valid, ref_det.reshape(got_det.shape), 0.0))
+        ok = torch.tensor([int(same)], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         gather_parity = bool(ok.item())
 

@@ -48,19 +48,18 @@ struct HdSmallSmem {
     int kc;
 };
 
-// zero rows [kc, max_det) of image b in the local outputs and in every replica (8-byte stores: a row is 24 bytes), index -1:
-// the padded outputs are then a function of the inputs alone (callers reuse the buffers across calls); whole CTA calls
+// zero rows [kc, max_det) of image b in the local outputs (8-byte stores: a row is 24 bytes), index -1: the padded outputs are
+// then a function of the inputs alone (callers reuse the buffers across calls).  The REPLICAS only receive the kept rows and the
+// count -- their rows at and beyond the count are unspecified -- so that a step does not push 15x its payload over NVLink.
+// Whole CTA calls.
 __device__ __forceinline__ void hd_zero_tail(float* out_det, long long* out_idx, const HdRep& rep, int max_det, int b, int kc) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lo = kc * 3, hi = max_det * 3;   // float2 units
     if (out_det) {
         float2* o = reinterpret_cast<float2*>(out_det + (size_t)b * max_det * 6);
         for (int i = lo + tid; i < hi; i += nt) o[i] = make_float2(0.f, 0.f);
-        for (int r = 0; r < rep.n; ++r) {
-            float2* pr = reinterpret_cast<float2*>(rep.det[r] + (size_t)b * max_det * 6);
-            for (int i = lo + tid; i < hi; i += nt) pr[i] = make_float2(0.f, 0.f);
-        }
     }
+    (void)rep;
     if (out_idx)
         for (int i = kc + tid; i < max_det; i += nt) out_idx[(size_t)b * max_det + i] = -1;
 }

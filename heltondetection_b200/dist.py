@@ -158,6 +158,9 @@ class PeerDetectionBuffers:
         return self.det[slot, lo:lo + self.B], self.count[slot, lo:lo + self.B]
 
     def replicas(self, slot):
+        import os
+        if os.environ.get("HD_PIPE_NO_REPLICA"):    # developer ablation switch: local outputs only
+            return None
         return self._rep[slot]
 
     def gathered(self, slot):

@@ -4,6 +4,7 @@
 ``YoloPostprocessor`` is the fast path (raw heads -> detections, decode kernel + NMS kernels, no host sync).
 """
 import ctypes as C
+import os
 import torch
 from . import _lib
 
@@ -283,9 +284,9 @@ class PostprocessPipeline:
         pipe.fork(); [pipe.step(k) for k in range(K)]; pipe.join()      # outputs of step k: pipe.outputs(k)
     """
 
-    def __init__(self, pool, depth=2, peer=None, device=None, cycle_graph=False, **pp_kwargs):
+    def __init__(self, pool, depth=2, peer=None, device=None, cycle_graph=False, min_cycle=48, **pp_kwargs):
         import math
-        self.pool, self.depth, self.peer = list(pool), int(depth), peer
+        self.pool, self.depth, self.peer, self.min_cycle = list(pool), int(depth), peer, min_cycle
         first = self.pool[0][0]
         self.device = torch.device(device) if device is not None else first.device
         if peer is not None and (peer.slots < self.depth or peer.slots % self.depth):
@@ -321,7 +322,7 @@ class PostprocessPipeline:
         dev, depth = self.device, self.depth
         # a cycle ends with the pipeline drained, so it should hold many steps: a multiple of the (input, workspace, gather slot)
         # period that is at least ~48 steps long
-        self.cycle_len = self.n_graphs * max(1, -(-48 // self.n_graphs))
+        self.cycle_len = self.n_graphs * max(1, -(-int(self.min_cycle) // self.n_graphs))
         main = torch.cuda.Stream(dev)
         streams = [torch.cuda.Stream(dev) for _ in range(depth)]
         side = torch.cuda.Stream(dev)
@@ -346,7 +347,8 @@ class PostprocessPipeline:
                             stepped.record(s)
                             with torch.cuda.stream(side):
                                 side.wait_event(stepped)
-                                self.peer.barrier(channel=slot)
+                                if not os.environ.get("HD_PIPE_NO_BARRIER"):     # developer ablation switch
+                                    self.peer.barrier(channel=slot)
                                 done = torch.cuda.Event()
                                 done.record(side)
                             gathered[slot] = done
