@@ -74,6 +74,9 @@ SIGNATURES = {
     "hd_rpn_set_cluster_size": (_i, [_i]),
     "hd_rpn_proposals_workspace_size": (_sz, [_i, _i, _i]),
     "hd_rpn_proposals": (_i, [C.POINTER(RpnLevel), _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hd_rpn_merge_levels": (_i, [_vp, _vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hd_rpn_select_nms_strided": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hd_rpn_finish_levels": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "hd_roi_head_decode_filter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(C.c_float), _i, _f, _f, _f, _d, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "hd_roi_head_postprocess_workspace_size": (_sz, [_i, _i, _i]),
     "hd_roi_head_postprocess": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(C.c_float), _i, _f, _f, _f, _d, _f, _d, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) rpn_decode_kernel(const __grid_constant__
 struct RpnSelParams {
     const float4* boxes; const float* scores; const uint32_t* keys;
     int B, N, n_pre, n_post;
+    long long img_stride;   // elements between consecutive images in boxes / scores / keys (N, or more for a level slice of a wider array)
     float thr;
     float* out_rois;   // [B, n_post, 5]
     float* out_scores; // [B, n_post] nullable
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.x;
     if (p.only && p.only[b] == 0) return;
-    const uint32_t* __restrict__ keys = p.keys + (size_t)b * p.N;
+    const uint32_t* __restrict__ keys = p.keys + (size_t)b * p.img_stride;
     const size_t off = (size_t)b * p.cap;
     uint64_t* k0 = p.k0 + off; uint64_t* k1 = p.k1 + off;
     uint32_t* v0 = p.v0 + off; uint32_t* v1 = p.v1 + off;
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
     }
     HD_PHASE(3);
     const uint32_t* order = res ? v1 : v0;
-    const float4* __restrict__ boxes = p.boxes + (size_t)b * p.N;
+    const float4* __restrict__ boxes = p.boxes + (size_t)b * p.img_stride;
     for (int r = tid; r < n; r += RPN_NT) sbox[r] = boxes[order[r]];
     __syncthreads();
     HD_PHASE(4);
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_kernel(const __grid_
             const int r = keep_r[q];
             const float4 bx = sbox[r];
             o[1] = bx.x; o[2] = bx.y; o[3] = bx.z; o[4] = bx.w;
-            if (p.out_scores) p.out_scores[(size_t)b * p.n_post + q] = p.scores[(size_t)b * p.N + order[r]];
+            if (p.out_scores) p.out_scores[(size_t)b * p.n_post + q] = p.scores[(size_t)b * p.img_stride + order[r]];
             if (p.out_idx) p.out_idx[(size_t)b * p.n_post + q] = (long long)order[r];
         } else {
             o[1] = o[2] = o[3] = o[4] = 0.0f;
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_cluster_kernel(const
     const int CL = (int)cluster.num_blocks();
     const int b = blockIdx.x / CL;
     const size_t off = (size_t)b * p.cap;
-    const uint32_t* __restrict__ gkeys = p.keys + (size_t)b * p.N;
+    const uint32_t* __restrict__ gkeys = p.keys + (size_t)b * p.img_stride;
     const int lo = min(crank * q.per, p.N), cntl = min(p.N, lo + q.per) - lo;   // this CTA's slice of the keys
     uint32_t* kcache = reinterpret_cast<uint32_t*>(dsm);
     if (q.key_cache) {
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_cluster_kernel(const
     __syncthreads();
     uint32_t* order = q.order + off;
     float4* sbox = p.sbox + off;
-    const float4* __restrict__ boxes = p.boxes + (size_t)b * p.N;
+    const float4* __restrict__ boxes = p.boxes + (size_t)b * p.img_stride;
     for (int i = tid; i < slen; i += RPN_NT) {
         const unsigned long long v = skey[slo + i];
         int rank = i;                                          // lower bound in the own slice
@@ -606,7 +607,7 @@ __global__ void __launch_bounds__(RPN_NT, 1) rpn_select_nms_cluster_kernel(const
             const int rr = keep_r[r];
             const float4 bx = sbox[rr];
             o[1] = bx.x; o[2] = bx.y; o[3] = bx.z; o[4] = bx.w;
-            if (p.out_scores) p.out_scores[(size_t)b * p.n_post + r] = p.scores[(size_t)b * p.N + order[rr]];
+            if (p.out_scores) p.out_scores[(size_t)b * p.n_post + r] = p.scores[(size_t)b * p.img_stride + order[rr]];
             if (p.out_idx) p.out_idx[(size_t)b * p.n_post + r] = (long long)order[rr];
         } else {
             o[1] = o[2] = o[3] = o[4] = 0.0f;
@@ -722,6 +723,14 @@ extern "C" HD_API size_t hd_rpn_select_nms_workspace_size(int B, int N, int n_pr
 extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores, const uint32_t* keys, int B, int N, int n_pre, int n_post,
                                         double nms_iou, float* out_rois, float* out_scores, int64_t* out_idx, int32_t* out_count,
                                         void* workspace, size_t workspace_bytes, void* stream) {
+    return hd_rpn_select_nms_strided(boxes, scores, keys, B, N, (int64_t)N, n_pre, n_post, nms_iou, out_rois, out_scores, out_idx, out_count,
+                                     workspace, workspace_bytes, stream);
+}
+
+extern "C" HD_API int hd_rpn_select_nms_strided(const float* boxes, const float* scores, const uint32_t* keys, int B, int N, int64_t image_stride,
+                                                int n_pre, int n_post, double nms_iou, float* out_rois, float* out_scores, int64_t* out_idx,
+                                                int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    HD_CHECK_ARG(image_stride >= N, "image_stride %lld < N %d", (long long)image_stride, N);
     HD_CHECK_ARG(B >= 0 && N >= 0 && n_post > 0, "bad shape B=%d N=%d n_post=%d", B, N, n_post);
     HD_CHECK_ARG(N < (1 << 24), "more than 2^24 proposals per image");
     if (B == 0) return HD_OK;
@@ -736,6 +745,7 @@ extern "C" HD_API int hd_rpn_select_nms(const float* boxes, const float* scores,
     RpnSelParams p;
     p.only = nullptr;
     p.boxes = (const float4*)boxes; p.scores = scores; p.keys = keys; p.B = B; p.N = N; p.n_pre = n_pre; p.n_post = n_post;
+    p.img_stride = image_stride;
     p.thr = hd_thr_floor(nms_iou);
     p.out_rois = out_rois; p.out_scores = out_scores; p.out_idx = (long long*)out_idx; p.out_count = out_count; p.cap = cap;
     p.k0 = (uint64_t*)(w0 + offs[0]); p.k1 = (uint64_t*)(w0 + offs[1]); p.v0 = (uint32_t*)(w0 + offs[2]); p.v1 = (uint32_t*)(w0 + offs[3]);

@@ -185,48 +185,69 @@ class RpnProposalsPerLevel:
         boxes, scores, keys = self.dec.decode(objectness, deltas)
         return self.filter_proposals(boxes, scores, keys, [d.shape[1] // 4 * d.shape[2] * d.shape[3] for d in deltas])
 
+    def _buffers(self, B, N, ks, dev):
+        key = (B, N, tuple(ks), dev)
+        if getattr(self, "_bkey", None) != key:
+            L = _lib.lib()
+            K = sum(ks)
+            self._lvl = []
+            for k_l, n_l in zip(ks, self._n_per_level):
+                ws_bytes = L.hd_rpn_select_nms_workspace_size(B, n_l, k_l)
+                self._lvl.append((torch.empty((ws_bytes,), dtype=torch.uint8, device=dev), ws_bytes,
+                                  torch.empty((B, k_l, 5), dtype=torch.float32, device=dev), torch.empty((B, k_l), dtype=torch.int64, device=dev),
+                                  torch.zeros((B,), dtype=torch.int32, device=dev), torch.cuda.Stream(dev)))
+            self._cb = torch.empty((B, K, 4), dtype=torch.float32, device=dev)
+            self._cs = torch.empty((B, K), dtype=torch.float32, device=dev)
+            self._cl = torch.empty((B, K), dtype=torch.int32, device=dev)
+            self._ca = torch.empty((B, K), dtype=torch.int32, device=dev)
+            self._cc = torch.zeros((B,), dtype=torch.int32, device=dev)
+            self._nws_bytes = L.hd_sort_nms_workspace_size(B, K)
+            self._nws = torch.empty((self._nws_bytes,), dtype=torch.uint8, device=dev)
+            self._det = torch.zeros((B, self.post, 6), dtype=torch.float32, device=dev)
+            self._slot = torch.zeros((B, self.post), dtype=torch.int64, device=dev)
+            self._cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+            self._bkey = key
+
     @_lib.on_device
     def filter_proposals(self, boxes, scores, keys, num_anchors_per_level):
-        """stage 2 on the decoded arrays: boxes [B,N,4], scores [B,N] (probabilities), keys [B,N] int32 (sortable logit bits)"""
+        """stage 2 on the decoded arrays: boxes [B,N,4], scores [B,N] (probabilities), keys [B,N] int32 (sortable logit bits).
+        Six launches on the device, no eager tensor glue: the per-level stable top-k of the L levels run side by side on L streams
+        (they read disjoint slices of the same arrays, in place), then hd_rpn_merge_levels, the level-aware NMS and hd_rpn_finish_levels."""
+        import ctypes as C
         L = _lib.lib()
+        boxes, scores, keys = _lib.f32c(boxes), _lib.f32c(scores), keys.contiguous()
         B, N = scores.shape
         dev = scores.device
-        sel_idx, sel_lvl = [], []
-        off = 0
-        for l, n_l in enumerate(num_anchors_per_level):
-            k_l = min(self.pre, n_l)
-            bl, sl, kl = boxes[:, off:off + n_l].contiguous(), scores[:, off:off + n_l].contiguous(), keys[:, off:off + n_l].contiguous()
-            ws_bytes = L.hd_rpn_select_nms_workspace_size(B, n_l, k_l)
-            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-            rois = torch.empty((B, k_l, 5), dtype=torch.float32, device=dev)
-            idx = torch.empty((B, k_l), dtype=torch.int64, device=dev)
-            cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
-            # IoU threshold 2: nothing is ever suppressed -> the call is a stable top-k + sort of the level
-            _lib.check(L.hd_rpn_select_nms(_lib.ptr(bl), _lib.ptr(sl), _lib.ptr(kl), B, n_l, k_l, k_l, 2.0, _lib.ptr(rois), None, _lib.ptr(idx),
-                                           _lib.ptr(cnt), _lib.ptr(ws), ws_bytes, _lib.stream()))
-            sel_idx.append(torch.where(idx >= 0, idx + off, idx))
-            sel_lvl.append(torch.full((B, k_l), l, dtype=torch.int32, device=dev))
+        self._n_per_level = list(num_anchors_per_level)
+        ks = [min(self.pre, n_l) for n_l in num_anchors_per_level]
+        K = sum(ks)
+        self._buffers(B, N, ks, dev)
+        cur = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        offs, off = [], 0
+        for l, (n_l, k_l) in enumerate(zip(num_anchors_per_level, ks)):
+            ws, ws_bytes, rois_l, idx_l, cnt_l, st = self._lvl[l]
+            offs.append(off)
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                # IoU threshold 2: nothing is ever suppressed -> the call is a stable top-k + sort of the level's slice
+                _lib.check(L.hd_rpn_select_nms_strided(
+                    C.c_void_p(boxes.data_ptr() + off * 16), C.c_void_p(scores.data_ptr() + off * 4), C.c_void_p(keys.data_ptr() + off * 4),
+                    B, n_l, N, k_l, k_l, 2.0, _lib.ptr(rois_l), None, _lib.ptr(idx_l), _lib.ptr(cnt_l), _lib.ptr(ws), ws_bytes, _lib.stream()))
+            cur.wait_stream(st)
             off += n_l
-        idx = torch.cat(sel_idx, 1)                       # [B,K] flat anchor index or -1, level-major, score-descending inside a level
-        lvl = torch.cat(sel_lvl, 1)
-        K = idx.shape[1]
-        safe = idx.clamp(min=0)
-        cb = torch.gather(boxes, 1, safe[..., None].expand(B, K, 4))
-        cs = torch.gather(scores, 1, safe)
-        valid = (idx >= 0) & ((cb[..., 2] - cb[..., 0]) >= self.min_size) & ((cb[..., 3] - cb[..., 1]) >= self.min_size) & (cs >= self.score_thresh)
-        order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)          # valid candidates first, relative order kept
-        cb = torch.gather(cb, 1, order[..., None].expand(B, K, 4)).contiguous()
-        cs, lvl, idx = torch.gather(cs, 1, order).contiguous(), torch.gather(lvl, 1, order).contiguous(), torch.gather(idx, 1, order)
-        counts = valid.sum(1).to(torch.int32)
-        ws_bytes = L.hd_sort_nms_workspace_size(B, K)
-        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-        det = torch.zeros((B, self.post, 6), dtype=torch.float32, device=dev)
-        slot = torch.full((B, self.post), -1, dtype=torch.int64, device=dev)
-        cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
-        _lib.check(L.hd_sort_nms_batched(_lib.ptr(cb), _lib.ptr(cs), _lib.ptr(lvl), None, _lib.ptr(counts), 0, B, K, self.nms_thresh, _lib.NMS_CLASS_EXACT,
-                                         0.0, 0, self.post, _lib.ptr(det), _lib.ptr(slot), _lib.ptr(cnt), _lib.ptr(ws), ws_bytes, _lib.stream()))
-        live = torch.arange(self.post, device=dev)[None, :] < cnt[:, None]
-        out_idx = torch.where(live, torch.gather(idx, 1, slot.clamp(min=0)), torch.full_like(slot, -1))
-        rois = torch.cat((torch.arange(B, device=dev, dtype=torch.float32)[:, None, None].expand(B, self.post, 1), det[..., :4]), 2)
-        rois = torch.where(live[..., None], rois, torch.cat((rois[..., :1], torch.zeros_like(rois[..., 1:])), 2))
-        return rois.reshape(B * self.post, 5), cnt, torch.where(live, det[..., 4], torch.zeros_like(det[..., 4])), out_idx
+        nl = len(ks)
+        sel = (C.c_void_p * nl)(*[self._lvl[l][3].data_ptr() for l in range(nl)])
+        karr, oarr = (C.c_int32 * nl)(*ks), (C.c_int32 * nl)(*offs)
+        _lib.check(L.hd_rpn_merge_levels(_lib.ptr(boxes), _lib.ptr(scores), sel, karr, oarr, nl, B, N, self.min_size, self.score_thresh,
+                                         _lib.ptr(self._cb), _lib.ptr(self._cs), _lib.ptr(self._cl), _lib.ptr(self._ca), _lib.ptr(self._cc), _lib.stream()))
+        _lib.check(L.hd_sort_nms_batched(_lib.ptr(self._cb), _lib.ptr(self._cs), _lib.ptr(self._cl), None, _lib.ptr(self._cc), 0, B, K, self.nms_thresh,
+                                         _lib.NMS_CLASS_EXACT, 0.0, 0, self.post, _lib.ptr(self._det), _lib.ptr(self._slot), _lib.ptr(self._cnt),
+                                         _lib.ptr(self._nws), self._nws_bytes, _lib.stream()))
+        rois = torch.empty((B * self.post, 5), dtype=torch.float32, device=dev)
+        osc = torch.empty((B, self.post), dtype=torch.float32, device=dev)
+        oidx = torch.empty((B, self.post), dtype=torch.int64, device=dev)
+        _lib.check(L.hd_rpn_finish_levels(_lib.ptr(self._det), _lib.ptr(self._slot), _lib.ptr(self._cnt), _lib.ptr(self._ca), B, K, self.post,
+                                          _lib.ptr(rois), _lib.ptr(osc), _lib.ptr(oidx), _lib.stream()))
+        return rois, self._cnt, osc, oidx

@@ -307,6 +307,10 @@ HD_API size_t hd_rpn_select_nms_workspace_size(int B, int N, int n_pre);
 HD_API int hd_rpn_select_nms(const float* boxes, const float* scores, const uint32_t* keys, int B, int N, int n_pre, int n_post,
                              double nms_iou, float* out_rois, float* out_scores, int64_t* out_idx, int32_t* out_count,
                              void* workspace, size_t workspace_bytes, void* stream);
+/* the same on a level slice (or any sub-range) of wider per-image arrays: image b's N elements start at b * image_stride */
+HD_API int hd_rpn_select_nms_strided(const float* boxes, const float* scores, const uint32_t* keys, int B, int N, int64_t image_stride,
+                                     int n_pre, int n_post, double nms_iou, float* out_rois, float* out_scores, int64_t* out_idx,
+                                     int32_t* out_count, void* workspace, size_t workspace_bytes, void* stream);
 /* Stage 2 runs as one thread-block CLUSTER (8 SMs) per image when n_pre <= 16384, else as one CTA per image; both
  * give bit-identical outputs.  hd_rpn_set_mode: 0 = automatic (default), 1 = force one CTA per image,
  * 2 = cluster whenever eligible.  Returns the previous mode (process-wide; developer / test aid). */
@@ -321,6 +325,21 @@ HD_API int hd_rpn_proposals(const hd_rpn_level* levels /*host*/, int n_levels, i
                             float min_size, float clamp_dwh, int n_pre, int n_post, double nms_iou, float* out_rois,
                             float* out_scores, int64_t* out_idx, int32_t* out_count, void* workspace, size_t workspace_bytes,
                             void* stream);
+/* Per-level selection (torchvision RegionProposalNetwork.filter_proposals, rpn.py:231-297), composed on the device:
+ * hd_rpn_decode(HD_RPN_KEY_LOGIT | HD_RPN_CLAMP_DWH) -> one hd_rpn_select_nms per level slice with nms_iou = 2 (= stable top-k + sort;
+ * the levels are independent: issue them on different streams) -> hd_rpn_merge_levels -> hd_sort_nms_batched(HD_NMS_CLASS_EXACT, cls =
+ * level) -> hd_rpn_finish_levels.
+ *   hd_rpn_merge_levels: sel[l] (HOST array of L device pointers) = [B, k[l]] int64 indices inside level l's slice (-1 = empty) as
+ *     written by hd_rpn_select_nms(out_idx); level_off[l] = first flat anchor of level l.  Gathers the boxes / probabilities, drops boxes
+ *     with a side < min_size or a probability < score_thresh, and compacts the survivors in (level, score) order:
+ *     cand_box [B,K,4], cand_score [B,K], cand_lvl [B,K], cand_anchor [B,K] (flat anchor index), cand_count [B], K = sum k[l].
+ *   hd_rpn_finish_levels: det / slot / count of the NMS call -> rois [B*n_post,5] = (b,x1,y1,x2,y2), scores [B,n_post] (nullable),
+ *     idx [B,n_post] flat anchor index (nullable); rows beyond the count are zero, index -1. */
+HD_API int hd_rpn_merge_levels(const float* boxes, const float* scores, const int64_t* const* sel /*host*/, const int32_t* k /*host*/,
+                               const int32_t* level_off /*host*/, int n_levels, int B, int N, float min_size, float score_thresh,
+                               float* cand_box, float* cand_score, int32_t* cand_lvl, int32_t* cand_anchor, int32_t* cand_count, void* stream);
+HD_API int hd_rpn_finish_levels(const float* det, const int64_t* slot, const int32_t* count, const int32_t* cand_anchor, int B, int K,
+                                int n_post, float* rois, float* scores, int64_t* idx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * TTA map-back + Weighted Boxes Fusion (README.md:19; ensemble-boxes weighted_boxes_fusion).
