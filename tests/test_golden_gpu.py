@@ -89,3 +89,33 @@ def test_roi_head_against_torchvision_method_fixture():
         det = torch.zeros((1, k, 6), device="cuda"); det[0, :, :4] = torch.from_numpy(G2[f"rh_boxes{i}"]).cuda()
         sc = roi_head.scale_coords((256, 320), det, [(480, 640)])
         assert np.array_equal(sc[0, :, :4].cpu().numpy(), G2[f"rh_scaled{i}"])
+
+
+def test_round2_fixtures_golden_v3():
+    """golden_v3.npz (tests/golden/make_golden_v3.py): exact-math RPN proposals (torch.equal), multi_label candidates, WBF conf types"""
+    from heltondetection_b200 import rpn, yolo, wbf
+    G3 = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v3.npz"))
+    obj = [C(f"rpn_obj{l}") for l in range(4)]
+    dlt = [C(f"rpn_dlt{l}") for l in range(4)]
+    bases = [G[f"rpn_base{l}"] for l in range(4)]
+    pr = rpn.RpnProposals(bases, (4, 8, 16, 32), (128, 128), n_pre_nms=600, n_post_nms=100, min_size=8, exact_math=True)
+    rois, cnt, sc, idx = pr(obj, dlt)
+    n = int(cnt[0])
+    assert np.array_equal(idx[0, :n].cpu().numpy(), G3["rpnx_idx"])
+    assert np.array_equal(rois[:n, 1:].cpu().numpy(), G3["rpnx_roi"]) and np.array_equal(sc[0, :n].cpu().numpy(), G3["rpnx_score"])
+    heads = [C(f"yolo_head{l}") for l in range(3)]
+    for conf in (0.25, 0.01):
+        det, cnt, idx = yolo.YoloPostprocessor(conf_thres=conf, iou_thres=0.45, multi_label=True)(heads)
+        n = int(cnt[0])
+        assert np.array_equal(idx[0, :n].cpu().numpy(), G3[f"ml_idx_{conf}"])
+        assert boxes_close(det[0, :n, :4], torch.from_numpy(G3[f"ml_det_{conf}"][:, :4]))
+    bl = [G[f"wbf_b{v}"] for v in range(3)]
+    sl = [G[f"wbf_s{v}"] for v in range(3)]
+    ll = [G[f"wbf_l{v}"] for v in range(3)]
+    w = G3["wbf_weights"].tolist()
+    for ct in ("box_and_model_avg", "absent_model_aware_avg"):
+        b, s, l = wbf.weighted_boxes_fusion(bl, sl, ll, w, 0.55, 0.1, ct)
+        assert np.array_equal(l, G3[f"wbf_{ct}_labels"]) and np.array_equal(b, G3[f"wbf_{ct}_boxes"]) and np.allclose(s, G3[f"wbf_{ct}_scores"], rtol=1e-12, atol=0)
+    for rule in ("len_weights", "sum_weights"):
+        b, s, l = wbf.weighted_boxes_fusion(bl, sl, ll, w, 0.55, 0.1, "avg", rescale=rule)
+        assert np.array_equal(b, G3[f"wbf_avg_{rule}_boxes"]) and np.array_equal(s, G3[f"wbf_avg_{rule}_scores"])

@@ -247,3 +247,37 @@ def test_plain_c_oracle_match_and_scale_pinned_to_torchvision_and_restatement():
     ref = oracle.roi_head.scale_coords((640, 640), det[:, :4], (1080, 1920))
     got = cref.scale_coords(det.numpy(), np.float32(pad[0]), np.float32(pad[1]), np.float32(gain), 1920.0, 1080.0)
     assert np.array_equal(got[:, :4], ref.numpy())
+
+
+def test_round2_oracle_variants_against_golden_v3():
+    """the oracle's round-2 variants reproduce tests/golden/golden_v3.npz (exact-math RPN, multi_label, WBF conf types / rescale)"""
+    G3 = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v3.npz"))
+    obj = [torch.from_numpy(G[f"rpn_obj{l}"]) for l in range(4)]
+    dlt = [torch.from_numpy(G[f"rpn_dlt{l}"]) for l in range(4)]
+    bases = [G[f"rpn_base{l}"] for l in range(4)]
+    roi, sc, ix = oracle.rpn.rpn_proposals(obj, dlt, bases, (4, 8, 16, 32), (128, 128), exact_math=True, n_pre_nms=600, n_post_nms=100, min_size=8)[0]
+    assert np.array_equal(ix.numpy(), G3["rpnx_idx"]) and np.array_equal(roi.numpy(), G3["rpnx_roi"])
+    # exact_math changes values by at most an ulp of the transcendental: same proposals as the fp32 chain up to near-ties
+    roi32, sc32, ix32 = oracle.rpn.rpn_proposals(obj, dlt, bases, (4, 8, 16, 32), (128, 128), n_pre_nms=600, n_post_nms=100, min_size=8)[0]
+    assert len(set(ix.tolist()) & set(ix32.tolist())) >= 0.97 * len(ix32)
+    heads = [torch.from_numpy(G[f"yolo_head{l}"]) for l in range(3)]
+    pred = oracle.yolo.decode_box(heads)
+    det, idx = oracle.yolo.non_max_suppression(pred, 0.01, 0.45, return_index=True, multi_label=True)
+    assert np.array_equal(idx[0].numpy(), G3["ml_idx_0.01"])
+    nc = pred.shape[2] - 5
+    x, ai = oracle.yolo.filter_candidates_multi_label(pred[0], 0.01)
+    x1, a1 = oracle.yolo.filter_candidates(pred[0], 0.01)
+    assert x.shape[0] >= x1.shape[0] and set((ai // nc).tolist()) == set(a1.tolist())       # same anchors, possibly several classes each
+    bl = [G[f"wbf_b{v}"] for v in range(3)]
+    sl = [G[f"wbf_s{v}"] for v in range(3)]
+    ll = [G[f"wbf_l{v}"] for v in range(3)]
+    w = G3["wbf_weights"].tolist()
+    for ct in ("box_and_model_avg", "absent_model_aware_avg"):
+        b, s, l = oracle.wbf.weighted_boxes_fusion(bl, sl, ll, w, 0.55, 0.1, ct)
+        assert np.array_equal(s, G3[f"wbf_{ct}_scores"]) and np.array_equal(b, G3[f"wbf_{ct}_boxes"])
+    a = oracle.wbf.weighted_boxes_fusion(bl, sl, ll, w, 0.55, 0.1, "avg", False, "len_weights")[1]
+    b = oracle.wbf.weighted_boxes_fusion(bl, sl, ll, w, 0.55, 0.1, "avg", False, "sum_weights")[1]
+    assert not np.array_equal(a, b)          # the two ensemble-boxes rules differ for non-unit weights ...
+    a1 = oracle.wbf.weighted_boxes_fusion(bl, sl, ll, None, 0.55, 0.1, "avg", False, "len_weights")[1]
+    b1 = oracle.wbf.weighted_boxes_fusion(bl, sl, ll, None, 0.55, 0.1, "avg", False, "sum_weights")[1]
+    assert np.array_equal(a1, b1)            # ... and agree for unit weights
