@@ -179,3 +179,113 @@ __device__ void hd_cta_bitonic_reg(unsigned long long* skey, uint32_t* sval) {
 
 // picks the smallest register-blocked network that holds n keys; returns N (keys beyond n must be padded with ~0ull up to N)
 __device__ __forceinline__ int hd_bitonic_padded(int n) { return n <= 2048 ? 2048 : (n <= 4096 ? 4096 : 8192); }
+
+// ------------------------------------------------------------------------------------------------------------
+// Bucket sort of n <= NT*E UNIQUE uint64 keys whose high word is a score bit pattern (piecewise-log in the score, so a
+// dense image's candidates spread over thousands of distinct values).  One counting pass over HD_BUCKET_BINS bins of the high
+// word scaled to the image's [min, max]; shared-memory atomics hand out arbitrary places inside a bin; then every element
+// ranks itself among the members of its bin by enumeration (lanes of a warp sit in the same bin: broadcast reads).
+// O(n + sum bin^2 / NT) instead of the bitonic network's O(n log^2 n): 6.8 k candidates sort in ~10 us instead of 79 us.
+// Element e of thread t is key k[e] with payload t + e*NT (its index), valid if that index < n.  On success sval[r] = index of
+// the rank-r element and the function returns true; skey is scratch.  Returns false (nothing usable written) when one bin
+// would hold more than HD_BUCKET_MAX elements (degenerate score distribution) -- the caller then runs the bitonic network.
+// `bins` = 2*HD_BUCKET_BINS ints of shared scratch, `red` = 64 ints.
+// ------------------------------------------------------------------------------------------------------------
+#define HD_BUCKET_BINS 4096
+#define HD_BUCKET_MAX 512
+template <int NT, int E>
+__device__ bool hd_cta_bucket_sort(const unsigned long long (&k)[E], int n, unsigned long long* skey, uint32_t* sval,
+                                   int* bins, int* red) {
+    static_assert(HD_BUCKET_BINS % NT == 0, "bins per thread");
+    constexpr int BPT = HD_BUCKET_BINS / NT;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int* start = bins;
+    int* cursor = bins + HD_BUCKET_BINS;
+    // 1. range of the high word
+    uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (tid + e * NT < n) { const uint32_t h = (uint32_t)(k[e] >> 32); lo = min(lo, h); hi = max(hi, h); }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(HD_FULL, lo, d));
+        hi = max(hi, __shfl_xor_sync(HD_FULL, hi, d));
+    }
+    if (lane == 0) { red[wid] = (int)lo; red[32 + wid] = (int)hi; }
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) start[tid * BPT + q] = 0;
+    __syncthreads();
+    lo = (uint32_t)red[lane % (NT / 32)];
+    hi = (uint32_t)red[32 + lane % (NT / 32)];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(HD_FULL, lo, d));
+        hi = max(hi, __shfl_xor_sync(HD_FULL, hi, d));
+    }
+    const uint32_t range = hi - lo;
+    const int shift = range < HD_BUCKET_BINS ? 0 : (32 - __clz(range)) - 12;   // (range >> shift) < 4096
+    // 2. histogram
+    int bin[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        bin[e] = -1;
+        if (tid + e * NT < n) { bin[e] = (int)(((uint32_t)(k[e] >> 32) - lo) >> shift); atomicAdd(&start[bin[e]], 1); }
+    }
+    __syncthreads();
+    // 3. exclusive scan (thread t owns bins t*BPT ..), bin-size check
+    int c[BPT], s = 0, cmax = 0;
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) { c[q] = start[tid * BPT + q]; s += c[q]; cmax = max(cmax, c[q]); }
+    int incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(HD_FULL, incl, d);
+        if (lane >= d) incl += y;
+    }
+    const bool too_big = __syncthreads_or(cmax > HD_BUCKET_MAX) != 0;   // (also orders the reads of red[] above before the writes below)
+    if (too_big) return false;
+    if (lane == 31) red[wid] = incl;
+    __syncthreads();
+    int wtot = (lane < NT / 32) ? red[lane] : 0, winc = wtot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(HD_FULL, winc, d);
+        if (lane >= d) winc += y;
+    }
+    int run = __shfl_sync(HD_FULL, winc - wtot, wid) + incl - s;
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) { start[tid * BPT + q] = run; cursor[tid * BPT + q] = run; run += c[q]; }
+    __syncthreads();
+    // 4. place (arbitrary order inside a bin)
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (bin[e] >= 0) {
+            const int pos = atomicAdd(&cursor[bin[e]], 1);
+            skey[pos] = k[e];
+            sval[pos] = (uint32_t)(tid + e * NT);
+        }
+    __syncthreads();
+    // 5. rank inside the bin; cursor[b] is now the end of bin b
+    int dest[E];
+    uint32_t pv[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int q = tid + e * NT;
+        dest[e] = -1;
+        if (q < n) {
+            const unsigned long long kq = skey[q];
+            pv[e] = sval[q];
+            const int b = (int)(((uint32_t)(kq >> 32) - lo) >> shift);
+            const int s0 = start[b], s1 = cursor[b];
+            int r = s0;
+            for (int j = s0; j < s1; ++j) r += (skey[j] < kq) ? 1 : 0;
+            dest[e] = r;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (dest[e] >= 0) sval[dest[e]] = pv[e];
+    __syncthreads();
+    return true;
+}

@@ -36,6 +36,7 @@ struct NmsParams {
     const int* only;            // nullable: run only the images whose flag is set (images the cluster kernel hands back)
     unsigned* hint;             // nullable: mapped host word that receives `call_id` when some image takes this (large) path
     unsigned call_id;
+    int bucket_sort;            // 1: dense images (n > NMS_BUCKET_MIN_N) use the bucket sort instead of the bitonic network
 };
 
 // NT = 1024: one whole SM per image (64 K registers, ~190 KB shared memory) -- the fast configuration for dense scenes.
@@ -43,6 +44,7 @@ struct NmsParams {
 // for a batch that has no large image still needs B empty SMs, i.e. it drains whatever else is running -- fatal for the
 // software-pipelined small-batch steps -- so the host launches the light variant while recent calls saw no large image
 // (see nms_large_recent below); either variant returns the same bits.
+#define NMS_BUCKET_MIN_N 2048
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) sort_nms_kernel(const __grid_constant__ NmsParams p) {
     extern __shared__ uint32_t removed[];  // ceil(cap/32)+4 words, (+pad)
@@ -76,22 +78,40 @@ __global__ void __launch_bounds__(NT, 1) sort_nms_kernel(const __grid_constant__
         unsigned long long* skey = reinterpret_cast<unsigned long long*>(removed + p.sort_off);
         uint32_t* sval = reinterpret_cast<uint32_t*>(skey + p.bitonic_cap);
         const int N = hd_bitonic_padded(n);
-        for (int i = tid; i < N; i += NT) {
-            if (i < n) {
-                const uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + i] : (uint32_t)i;
-                skey[i] = ((uint64_t)(~hd_orderable(p.scores[off + i])) << 32) | tb;
-                sval[i] = (uint32_t)i;
-            } else {
-                skey[i] = ~0ull;
-                sval[i] = 0u;
+        bool sorted = false;
+        if (NT == 1024 && n > NMS_BUCKET_MIN_N && p.bucket_sort) {
+            // dense image: composites straight into registers, bucket sort on the score word (hd_sort.cuh)
+            unsigned long long kreg[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int i = tid + e * NT;
+                kreg[e] = ~0ull;
+                if (i < n) {
+                    const uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + i] : (uint32_t)i;
+                    kreg[e] = ((uint64_t)(~hd_orderable(p.scores[off + i])) << 32) | tb;
+                }
             }
+            HD_PHASE(2);
+            sorted = hd_cta_bucket_sort<NT, 8>(kreg, n, skey, sval, &ssm.warp_cnt[0][0], ssm.hist);
         }
-        __syncthreads();
-        HD_PHASE(2);
-        if (NT == 1024) {   // (bitonic_cap is 0 for the light variant: the register-blocked network needs 1024 threads)
-            if (N == 2048) hd_cta_bitonic_reg<2, true>(skey, sval);
-            else if (N == 4096) hd_cta_bitonic_reg<4, true>(skey, sval);
-            else hd_cta_bitonic_reg<8, true>(skey, sval);
+        if (!sorted) {
+            for (int i = tid; i < N; i += NT) {
+                if (i < n) {
+                    const uint32_t tb = p.tiebreak ? (uint32_t)p.tiebreak[off + i] : (uint32_t)i;
+                    skey[i] = ((uint64_t)(~hd_orderable(p.scores[off + i])) << 32) | tb;
+                    sval[i] = (uint32_t)i;
+                } else {
+                    skey[i] = ~0ull;
+                    sval[i] = 0u;
+                }
+            }
+            __syncthreads();
+            HD_PHASE(2);
+            if (NT == 1024) {   // (bitonic_cap is 0 for the light variant: the register-blocked network needs 1024 threads)
+                if (N == 2048) hd_cta_bitonic_reg<2, true>(skey, sval);
+                else if (N == 4096) hd_cta_bitonic_reg<4, true>(skey, sval);
+                else hd_cta_bitonic_reg<8, true>(skey, sval);
+            }
         }
         order = sval;
     } else {
@@ -339,7 +359,7 @@ static bool nms_hint_slot(const void* workspace, cudaStream_t st, unsigned** dev
     const unsigned slot = (unsigned)((((uintptr_t)workspace) >> 8) * 2654435761u) % NMS_HINT_SLOTS;
     const unsigned last_big = *reinterpret_cast<volatile unsigned*>(g_hint_host[d] + slot);
     const unsigned prev = g_hint_calls[d][slot];
-    *large_recent = (prev - last_big) < 8u;          // one of the last 8 calls through this workspace reported a large image
+    *large_recent = (prev - last_big) < 64u;         // one of the last 64 calls through this workspace reported a large image
     *call_id = ++g_hint_calls[d][slot];
     *dev_word = g_hint_dev[d] + slot;
     return true;
@@ -478,6 +498,7 @@ int hd_sort_nms_batched_min(const float* boxes, const float* scores, const int32
     }
     if (mode == 3) heavy = false;
     else if (mode != 0) heavy = true;
+    p.bucket_sort = (mode != 5);   // mode 5: heavy kernel with the bitonic network for every size (A/B of the bucket sort)
     if (min_n < 0 && (counts != nullptr || n_fixed <= HD_SMALL_N)) {
         // images with <= HD_SMALL_N candidates: shared-memory kernel; the radix-sort kernel below then only
         // works on the larger ones (it returns at once for the rest)

@@ -52,6 +52,7 @@ struct YoloParams {
     int n_levels, B, A, nc, no;
     float thr;   // (float) conf_thres: torch compares the fp32 tensor with the scalar cast to fp32
     float gate;  // conservative logit-domain pre-test for sigmoid(obj) > thr
+    float gate2; // ... and for sigmoid(obj)*sigmoid(cls) > thr: min(obj,0) + min(cls,0) > ln(thr) - margin
     int ge, dense, cap;
     int multi;   // HD_FLAG_MULTI_LABEL: every (anchor, class) pair with obj*cls > thr is a candidate (ultralytics multi_label)
     int items_per_image;
@@ -72,7 +73,7 @@ struct YoloParams {
 //   - survivors are compacted with one atomicAdd per warp.
 // ------------------------------------------------------------------------------------------------
 template <bool VEC, typename T>
-__device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long long item, const int lane,
+__device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long long item, const int lane, float* stage,
                                                  float4* __restrict__ cand_box, float* __restrict__ cand_score,
                                                  int* __restrict__ cand_cls, int* __restrict__ cand_anchor,
                                                  int* __restrict__ cand_count) {
@@ -110,7 +111,28 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
 
 #pragma unroll
     for (int k = 0; k < 4; ++k) o[k] = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bx[c][k] = 0.0f;
+    }
+    // U independent class-plane loads in flight per lane (same bytes in flight for 32-bit and 16-bit heads)
+    constexpr int U = (sizeof(T) == 4) ? 8 : 16;
+    constexpr int HEAD = 3;
+    // dense read: nothing depends on the objectness test, so the objectness plane, the four box planes and the first nc % U class
+    // planes (when there are at most HEAD of them) leave as ONE batch of independent loads -- a 15-plane head (nc = 10) costs two
+    // memory round trips per tile instead of five
+    const int t_head = VEC ? p.nc % U : 0;
+    const bool merged = VEC && p.dense && t_head <= HEAD;
+    HdRaw4<T> head_raw[HEAD];
     load4(4, o);
+    if (merged) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) load4(c, bx[c]);
+#pragma unroll
+        for (int u = 0; u < HEAD; ++u)
+            if (valid[0] && u < t_head) head_raw[u] = hd_load_raw4<T>(base + (size_t)(5 + u) * HW);
+    }
     bool gate_any = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k) gate_any |= valid[k] && (o[k] > p.gate);
@@ -119,11 +141,9 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
     // surviving tile shrinks from 85 x 512 B to 85 x (one 32-byte sector per surviving lane)
     need = p.dense || gate_any;
 
+    if (!merged) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) bx[c][k] = 0.0f;
-        load4(c, bx[c]);
+        for (int c = 0; c < 4; ++c) load4(c, bx[c]);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { m[k] = -INFINITY; L[k] = -INFINITY; j[k] = 0; }
@@ -139,9 +159,17 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
     };
     int c = 0;
     if (VEC) {
-        // U independent plane loads in flight per lane (same bytes in flight for 32-bit and 16-bit heads)
-        constexpr int U = (sizeof(T) == 4) ? 8 : 16;
         const bool ld = valid[0] && need;
+        if (merged) {
+#pragma unroll
+            for (int u = 0; u < HEAD; ++u)
+                if (u < t_head) {
+                    float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    if (ld) hd_unpack4<T>(head_raw[u], v);
+                    upd(v, u);
+                }
+            c = t_head;
+        }
         for (; c + U <= p.nc; c += U) {
             HdRaw4<T> raw[U];
 #pragma unroll
@@ -154,88 +182,113 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
                 upd(v, c + u);
             }
         }
-    } else {
-        constexpr int U = 8;
-        for (; c + U <= p.nc; c += U) {
-            float v[U][4];
+        if (c < p.nc) {   // the last nc % U planes, again as one batch
+            HdRaw4<T> raw[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
+            for (int u = 0; u < U - 1; ++u)
+                if (ld && c + u < p.nc) raw[u] = hd_load_raw4<T>(base + (size_t)(5 + c + u) * HW);
+#pragma unroll
+            for (int u = 0; u < U - 1; ++u)
+                if (c + u < p.nc) {
+                    float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    if (ld) hd_unpack4<T>(raw[u], v);
+                    upd(v, c + u);
+                }
+            c = p.nc;
+        }
+    } else {
+        for (; c + 8 <= p.nc; c += 8) {
+            float v[8][4];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) v[u][k] = -INFINITY;
                 load4(5 + c + u, v[u]);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) upd(v[u], c + u);
+            for (int u = 0; u < 8; ++u) upd(v[u], c + u);
         }
-    }
-    for (; c < p.nc; ++c) {
-        float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        load4(5 + c, v);
-        upd(v, c);
+        for (; c < p.nc; ++c) {
+            float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            load4(5 + c, v);
+            upd(v, c);
+        }
     }
 
-    // survivors
-    float conf[4];
-    int npass = 0;
-    bool pass[4];
+    // ---- survivors.  A dense scene at an evaluation threshold (conf 0.001) has ~9 candidates among the 128 cells of a tile: walking
+    // the four cells of every lane would run the sigmoids with 7 % of the lanes active.  Instead a necessary condition in the logit
+    // domain picks the cells that may pass -- sigmoid(x) < min(1, e^x), hence sigmoid(o)*sigmoid(m) > thr needs
+    // min(o,0) + min(m,0) > ln(thr) -- and those cells are dealt out one per lane through a warp-private staging area, so the exact
+    // fp32 test, the box decode and the (now coalesced) stores run with the lanes packed.
+    unsigned pm[4];
+    int before = 0, mine[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        pass[k] = false;
-        if (valid[k] && o[k] > p.gate) {
-            float po = hd_sigmoid(o[k]);
-            float cf = __fmul_rn(hd_sigmoid(m[k]), po);
-            bool ok = p.ge ? (po >= p.thr && cf >= p.thr) : (po > p.thr && cf > p.thr);
-            if (ok) {
-                if (L[k] > -INFINITY && __fmul_rn(hd_sigmoid(L[k]), po) == cf) {
-                    // an earlier class ties after rounding: torch.max returns the first maximal product
-                    const T* q = base + k;
-                    for (int cc = 0; cc < j[k]; ++cc) {
-                        float lg = hd_load1<T>(q + (size_t)(5 + cc) * HW);
-                        if (__fmul_rn(hd_sigmoid(lg), po) == cf) { j[k] = cc; break; }
-                    }
-                }
-                pass[k] = true;
-                conf[k] = cf;
-                ++npass;
-            }
-        }
+        const bool pre = valid[k] && o[k] > p.gate && __fadd_rn(fminf(o[k], 0.0f), fminf(m[k], 0.0f)) > p.gate2;
+        pm[k] = __ballot_sync(HD_FULL, pre);
+        mine[k] = pre ? before + __popc(pm[k] & hd_lanemask_lt()) : -1;
+        before += __popc(pm[k]);
     }
-    // warp-aggregated slot claim
-    int incl = npass;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int y = __shfl_up_sync(HD_FULL, incl, d);
-        if (lane >= d) incl += y;
-    }
-    int total = __shfl_sync(HD_FULL, incl, 31);
-    if (total == 0) return;
-    int slot0 = 0;
-    if (lane == 31) slot0 = atomicAdd(cand_count + b, total);
-    slot0 = __shfl_sync(HD_FULL, slot0, 31);
-    int slot = slot0 + incl - npass;
+    const int n_pre = before;
+    if (n_pre == 0) return;
     const float s = p.stride[l];
     const float aw = p.anchor[l][2 * a], ah = p.anchor[l][2 * a + 1];
     const int W = p.W[l];
+    for (int r0 = 0; r0 < n_pre; r0 += 32) {
+        __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (!pass[k]) continue;
-        if (slot < p.cap) {
-            const int cell = cell0 + k;
+        for (int k = 0; k < 4; ++k) {
+            const int q = mine[k] - r0;
+            if (q >= 0 && q < 32) {
+                stage[0 * 32 + q] = o[k]; stage[1 * 32 + q] = m[k]; stage[2 * 32 + q] = L[k];
+                stage[3 * 32 + q] = __int_as_float(j[k] | ((lane * 4 + k) << 16));
+                stage[4 * 32 + q] = bx[0][k]; stage[5 * 32 + q] = bx[1][k]; stage[6 * 32 + q] = bx[2][k]; stage[7 * 32 + q] = bx[3][k];
+            }
+        }
+        __syncwarp();
+        bool ok = false;
+        float cf = 0.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+        int jj = 0, cell_in = 0;
+        if (r0 + lane < n_pre) {
+            const float oo = stage[0 * 32 + lane], mm = stage[1 * 32 + lane], LL = stage[2 * 32 + lane];
+            const int pk = __float_as_int(stage[3 * 32 + lane]);
+            jj = pk & 0xffff; cell_in = pk >> 16;
+            b0 = stage[4 * 32 + lane]; b1 = stage[5 * 32 + lane]; b2 = stage[6 * 32 + lane]; b3 = stage[7 * 32 + lane];
+            const float po = hd_sigmoid(oo);
+            cf = __fmul_rn(hd_sigmoid(mm), po);
+            ok = p.ge ? (po >= p.thr && cf >= p.thr) : (po > p.thr && cf > p.thr);
+            if (ok && LL > -INFINITY && __fmul_rn(hd_sigmoid(LL), po) == cf) {
+                // an earlier class ties after rounding: torch.max returns the first maximal product
+                const T* q = base - lane * 4 + cell_in;
+                for (int cc = 0; cc < jj; ++cc) {
+                    float lg = hd_load1<T>(q + (size_t)(5 + cc) * HW);
+                    if (__fmul_rn(hd_sigmoid(lg), po) == cf) { jj = cc; break; }
+                }
+            }
+        }
+        // warp-aggregated slot claim
+        const unsigned okm = __ballot_sync(HD_FULL, ok);
+        if (okm == 0u) continue;
+        int slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(cand_count + b, __popc(okm));
+        slot0 = __shfl_sync(HD_FULL, slot0, 0);
+        const int slot = slot0 + __popc(okm & hd_lanemask_lt());
+        if (ok && slot < p.cap) {
+            const int cell = t * 128 + cell_in;
             const int gi = cell / W, gj = cell - gi * W;
             // (p*2 - 0.5 + grid) * s ; (p*2)^2 * anchor : fp32, op order of the reference decode
-            float px = __fmul_rn(hd_sigmoid(bx[0][k]), 2.0f), py = __fmul_rn(hd_sigmoid(bx[1][k]), 2.0f);
-            float pw = __fmul_rn(hd_sigmoid(bx[2][k]), 2.0f), ph = __fmul_rn(hd_sigmoid(bx[3][k]), 2.0f);
+            float px = __fmul_rn(hd_sigmoid(b0), 2.0f), py = __fmul_rn(hd_sigmoid(b1), 2.0f);
+            float pw = __fmul_rn(hd_sigmoid(b2), 2.0f), ph = __fmul_rn(hd_sigmoid(b3), 2.0f);
             float cx = __fmul_rn(__fadd_rn(__fsub_rn(px, 0.5f), (float)gj), s);
             float cy = __fmul_rn(__fadd_rn(__fsub_rn(py, 0.5f), (float)gi), s);
             float w = __fmul_rn(__fmul_rn(pw, pw), aw), h = __fmul_rn(__fmul_rn(ph, ph), ah);
             float hw2 = __fmul_rn(w, 0.5f), hh2 = __fmul_rn(h, 0.5f);  // w/2 exact
             size_t g = (size_t)b * p.cap + slot;
             cand_box[g] = make_float4(__fsub_rn(cx, hw2), __fsub_rn(cy, hh2), __fadd_rn(cx, hw2), __fadd_rn(cy, hh2));
-            cand_score[g] = conf[k];
-            cand_cls[g] = j[k];
+            cand_score[g] = cf;
+            cand_cls[g] = jj;
             cand_anchor[g] = p.level_off[l] + a * HW + cell;
         }
-        ++slot;
     }
 }
 
@@ -369,8 +422,9 @@ __global__ void __launch_bounds__(256, 4) yolo_decode_filter_kernel(const __grid
                                                                  int* __restrict__ cand_anchor,
                                                                  int* __restrict__ cand_count) {
     const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ float stage[8][8 * 32];   // per warp: 32 dealt-out cells x (obj, max logit, runner-up, class|cell, 4 box logits)
     if (item >= p.total_items) return;
-    yolo_decode_item<VEC, T>(p, item, threadIdx.x & 31, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
+    yolo_decode_item<VEC, T>(p, item, threadIdx.x & 31, stage[threadIdx.x >> 5], cand_box, cand_score, cand_cls, cand_anchor, cand_count);
 }
 
 template <bool VEC, typename T = float>
@@ -730,7 +784,7 @@ static int fill_params(YoloParams& p, const hd_yolo_level* levels, int n_levels,
     HD_CHECK_ARG(levels != nullptr, "levels is NULL");
     HD_CHECK_ARG(n_levels >= 1 && n_levels <= HD_MAX_LEVELS, "n_levels must be in [1,%d], got %d", HD_MAX_LEVELS, n_levels);
     HD_CHECK_ARG(A >= 1 && A <= HD_MAX_ANCHORS, "A must be in [1,%d], got %d", HD_MAX_ANCHORS, A);
-    HD_CHECK_ARG(B >= 0 && nc >= 1, "B must be >= 0 and nc >= 1, got B=%d nc=%d", B, nc);
+    HD_CHECK_ARG(B >= 0 && nc >= 1 && nc < 65536, "B must be >= 0 and nc in [1, 65535], got B=%d nc=%d", B, nc);
     memset(&p, 0, sizeof(p));
     p.n_levels = n_levels; p.B = B; p.A = A; p.nc = nc; p.no = 5 + nc;
     int tiles = 0, off = 0;
@@ -769,6 +823,7 @@ extern "C" HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels, int n_l
     HD_CHECK_ARG(cap > 0 && cand_box && cand_score && cand_cls && cand_anchor && cand_count, "null output or cap <= 0");
     p.thr = (float)conf_thres;
     p.gate = conf_gate(conf_thres);
+    p.gate2 = (conf_thres > 0.0) ? (float)(log(conf_thres < 1.0 ? conf_thres : 1.0) - 1e-3) : -INFINITY;
     p.ge = (flags & HD_FLAG_CONF_GE) ? 1 : 0;
     p.dense = (flags & HD_FLAG_DENSE_READ) ? 1 : 0;
     p.multi = (flags & HD_FLAG_MULTI_LABEL) ? 1 : 0;
