@@ -366,7 +366,8 @@ static bool nms_hint_slot(const void* workspace, cudaStream_t st, unsigned** dev
 }
 
 // developer/test knob (process-wide, atomic): 0 auto, 1 one CTA per image only, 2 cluster kernel whenever the batch allows,
-// 3 light (256-thread) large-image kernel always, 4 heavy (1024-thread, no clusters unless the batch allows) always
+// 3 light (256-thread) large-image kernel always, 4 heavy (1024-thread, no clusters unless the batch allows) always,
+// 5 one CTA per image with the bitonic network for every size (A/B of the bucket sort)
 static int g_nms_mode = 0;
 extern "C" HD_API int hd_nms_set_mode(int mode) { return __atomic_exchange_n(&g_nms_mode, mode, __ATOMIC_ACQ_REL); }
 static int nms_cluster_capacity(int CL) {
@@ -386,7 +387,8 @@ static int nms_cluster_capacity(int CL) {
 // CTAs per image for a batch of B images: the largest cluster (8 or 4) that still runs the whole batch in one wave; 0 = the
 // batch is large enough for one CTA per image (or the mode forbids clusters)
 static int nms_cluster_size(int B, bool for_layout = false) {
-    if ((__atomic_load_n(&g_nms_mode, __ATOMIC_ACQUIRE) == 1 && !for_layout) || B <= 0) return 0;
+    const int mode = __atomic_load_n(&g_nms_mode, __ATOMIC_ACQUIRE);
+    if (((mode == 1 || mode == 5) && !for_layout) || B <= 0) return 0;
     for (int c = RPNC_MAXCL; c >= 4; c >>= 1)     // clusters of 2 measured no faster than one CTA per image (cfg4, B=64)
         if (B <= nms_cluster_capacity(c)) return c;
     return 0;

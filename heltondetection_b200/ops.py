@@ -9,7 +9,9 @@ from . import _lib
 
 
 def set_nms_mode(mode):
-    """large-segment NMS kernel choice: 0 auto (thread-block clusters for small batches), 1 one CTA per image; returns the previous mode."""
+    """large-segment NMS kernel choice: 0 auto (thread-block clusters for small batches), 1 one CTA per image, 2 clusters whenever
+    possible, 3 always the light 256-thread kernel, 4 always the 1024-thread kernel, 5 as 1 with the bitonic network instead of the
+    bucket sort; returns the previous mode."""
     return _lib.lib().hd_nms_set_mode(int(mode))
 
 

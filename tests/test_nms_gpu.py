@@ -176,3 +176,34 @@ def test_cluster_and_single_cta_large_segment_kernels_bit_exact(class_mode):
         k = int(outs[0][2][b])
         assert k == min(ref.numel(), 300)
         assert torch.equal(outs[0][1][b, :k], ref[:300])
+
+
+@pytest.mark.parametrize("dist", ["uniform", "all_equal", "three_values", "one_ulp_apart", "log_uniform", "half_equal"])
+@pytest.mark.parametrize("n", [2049, 6800, 8192])
+def test_bucket_sort_score_distributions(dist, n):
+    """single-CTA large-image kernel (mode 1): the bucket sort on the score word (n > 2048) must give the order of the bitonic network
+    (mode 5) and of torchvision for friendly and degenerate score distributions -- equal scores fall back on the anchor tiebreak, a bin
+    with more than 512 members sends the image to the bitonic network."""
+    from heltondetection_b200 import ops
+    b, s = _boxes(n, 900 + n, cluster=False)
+    g = torch.Generator().manual_seed(n)
+    if dist == "all_equal":
+        s = torch.full((n,), 0.5)
+    elif dist == "three_values":
+        s = torch.tensor([0.2, 0.5, 0.9])[torch.randint(0, 3, (n,), generator=g)]
+    elif dist == "one_ulp_apart":
+        s = (torch.full((n,), 0.75).view(torch.int32) + torch.randint(0, 64, (n,), generator=g).int()).view(torch.float32)
+    elif dist == "log_uniform":
+        s = torch.exp(-7.0 * torch.rand((n,), generator=g))
+    elif dist == "half_equal":
+        s = torch.where(torch.rand((n,), generator=g) < 0.5, torch.full((n,), 0.001), s)
+    ref_stable = torchvision.ops.nms(b, s, 0.5)   # (its CPU sort keeps equal scores in index order, as the lineage does)
+    outs = {}
+    for mode in (1, 5):
+        old = ops.set_nms_mode(mode)
+        try:
+            outs[mode] = _run(b, s, 0.5)
+        finally:
+            ops.set_nms_mode(old)
+    assert torch.equal(outs[1], outs[5])
+    assert torch.equal(outs[1], ref_stable)
