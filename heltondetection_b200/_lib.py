@@ -54,6 +54,7 @@ SIGNATURES = {
     "hd_debug_phases": (_i, [_i, C.POINTER(C.c_longlong)]),
     "hd_debug_launch_count": (C.c_ulonglong, []),
     "hd_debug_roi_profile": (_i, [_i, C.POINTER(C.c_ulonglong)]),
+    "hd_debug_roi_align_sliced": (_i, [C.POINTER(RoiLevel), _i, _i, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "hd_yolo_decode": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _vp, _vp]),
     "hd_yolo_decode_filter": (_i, [C.POINTER(YoloLevel), _i, _i, _i, _i, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "hd_yolo_postprocess_workspace_size": (_sz, [_i, _i]),

@@ -162,7 +162,34 @@ __device__ __forceinline__ float4 roi_row_quad(const float4* __restrict__ row, c
     return r;
 }
 
-template <int E>
+// R table rows (fixed y cells) of a bin with their NX x entries each: R*NX independent loads in flight, then the same fma order
+// as the row-at-a-time form (r = sum_b wx[b] v[b]; acc = fma(wy, r, acc), rows ascending)
+template <int R, int NX>
+__device__ __forceinline__ void roi_rows_quad(const float* __restrict__ f, int q, const AxisEntry* yt, const int* xo, const float* wx, float4& acc) {
+    float4 v[R][NX];
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+        const float4* __restrict__ row = reinterpret_cast<const float4*>(f + yt[a].off) + q;
+#pragma unroll
+        for (int b = 0; b < NX; ++b) v[a][b] = __ldg(row + xo[b]);
+    }
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < NX; ++b) { r.x = fmaf(wx[b], v[a][b].x, r.x); r.y = fmaf(wx[b], v[a][b].y, r.y); r.z = fmaf(wx[b], v[a][b].z, r.z); r.w = fmaf(wx[b], v[a][b].w, r.w); }
+        const float wy = yt[a].w;
+        acc.x = fmaf(wy, r.x, acc.x); acc.y = fmaf(wy, r.y, acc.y); acc.z = fmaf(wy, r.z, acc.z); acc.w = fmaf(wy, r.w, acc.w);
+    }
+}
+template <int NX, int MLP>
+__device__ __forceinline__ void roi_bin_rows(const float* __restrict__ f, int q, const AxisEntry* yt, int ny, const int* xo, const float* wx, float4& acc) {
+    int a = 0;
+    for (; a + 2 <= ny; a += 2) roi_rows_quad<2, NX>(f, q, yt + a, xo, wx, acc);
+    if (a < ny) roi_rows_quad<1, NX>(f, q, yt + a, xo, wx, acc);
+}
+
+template <int E, int MLP = 1>
 __device__ __forceinline__ void roi_align_bins_quad(const float* __restrict__ f, int q, int g, int groups, const AxisEntry* ytab,
                                                     const AxisEntry* xtab, const int* ycnt, const int* xcnt, int PH, int PW, float count,
                                                     float* tile, int rot) {
@@ -178,7 +205,13 @@ __device__ __forceinline__ void roi_align_bins_quad(const float* __restrict__ f,
         for (int b = 0; b < E; ++b) { xo[b] = xtab[pw * E + b].off >> 2; wx[b] = xtab[pw * E + b].w; }
         const int ny = ycnt[ph], nx = xcnt[pw];   // real (merged) entries; the rest of the table is zero-weight padding
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (E == 4) {
+        if (E == 4 && MLP > 1) {
+            const AxisEntry* yt = ytab + ph * E;
+            if (nx == 2) roi_bin_rows<2, MLP>(f, q, yt, ny, xo, wx, acc);
+            else if (nx == 3) roi_bin_rows<3, MLP>(f, q, yt, ny, xo, wx, acc);
+            else if (nx == 4) roi_bin_rows<4, MLP>(f, q, yt, ny, xo, wx, acc);
+            else if (nx == 1) roi_bin_rows<1, MLP>(f, q, yt, ny, xo, wx, acc);
+        } else if (E == 4) {
             for (int a = 0; a < ny; ++a) {
                 const float wy = ytab[ph * E + a].w;
                 const float4* __restrict__ row = reinterpret_cast<const float4*>(f + ytab[ph * E + a].off) + q;
@@ -212,8 +245,8 @@ __device__ __forceinline__ void roi_align_bins_quad(const float* __restrict__ f,
 
 // EFIX = table width fixed by the host from sampling_ratio (4: sr<=2, 8: sr<=4, 16: sr<=8; small tables, the sr<=2 variant
 // runs 4 CTAs/SM); EFIX = 0: adaptive sampling, width chosen per RoI (3 CTAs/SM, more registers)
-template <int EFIX>
-__global__ void __launch_bounds__(256, EFIX == 4 ? 4 : 3) roi_align_nhwc_quad_kernel(const __grid_constant__ RoiParams p, int use_tma, int QT, int tab) {
+template <int EFIX, int MLP = 1>
+__global__ void __launch_bounds__(256, (EFIX == 4 && MLP == 1) ? 4 : 3) roi_align_nhwc_quad_kernel(const __grid_constant__ RoiParams p, int use_tma, int QT, int tab) {
     extern __shared__ __align__(128) float smem_f[];
     float* tile = smem_f;                                  // [C][PH*PW]
     AxisEntry* ytab = (AxisEntry*)(tile + (size_t)p.C * p.PH * p.PW);
@@ -248,7 +281,7 @@ __global__ void __launch_bounds__(256, EFIX == 4 ? 4 : 3) roi_align_nhwc_quad_ke
         __syncthreads();
         const int nq = p.C >> 2, groups = 256 / QT, g = threadIdx.x / QT, rot = (threadIdx.x & 31) >> 3;
         for (int q = threadIdx.x % QT; q < nq; q += QT) {
-            if (EFIX) roi_align_bins_quad<(EFIX ? EFIX : 4)>(f, q, g, groups, ytab, xtab, ycnt, xcnt, p.PH, p.PW, count, tile, rot);
+            if (EFIX) roi_align_bins_quad<(EFIX ? EFIX : 4), MLP>(f, q, g, groups, ytab, xtab, ycnt, xcnt, p.PH, p.PW, count, tile, rot);
             else if (E == 4) roi_align_bins_quad<4>(f, q, g, groups, ytab, xtab, ycnt, xcnt, p.PH, p.PW, count, tile, rot);
             else if (E == 8) roi_align_bins_quad<8>(f, q, g, groups, ytab, xtab, ycnt, xcnt, p.PH, p.PW, count, tile, rot);
             else roi_align_bins_quad<16>(f, q, g, groups, ytab, xtab, ycnt, xcnt, p.PH, p.PW, count, tile, rot);
@@ -328,6 +361,48 @@ __global__ void __launch_bounds__(256, EFIX == 4 ? 4 : 3) roi_align_nhwc_quad_ke
     }
     tile_store(p.out + (size_t)k * p.C * nb, tile, p.C * nb, use_tma != 0);
     __syncthreads();   // the tile and the tables are rewritten by the next RoI of the walk
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ RoIAlign NHWC, channel slices
+// Locality variant of the channel-quad kernel for sampling_ratio <= 2: gridDim.y channel slices per RoI (a 64-channel slice keeps a
+// 12.5 KB tile, so four resident CTAs leave most of the SM's 256 KB to L1) and every CTA walks a CONTIGUOUS chunk of a RoI list
+// that the caller sorted by position -- consecutive RoIs of an image overlap (2 000 proposals cover the stride-4 map ~7x), so the
+// cells of RoI i+1 are mostly L1 hits instead of L2 round trips.  Same tables and arithmetic as the kernel above.
+__global__ void __launch_bounds__(256, 4) roi_align_sliced_kernel(const __grid_constant__ RoiParams p, int QT, int tab, int chunk) {
+    extern __shared__ __align__(128) float smem_f[];
+    const int slices = gridDim.y, sl = blockIdx.y;
+    const int Cs = p.C / slices, nb = p.PH * p.PW;
+    float* tile = smem_f;                                  // [Cs][PH*PW]
+    AxisEntry* ytab = (AxisEntry*)(tile + (size_t)Cs * nb);
+    AxisEntry* xtab = ytab + tab;
+    __shared__ int ycnt[64], xcnt[64];
+    const long long nk = p.list ? (long long)*p.list_count : p.K;
+    const long long k0 = (long long)blockIdx.x * chunk, k1 = (k0 + chunk < nk) ? k0 + chunk : nk;
+    for (long long kk = k0; kk < k1; ++kk) {
+        const long long k = p.list ? (long long)p.list[kk] : kk;
+        const float* roi = p.rois + k * 5;
+        const int lvl = p.level_ids ? p.level_ids[k] : 0;
+        const int H = p.H[lvl], W = p.W[lvl];
+        const float sc = p.scale[lvl];
+        const int bidx = (int)roi[0];
+        const float off = p.aligned ? 0.5f : 0.0f;
+        const float sw = __fsub_rn(__fmul_rn(roi[1], sc), off), sh = __fsub_rn(__fmul_rn(roi[2], sc), off);
+        const float ew = __fsub_rn(__fmul_rn(roi[3], sc), off), eh = __fsub_rn(__fmul_rn(roi[4], sc), off);
+        float rw = __fsub_rn(ew, sw), rh = __fsub_rn(eh, sh);
+        if (!p.aligned) { rw = fmaxf(rw, 1.0f); rh = fmaxf(rh, 1.0f); }
+        const float bh = __fdiv_rn(rh, (float)p.PH), bw = __fdiv_rn(rw, (float)p.PW);
+        const int gh = p.sampling_ratio, gw = p.sampling_ratio;
+        const float count = (float)max(gh * gw, 1);
+        const float* __restrict__ f = p.data[lvl] + (size_t)bidx * H * W * p.C;
+        if (threadIdx.x < p.PH) build_axis(ytab, ycnt, threadIdx.x, 4, sh, bh, gh, H, W * p.C, 4);
+        else if (threadIdx.x >= 64 && threadIdx.x < 64 + p.PW) build_axis(xtab, xcnt, threadIdx.x - 64, 4, sw, bw, gw, W, p.C, 4);
+        __syncthreads();
+        const int nqs = Cs >> 2, q0 = sl * nqs, groups = 256 / QT, g = threadIdx.x / QT, rot = (threadIdx.x & 31) >> 3;
+        for (int q = q0 + threadIdx.x % QT; q < q0 + nqs; q += QT)
+            roi_align_bins_quad<4>(f, q, g, groups, ytab, xtab, ycnt, xcnt, p.PH, p.PW, count, tile - (size_t)(4 * q0) * nb, rot);
+        tile_store(p.out + ((size_t)k * p.C + (size_t)sl * Cs) * nb, tile, Cs * nb, true);
+        __syncthreads();   // the tile and the tables are rewritten by the next RoI of the walk
     }
 }
 
@@ -858,8 +933,8 @@ static int fill_roi(RoiParams& p, const hd_roi_level* levels, int n_levels, int 
 }
 
 // 0 auto (= gather kernels: the staged-row kernel measured 2.5x slower on B200, see profiles/r1_results.md), 1 gather kernels
-// only, 2 staged-row kernel whenever eligible; bits 4.. are debug switches of the staged-row kernel (1: no tile store,
-// 2: no compute, 8: nothing staged)
+// only, 2 staged-row kernel whenever eligible; bits 4..7 are debug switches of the staged-row kernel (1: no tile store,
+// 2: no compute, 8: nothing staged); bit 8: gather kernel with one table row in flight per thread (round-1 form, A/B)
 static int g_roi_mode_ = 0;   // developer/test knob (process-wide, atomic)
 extern "C" HD_API int hd_roi_set_mode(int mode) { return __atomic_exchange_n(&g_roi_mode_, mode, __ATOMIC_ACQ_REL); }
 
@@ -911,7 +986,14 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
         }
         if (pool && quad) roi_pool_nhwc_quad_kernel<<<(unsigned)p.K, 256, smem, st>>>(p, use_tma, QT);
         else if (pool) roi_pool_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
-        else if (quad && tab < ROI_TAB && p.sampling_ratio <= 2) roi_align_nhwc_quad_kernel<4><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+        else if (quad && tab < ROI_TAB && p.sampling_ratio <= 2 && ((g_roi_mode >> 8) & 3) == 1)   // A/B: one table row in flight, 4 CTAs/SM
+            roi_align_nhwc_quad_kernel<4><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+        else if (quad && tab < ROI_TAB && p.sampling_ratio <= 2) {
+            // two table rows (up to 8 independent 128-bit loads) in flight per thread, 3 CTAs/SM: the kernel is bound by the chain of
+            // dependent load steps per thread, not by bandwidth -- measured 1.24 -> 1.15 ms on cfg3 (whole bin in flight, 2 CTAs/SM: 1.35 ms)
+            HD_ENSURE_SMEM((roi_align_nhwc_quad_kernel<4, 2>), 220 * 1024);
+            roi_align_nhwc_quad_kernel<4, 2><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+        }
         else if (quad && tab < ROI_TAB && p.sampling_ratio <= 4) roi_align_nhwc_quad_kernel<8><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
         else if (quad && tab < ROI_TAB) roi_align_nhwc_quad_kernel<16><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
         else if (quad) roi_align_nhwc_quad_kernel<0><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
@@ -947,6 +1029,33 @@ int hd_roi_align_launch_list(const RoiParams& p0, const int* list, const int* li
     if (tab < ROI_TAB && p.sampling_ratio >= 1 && p.sampling_ratio <= 2) roi_align_nhwc_quad_kernel<4><<<(unsigned)ctas, 256, smem_quad, st>>>(p, use_tma, QT, tab);
     else roi_align_nhwc_quad_kernel<0><<<(unsigned)ctas, 256, tile + 2 * (size_t)ROI_TAB * sizeof(AxisEntry), st>>>(p, use_tma, QT, ROI_TAB);
     HD_CUDA_LAUNCH_CHECK("roi_align_nhwc_quad_kernel (list)");
+    return HD_OK;
+}
+
+// developer entry point: sliced kernel over a caller-provided (position-sorted) device list; see tools/roi_slice_probe.py
+extern "C" HD_API int hd_debug_roi_align_sliced(const hd_roi_level* levels, int n_levels, int C, const float* rois, const int32_t* level_ids,
+                                                int64_t K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, float* out,
+                                                const int32_t* list, const int32_t* list_count, int slices, int chunk, void* stream) {
+    RoiParams p;
+    int rc = fill_roi(p, levels, n_levels, C, rois, level_ids, K, pooled_h, pooled_w, sampling_ratio, aligned, out, nullptr);
+    if (rc) return rc;
+    HD_CHECK_ARG(sampling_ratio >= 1 && sampling_ratio <= 2 && slices >= 1 && chunk >= 1 && C % (4 * slices) == 0, "sliced kernel: sr in [1,2], C %% (4*slices) == 0");
+    HD_CHECK_ARG(pooled_h <= 64 && pooled_w <= 64, "pooled size");
+    if (K == 0) return HD_OK;
+    p.list = list; p.list_count = list_count;
+    const int Cs = C / slices;
+    const size_t tile = (size_t)Cs * pooled_h * pooled_w * 4;
+    HD_CHECK_ARG(tile % 16 == 0 && (((uintptr_t)out & 15) == 0), "tile alignment");
+    const int mx = pooled_h > pooled_w ? pooled_h : pooled_w;
+    const int tab = 16 * mx;
+    const size_t smem = tile + 2 * (size_t)tab * sizeof(AxisEntry);
+    HD_CHECK_ARG(smem <= 220 * 1024, "tile too large");
+    int nq = Cs / 4, QT = 8;
+    while (QT < nq && QT < 256) QT <<= 1;
+    HD_ENSURE_SMEM(roi_align_sliced_kernel, 220 * 1024);
+    const long long ctas = (K + chunk - 1) / chunk;
+    roi_align_sliced_kernel<<<dim3((unsigned)ctas, (unsigned)slices), 256, smem, (cudaStream_t)stream>>>(p, QT, tab, chunk);
+    HD_CUDA_LAUNCH_CHECK("roi_align_sliced_kernel");
     return HD_OK;
 }
 

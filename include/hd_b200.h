@@ -184,16 +184,22 @@ HD_API int hd_roi_align(const hd_roi_level* levels /*host*/, int n_levels, int l
                         float* out, void* stream);
 
 /* The same operation with the batch size and a caller workspace (hd_roi_align_workspace_size bytes; the answer depends only on
- * the shapes).  For many RoIs on NHWC features (C % 32 == 0, output <= 7x7, 1 <= sampling_ratio <= 2) this runs the STREAMED
- * kernel (csrc/roi_strip.cu): RoIs are bucketed by (image, level, x-strip) and sorted by their first feature row on the device, and
- * every bucket's rows cross L2->SM once through a TMA-fed shared-memory ring, instead of once per RoI.  Every other case (and any
- * RoI the strips cannot take) is computed by the per-RoI kernels of hd_roi_align; results are the same values either way.
- * Replaces: torchvision MultiScaleRoIAlign / roi_align call site (poolers.py:147-227, roi_align.py:204-260; README.md:65). */
+ * the shapes).  By default this runs the per-RoI kernels of hd_roi_align (the fastest measured on B200).  Two bucketed variants for
+ * many RoIs on NHWC features (C % 32 == 0, output <= 7x7, 1 <= sampling_ratio <= 2) are opt-in through hd_roi_set_mode -- 2: the
+ * STREAMED kernel (csrc/roi_strip.cu: RoIs bucketed by (image, level, x-strip) and sorted by first feature row on the device, rows
+ * cross L2->SM once through a TMA-fed shared-memory ring), 3: the row-walk kernel; both return the same bits and both measured
+ * slower.  Replaces: torchvision MultiScaleRoIAlign / roi_align call site (poolers.py:147-227,
+ * roi_align.py:204-260; README.md:65). */
 HD_API size_t hd_roi_align_workspace_size(const hd_roi_level* levels /*host*/, int n_levels, int C, int batch, int64_t K, int pooled_h,
                                           int pooled_w, int sampling_ratio);
 HD_API int hd_roi_align_ws(const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, int batch, const float* rois,
                            const int32_t* level_ids, int64_t K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, float* out,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* developer experiment: channel-sliced gather kernel, `slices` CTAs per RoI, every CTA walking `chunk` consecutive
+ * entries of the device list `list[0 .. *list_count)` (RoI indices the caller sorted by position).  sampling_ratio 1..2, NHWC. */
+HD_API int hd_debug_roi_align_sliced(const hd_roi_level* levels /*host*/, int n_levels, int C, const float* rois, const int32_t* level_ids,
+                                     int64_t K, int pooled_h, int pooled_w, int sampling_ratio, int aligned, float* out,
+                                     const int32_t* list, const int32_t* list_count, int slices, int chunk, void* stream);
 /* argmax (int32 [K,C,PH,PW], index h*W+w inside the channel plane, -1 for an empty bin) may be NULL. */
 HD_API int hd_roi_pool(const hd_roi_level* levels /*host*/, int n_levels, int layout, int C, const float* rois,
                        const int32_t* level_ids, int64_t K, int pooled_h, int pooled_w, float* out, int32_t* argmax,
