@@ -165,6 +165,25 @@ __device__ __forceinline__ float4 roi_row_quad(const float4* __restrict__ row, c
 // R table rows (fixed y cells) of a bin with their NX x entries each: R*NX independent loads in flight, then the same fma order
 // as the row-at-a-time form (r = sum_b wx[b] v[b]; acc = fma(wy, r, acc), rows ascending)
 template <int R, int NX>
+__device__ __forceinline__ void roi_rows_quad(const float* __restrict__ f, int q, const AxisEntry* yt, const int* xo, const float* wx, float4& acc, float4& last) {
+    float4 v[R][NX];
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+        const float4* __restrict__ row = reinterpret_cast<const float4*>(f + yt[a].off) + q;
+#pragma unroll
+        for (int b = 0; b < NX; ++b) v[a][b] = __ldg(row + xo[b]);
+    }
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < NX; ++b) { r.x = fmaf(wx[b], v[a][b].x, r.x); r.y = fmaf(wx[b], v[a][b].y, r.y); r.z = fmaf(wx[b], v[a][b].z, r.z); r.w = fmaf(wx[b], v[a][b].w, r.w); }
+        const float wy = yt[a].w;
+        acc.x = fmaf(wy, r.x, acc.x); acc.y = fmaf(wy, r.y, acc.y); acc.z = fmaf(wy, r.z, acc.z); acc.w = fmaf(wy, r.w, acc.w);
+        if (a == R - 1) last = r;
+    }
+}
+template <int R, int NX>
 __device__ __forceinline__ void roi_rows_quad(const float* __restrict__ f, int q, const AxisEntry* yt, const int* xo, const float* wx, float4& acc) {
     float4 v[R][NX];
 #pragma unroll
@@ -361,6 +380,99 @@ __global__ void __launch_bounds__(256, (EFIX == 4 && MLP == 1) ? 4 : 3) roi_alig
     }
     tile_store(p.out + (size_t)k * p.C * nb, tile, p.C * nb, use_tma != 0);
     __syncthreads();   // the tile and the tables are rewritten by the next RoI of the walk
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ RoIAlign NHWC, column owners
+// Same tables, loads and fma order as the channel-quad kernel above (bit-identical results), different loop nest: warp = output
+// column pw, lane = channel quad.  The x entries of a column (offsets, weights, their count) are fixed for the whole RoI, so they sit
+// in registers and the code path is chosen once per warp instead of once per bin row; the bin loop is ph = 0..PH-1 with nothing
+// but the y entries (broadcast shared-memory reads) changing.  ~2.3x fewer instructions per bin than the bin-group walk, which was
+// half issue-bound (ncu: sm 53 %, 210 instructions per bin and thread of which ~80 are loads and fmas).
+template <int NX>
+__device__ __forceinline__ void roi_align_col_quad(const float* __restrict__ f, int lane, int nq, int pw, const AxisEntry* ytab, const AxisEntry* xt,
+                                                   const int* ycnt, int PH, int PW, float count, float* tile) {
+    int xo[NX]; float wx[NX];
+#pragma unroll
+    for (int b = 0; b < NX; ++b) { xo[b] = xt[b].off >> 2; wx[b] = xt[b].w; }
+    const int nb = PH * PW;
+    const int icount = (int)count;
+    const bool pow2 = (icount & (icount - 1)) == 0;                   // x / 2^k == x * 2^-k exactly
+    const float inv = 1.0f / count;
+    const int rot = lane >> 3;
+    for (int q = lane; q < nq; q += 32) {
+        float* tq = tile + (size_t)(4 * q) * nb + pw;
+        // Consecutive bins of a column usually share their boundary cell row (bin height ~1.8 cells at sampling_ratio 2: cells
+        // {0,1,2} then {2,3,4}).  Its x-interpolated value r is the same number for both bins (same cells, same x weights), so it is
+        // kept in registers: ~1/3 fewer loads and fmas, and most bins need ONE round of loads (two new rows) instead of two.
+        float4 rl = make_float4(0.f, 0.f, 0.f, 0.f);
+        int offl = -1;
+        for (int ph = 0; ph < PH; ++ph) {
+            const AxisEntry* yt = ytab + ph * 4;
+            const int ny = ycnt[ph];
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int a = 0;
+            if (ny > 0 && yt[0].off == offl) {
+                const float wy = yt[0].w;
+                acc.x = fmaf(wy, rl.x, acc.x); acc.y = fmaf(wy, rl.y, acc.y); acc.z = fmaf(wy, rl.z, acc.z); acc.w = fmaf(wy, rl.w, acc.w);
+                a = 1;
+            }
+            for (; a + 2 <= ny; a += 2) roi_rows_quad<2, NX>(f, q, yt + a, xo, wx, acc, rl);
+            if (a < ny) roi_rows_quad<1, NX>(f, q, yt + a, xo, wx, acc, rl);
+            if (ny > 0) offl = yt[ny - 1].off;
+            if (pow2) { acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv; }
+            else { acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count); acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count); }
+            // lane-rotated store order (rot = lane/8): at every step the 32 lanes hit 32 different banks
+            float* t = tq + ph * PW;
+            const float a0 = (rot & 1) ? acc.y : acc.x, a1 = (rot & 1) ? acc.z : acc.y, a2 = (rot & 1) ? acc.w : acc.z, a3 = (rot & 1) ? acc.x : acc.w;
+            const float b0 = (rot & 2) ? a2 : a0, b1 = (rot & 2) ? a3 : a1, b2 = (rot & 2) ? a0 : a2, b3 = (rot & 2) ? a1 : a3;  // b_s = acc[(s+rot)&3]
+            t[((0 + rot) & 3) * nb] = b0; t[((1 + rot) & 3) * nb] = b1; t[((2 + rot) & 3) * nb] = b2; t[((3 + rot) & 3) * nb] = b3;
+        }
+    }
+}
+
+// blockDim.x = 32 * PW (3 <= PW <= 7: 224 threads, 71 registers, 4 CTAs per SM beside their 50 KB tiles), sampling_ratio 1..2, C % 4 == 0
+__global__ void __launch_bounds__(224, 4) roi_align_nhwc_col_kernel(const __grid_constant__ RoiParams p, int use_tma, int tab, int dbg) {
+    extern __shared__ __align__(128) float smem_f[];
+    float* tile = smem_f;                                  // [C][PH*PW]
+    AxisEntry* ytab = (AxisEntry*)(tile + (size_t)p.C * p.PH * p.PW);
+    AxisEntry* xtab = ytab + tab;
+    __shared__ int ycnt[64], xcnt[64];
+    const long long nk = p.list ? (long long)*p.list_count : p.K;
+    for (long long kk = blockIdx.x; kk < nk; kk += gridDim.x) {
+        const long long k = p.list ? (long long)p.list[kk] : kk;
+        const float* roi = p.rois + k * 5;
+        const int lvl = p.level_ids ? p.level_ids[k] : 0;
+        const int H = p.H[lvl], W = p.W[lvl];
+        const float sc = p.scale[lvl];
+        const int bidx = (int)roi[0];
+        const float off = p.aligned ? 0.5f : 0.0f;
+        const float sw = __fsub_rn(__fmul_rn(roi[1], sc), off), sh = __fsub_rn(__fmul_rn(roi[2], sc), off);
+        const float ew = __fsub_rn(__fmul_rn(roi[3], sc), off), eh = __fsub_rn(__fmul_rn(roi[4], sc), off);
+        float rw = __fsub_rn(ew, sw), rh = __fsub_rn(eh, sh);
+        if (!p.aligned) { rw = fmaxf(rw, 1.0f); rh = fmaxf(rh, 1.0f); }
+        const float bh = __fdiv_rn(rh, (float)p.PH), bw = __fdiv_rn(rw, (float)p.PW);
+        const int gh = p.sampling_ratio, gw = p.sampling_ratio;
+        const float count = (float)max(gh * gw, 1);
+        const float* __restrict__ f = p.data[lvl] + (size_t)bidx * H * W * p.C;
+        if (threadIdx.x < p.PH) build_axis(ytab, ycnt, threadIdx.x, 4, sh, bh, gh, H, W * p.C, 4);
+        else if (threadIdx.x >= 64 && threadIdx.x < 64 + p.PW) build_axis(xtab, xcnt, threadIdx.x - 64, 4, sw, bw, gw, W, p.C, 4);
+        __syncthreads();
+        const int pw = threadIdx.x >> 5, lane = threadIdx.x & 31, nq = p.C >> 2, nx = (dbg & 2) ? 0 : xcnt[pw];   // (dbg 2: no loads)
+        const AxisEntry* xt = xtab + pw * 4;
+        if (nx == 2) roi_align_col_quad<2>(f, lane, nq, pw, ytab, xt, ycnt, p.PH, p.PW, count, tile);
+        else if (nx == 3) roi_align_col_quad<3>(f, lane, nq, pw, ytab, xt, ycnt, p.PH, p.PW, count, tile);
+        else if (nx == 4) roi_align_col_quad<4>(f, lane, nq, pw, ytab, xt, ycnt, p.PH, p.PW, count, tile);
+        else if (nx == 1) roi_align_col_quad<1>(f, lane, nq, pw, ytab, xt, ycnt, p.PH, p.PW, count, tile);
+        else {   // every sample of this column lies outside the map: zeros
+            const int nb = p.PH * p.PW;
+            for (int q = lane; q < nq; q += 32)
+                for (int ph = 0; ph < p.PH; ++ph)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) tile[(size_t)(4 * q + c) * nb + ph * p.PW + pw] = 0.0f;
+        }
+        if (!(dbg & 1)) tile_store(p.out + (size_t)k * p.C * (p.PH * p.PW), tile, p.C * (p.PH * p.PW), use_tma != 0);   // (dbg 1: no output)
+        __syncthreads();   // the tile and the tables are rewritten by the next RoI of the walk
     }
 }
 
@@ -988,6 +1100,10 @@ static int launch_roi(const RoiParams& p, int layout, bool pool, cudaStream_t st
         else if (pool) roi_pool_nhwc_kernel<<<(unsigned)p.K, threads, smem, st>>>(p, use_tma);
         else if (quad && tab < ROI_TAB && p.sampling_ratio <= 2 && ((g_roi_mode >> 8) & 3) == 1)   // A/B: one table row in flight, 4 CTAs/SM
             roi_align_nhwc_quad_kernel<4><<<(unsigned)p.K, 256, smem_quad, st>>>(p, use_tma, QT, tab);
+        else if (quad && tab < ROI_TAB && p.sampling_ratio <= 2 && p.PW >= 3 && p.PW <= 7 && ((g_roi_mode >> 8) & 3) != 2) {
+            HD_ENSURE_SMEM(roi_align_nhwc_col_kernel, 220 * 1024);
+            roi_align_nhwc_col_kernel<<<(unsigned)p.K, 32 * p.PW, smem_quad, st>>>(p, use_tma, tab, (g_roi_mode >> 4) & 15);
+        }
         else if (quad && tab < ROI_TAB && p.sampling_ratio <= 2) {
             // two table rows (up to 8 independent 128-bit loads) in flight per thread, 3 CTAs/SM: the kernel is bound by the chain of
             // dependent load steps per thread, not by bandwidth -- measured 1.24 -> 1.15 ms on cfg3 (whole bin in flight, 2 CTAs/SM: 1.35 ms)

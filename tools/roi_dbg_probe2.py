@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""cfg3 RoIAlign gather kernels: bin-group walk with 1 / 2 table rows in flight per thread vs the column-owner kernel (default); L2 flushed."""
+"""cfg3 RoIAlign column-owner kernel, ablations through hd_roi_set_mode bits 4..7 (1: no output store, 2: no loads): where the time goes."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,7 +12,6 @@ pr = rpn.RpnProposals(bases, (4, 8, 16, 32), (img, img), n_pre_nms=12000, n_post
 rois, cnt, _, _ = pr([o.cuda() for o in obj], [d.cuda() for d in dlt])
 scales = [1 / 4, 1 / 8, 1 / 16, 1 / 32]
 flush = torch.empty((256 << 20,), dtype=torch.uint8, device="cuda")
-nbytes = sum(f.numel() * 4 for f in feats) + rois.shape[0] * 256 * 49 * 4
 
 
 def timed(fn, iters=10):
@@ -26,12 +25,11 @@ def timed(fn, iters=10):
     return sum(a.elapsed_time(b) for a, b in ev) / iters
 
 
-roi.set_mode(1)
-ref = roi.multilevel_roi_align(feats, rois, 7, scales, 2, False)[0]
-for name, mode in (("bin groups, 1 row in flight", 1 | (1 << 8)), ("bin groups, 2 rows in flight", 1 | (2 << 8)), ("column owners (default)", 1)):
-    roi.set_mode(mode)
-    for sr in (2, 1):
-        t = timed(lambda: roi.multilevel_roi_align(feats, rois, 7, scales, sr, False))
-        eq = bool(torch.equal(roi.multilevel_roi_align(feats, rois, 7, scales, 2, False)[0], ref))
-        print(f"{name:34s} sr={sr}: {t * 1e3:8.1f} us  {nbytes / t / 1e6:7.1f} GB/s ({nbytes / t / 1e6 / 6536.7 * 100:.1f}% of measured peak)  bit-equal {eq}", flush=True)
+for name, dbg in (("full", 0), ("no output store", 1), ("no loads", 2), ("no loads, no output store", 3)):
+    roi.set_mode(1 | (dbg << 4))
+    t = timed(lambda: roi.multilevel_roi_align(feats, rois, 7, scales, 2, False))
+    print(f"{name:28s} {t * 1e3:8.1f} us", flush=True)
 roi.set_mode(0)
+out = torch.empty((rois.shape[0], 256, 7, 7), device="cuda")
+print(f"{'torch fill of the output':28s} {timed(lambda: out.fill_(1.0)) * 1e3:8.1f} us")
+print(f"{'torch empty (allocator)':28s} {timed(lambda: torch.empty((rois.shape[0], 256, 7, 7), device='cuda')) * 1e3:8.1f} us")
