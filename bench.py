@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--depth", type=int, default=0, help="software-pipeline depth (CUDA streams); 0 = auto: 4 for shards of >= 128 images, "
                     "8 below (measured on B200: a 32-image shard runs 45.9 / 41.0 / 38.8 / 38.5 us per step at depth 3 / 4 / 6 / 8)")
     ap.add_argument("--batch", type=int, default=BATCH, help="global batch (strong) / per-rank batch (weak)")
-    ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg1/3/4/5 lines (they are only produced at N=1)")
     return ap.parse_args()

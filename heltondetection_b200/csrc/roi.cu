@@ -54,7 +54,11 @@ __device__ __forceinline__ void tile_store(float* __restrict__ gdst, const float
         }
     } else {
         __syncthreads();
-        for (int i = threadIdx.x; i < n_floats; i += blockDim.x) gdst[i] = tile[i];
+        if ((n_floats & 3) == 0 && (((uintptr_t)gdst) & 15) == 0) {
+            for (int i = threadIdx.x; i < (n_floats >> 2); i += blockDim.x) reinterpret_cast<float4*>(gdst)[i] = reinterpret_cast<const float4*>(tile)[i];
+        } else {
+            for (int i = threadIdx.x; i < n_floats; i += blockDim.x) gdst[i] = tile[i];
+        }
     }
 }
 
@@ -471,7 +475,7 @@ __global__ void __launch_bounds__(224, 4) roi_align_nhwc_col_kernel(const __grid
 #pragma unroll
                     for (int c = 0; c < 4; ++c) tile[(size_t)(4 * q + c) * nb + ph * p.PW + pw] = 0.0f;
         }
-        if (!(dbg & 1)) tile_store(p.out + (size_t)k * p.C * (p.PH * p.PW), tile, p.C * (p.PH * p.PW), use_tma != 0);   // (dbg 1: no output)
+        if (!(dbg & 1)) tile_store(p.out + (size_t)k * p.C * (p.PH * p.PW), tile, p.C * (p.PH * p.PW), use_tma != 0 && !(dbg & 4));   // (dbg 1: no output, 4: thread stores)
         __syncthreads();   // the tile and the tables are rewritten by the next RoI of the walk
     }
 }

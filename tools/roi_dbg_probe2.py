@@ -25,7 +25,7 @@ def timed(fn, iters=10):
     return sum(a.elapsed_time(b) for a, b in ev) / iters
 
 
-for name, dbg in (("full", 0), ("no output store", 1), ("no loads", 2), ("no loads, no output store", 3)):
+for name, dbg in (("full", 0), ("full, thread stores (no TMA)", 4), ("no output store", 1), ("no loads", 2), ("no loads, thread stores", 6), ("no loads, no output store", 3)):
     roi.set_mode(1 | (dbg << 4))
     t = timed(lambda: roi.multilevel_roi_align(feats, rois, 7, scales, 2, False))
     print(f"{name:28s} {t * 1e3:8.1f} us", flush=True)
