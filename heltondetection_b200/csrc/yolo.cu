@@ -73,7 +73,7 @@ struct YoloParams {
 //   - survivors are compacted with one atomicAdd per warp.
 // ------------------------------------------------------------------------------------------------
 template <bool VEC, typename T>
-__device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long long item, const int lane, float* stage,
+__device__ __forceinline__ void yolo_decode_item_packed(const YoloParams& p, const long long item, const int lane, float* stage,
                                                  float4* __restrict__ cand_box, float* __restrict__ cand_score,
                                                  int* __restrict__ cand_cls, int* __restrict__ cand_anchor,
                                                  int* __restrict__ cand_count) {
@@ -293,6 +293,180 @@ __device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lean variant of the tile walk above for deployment thresholds (conf >= 0.05 and nc >= 16): survivors are rare, so each lane
+// simply walks its own four cells, and nothing but the plane loop holds registers -- on the 85-plane cfg2 head this form runs
+// at the copy bandwidth (0.311 ms per 256 images), 6 % faster than the packed variant, whose staging bookkeeping costs six spilled
+// registers inside the plane loop.  Same candidates (the order inside an image is arbitrary in both).
+// ------------------------------------------------------------------------------------------------
+template <bool VEC, typename T>
+__device__ __forceinline__ void yolo_decode_item(const YoloParams& p, const long long item, const int lane,
+                                                 float4* __restrict__ cand_box, float* __restrict__ cand_score,
+                                                 int* __restrict__ cand_cls, int* __restrict__ cand_anchor,
+                                                 int* __restrict__ cand_count) {
+    const int b = (int)(item / p.items_per_image);
+    int r = (int)(item - (long long)b * p.items_per_image);
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < HD_MAX_LEVELS; ++q)
+        if (q < p.n_levels && r >= p.A * p.tile_start[q]) l = q;
+    r -= p.A * p.tile_start[l];
+    const int tiles_l = p.tile_start[l + 1] - p.tile_start[l];
+    const int a = r / tiles_l;
+    const int t = r - a * tiles_l;
+    const int HW = p.HW[l];
+    const int cell0 = t * 128 + lane * 4;
+    const T* __restrict__ base = reinterpret_cast<const T*>(p.data[l]) + ((size_t)(b * p.A + a) * p.no) * HW + cell0;
+
+    float o[4], bx[4][4], m[4], L[4];
+    int j[4];
+    bool valid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) valid[k] = (cell0 + k) < HW;
+
+    bool need = true;  // lane fetches the non-objectness planes (narrowed below in sparse mode)
+    auto load4 = [&](int plane, float* v) {
+        const T* q = base + (size_t)plane * HW;
+        if (VEC) {
+            if (valid[0] && need) hd_load4<T>(q, v);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (valid[k] && need) v[k] = hd_load1<T>(q + k);
+        }
+    };
+
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = -INFINITY;
+    load4(4, o);
+    bool gate_any = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gate_any |= valid[k] && (o[k] > p.gate);
+    if (!p.dense && !__any_sync(HD_FULL, gate_any)) return;
+    // sparse mode: only lanes that own a possible survivor touch the other 84 planes, so the traffic of a
+    // surviving tile shrinks from 85 x 512 B to 85 x (one 32-byte sector per surviving lane)
+    need = p.dense || gate_any;
+
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bx[c][k] = 0.0f;
+        load4(c, bx[c]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m[k] = -INFINITY; L[k] = -INFINITY; j[k] = 0; }
+
+    auto upd = [&](const float* v, int c) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bool g = v[k] > m[k];
+            L[k] = g ? m[k] : L[k];
+            j[k] = g ? c : j[k];
+            m[k] = g ? v[k] : m[k];
+        }
+    };
+    int c = 0;
+    if (VEC) {
+        // U independent plane loads in flight per lane (same bytes in flight for 32-bit and 16-bit heads)
+        constexpr int U = (sizeof(T) == 4) ? 8 : 16;
+        const bool ld = valid[0] && need;
+        for (; c + U <= p.nc; c += U) {
+            HdRaw4<T> raw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ld) raw[u] = hd_load_raw4<T>(base + (size_t)(5 + c + u) * HW);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (ld) hd_unpack4<T>(raw[u], v);
+                upd(v, c + u);
+            }
+        }
+    } else {
+        constexpr int U = 8;
+        for (; c + U <= p.nc; c += U) {
+            float v[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[u][k] = -INFINITY;
+                load4(5 + c + u, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) upd(v[u], c + u);
+        }
+    }
+    for (; c < p.nc; ++c) {
+        float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        load4(5 + c, v);
+        upd(v, c);
+    }
+
+    // survivors
+    float conf[4];
+    int npass = 0;
+    bool pass[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        pass[k] = false;
+        if (valid[k] && o[k] > p.gate) {
+            float po = hd_sigmoid(o[k]);
+            float cf = __fmul_rn(hd_sigmoid(m[k]), po);
+            bool ok = p.ge ? (po >= p.thr && cf >= p.thr) : (po > p.thr && cf > p.thr);
+            if (ok) {
+                if (L[k] > -INFINITY && __fmul_rn(hd_sigmoid(L[k]), po) == cf) {
+                    // an earlier class ties after rounding: torch.max returns the first maximal product
+                    const T* q = base + k;
+                    for (int cc = 0; cc < j[k]; ++cc) {
+                        float lg = hd_load1<T>(q + (size_t)(5 + cc) * HW);
+                        if (__fmul_rn(hd_sigmoid(lg), po) == cf) { j[k] = cc; break; }
+                    }
+                }
+                pass[k] = true;
+                conf[k] = cf;
+                ++npass;
+            }
+        }
+    }
+    // warp-aggregated slot claim
+    int incl = npass;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(HD_FULL, incl, d);
+        if (lane >= d) incl += y;
+    }
+    int total = __shfl_sync(HD_FULL, incl, 31);
+    if (total == 0) return;
+    int slot0 = 0;
+    if (lane == 31) slot0 = atomicAdd(cand_count + b, total);
+    slot0 = __shfl_sync(HD_FULL, slot0, 31);
+    int slot = slot0 + incl - npass;
+    const float s = p.stride[l];
+    const float aw = p.anchor[l][2 * a], ah = p.anchor[l][2 * a + 1];
+    const int W = p.W[l];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!pass[k]) continue;
+        if (slot < p.cap) {
+            const int cell = cell0 + k;
+            const int gi = cell / W, gj = cell - gi * W;
+            // (p*2 - 0.5 + grid) * s ; (p*2)^2 * anchor : fp32, op order of the reference decode
+            float px = __fmul_rn(hd_sigmoid(bx[0][k]), 2.0f), py = __fmul_rn(hd_sigmoid(bx[1][k]), 2.0f);
+            float pw = __fmul_rn(hd_sigmoid(bx[2][k]), 2.0f), ph = __fmul_rn(hd_sigmoid(bx[3][k]), 2.0f);
+            float cx = __fmul_rn(__fadd_rn(__fsub_rn(px, 0.5f), (float)gj), s);
+            float cy = __fmul_rn(__fadd_rn(__fsub_rn(py, 0.5f), (float)gi), s);
+            float w = __fmul_rn(__fmul_rn(pw, pw), aw), h = __fmul_rn(__fmul_rn(ph, ph), ah);
+            float hw2 = __fmul_rn(w, 0.5f), hh2 = __fmul_rn(h, 0.5f);  // w/2 exact
+            size_t g = (size_t)b * p.cap + slot;
+            cand_box[g] = make_float4(__fsub_rn(cx, hw2), __fsub_rn(cy, hh2), __fadd_rn(cx, hw2), __fadd_rn(cy, hh2));
+            cand_score[g] = conf[k];
+            cand_cls[g] = j[k];
+            cand_anchor[g] = p.level_off[l] + a * HW + cell;
+        }
+        ++slot;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // multi_label variant (ultralytics non_max_suppression with multi_label=True, the evaluation setting conf 0.001 / iou 0.6 when
 // nc > 1): after `x[:, 5:] *= x[:, 4:5]` EVERY class with obj*cls > conf_thres yields a candidate (box, obj*cls, class), in
 // (anchor, class) order.  Same tile walk as above; per group of class planes the lanes count their hits (logit gate first, then the
@@ -422,9 +596,22 @@ __global__ void __launch_bounds__(256, 4) yolo_decode_filter_kernel(const __grid
                                                                  int* __restrict__ cand_anchor,
                                                                  int* __restrict__ cand_count) {
     const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= p.total_items) return;
+    yolo_decode_item<VEC, T>(p, item, threadIdx.x & 31, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
+}
+
+// packed-survivor variant (evaluation thresholds / small heads), see yolo_decode_item_packed
+template <bool VEC, typename T = float>
+__global__ void __launch_bounds__(256, 4) yolo_decode_filter_packed_kernel(const __grid_constant__ YoloParams p,
+                                                                        float4* __restrict__ cand_box,
+                                                                        float* __restrict__ cand_score,
+                                                                        int* __restrict__ cand_cls,
+                                                                        int* __restrict__ cand_anchor,
+                                                                        int* __restrict__ cand_count) {
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     __shared__ float stage[8][8 * 32];   // per warp: 32 dealt-out cells x (obj, max logit, runner-up, class|cell, 4 box logits)
     if (item >= p.total_items) return;
-    yolo_decode_item<VEC, T>(p, item, threadIdx.x & 31, stage[threadIdx.x >> 5], cand_box, cand_score, cand_cls, cand_anchor, cand_count);
+    yolo_decode_item_packed<VEC, T>(p, item, threadIdx.x & 31, stage[threadIdx.x >> 5], cand_box, cand_score, cand_cls, cand_anchor, cand_count);
 }
 
 template <bool VEC, typename T = float>
@@ -885,9 +1072,12 @@ extern "C" HD_API int hd_yolo_decode_filter(const hd_yolo_level* levels, int n_l
     const int warps = 8;
     long long blocks = (p.total_items + warps - 1) / warps;
     HD_CHECK_ARG(blocks < (1ll << 31), "grid too large");
+    // many survivors per tile (evaluation thresholds) or few planes per tile: the packed variant; else the lean one
+    const bool packed = conf_thres < 0.05 || nc < 16;
 #define HD_YOLO_LAUNCH(V, T)                                                                                                                     \
     do {                                                                                                                                         \
         if (p.multi) yolo_decode_filter_multi_kernel<V, T><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count); \
+        else if (packed) yolo_decode_filter_packed_kernel<V, T><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count); \
         else yolo_decode_filter_kernel<V, T><<<(unsigned)blocks, warps * 32, 0, st>>>(p, (float4*)cand_box, cand_score, cand_cls, cand_anchor, cand_count);                \
     } while (0)
     if (dt == 0) { if (vec) HD_YOLO_LAUNCH(true, float); else HD_YOLO_LAUNCH(false, float); }
