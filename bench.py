@@ -316,8 +316,14 @@ def extra_configs(dev, peak, cpu_cores):
             fusion.map_back(v, det, c)
         return fusion.fuse()
     nbytes = sum(h.numel() * 4 for d in devh for h in d)
-    t_full = time_flushed(full, flush, 10)
-    full()
+    t_eager = time_flushed(full, flush, 10)
+    ref_out = [t.clone() for t in full()]
+    # the form a deployment uses: views alternating over three streams (NMS + map-back of one view under the decode of the next), one graph
+    replay, g_out = fusion.graph(pps, devh, n_streams=3)
+    t_full = time_flushed(replay, flush, 10)
+    replay()
+    torch.cuda.synchronize()
+    same = bool(all(torch.equal(a, b) for a, b in zip(g_out, ref_out)))
     t_wbf = time_flushed(lambda: fusion.fuse(), flush, 10)
 
     def tta_cpu():
@@ -331,6 +337,8 @@ def extra_configs(dev, peak, cpu_cores):
     cpu_t = _best(tta_cpu, 1)
     out["cfg5"] = {"workload": "cfg5: YOLOv5s TTA 6 views (544/640/768 x {id,hflip}) batch 64: 6x(decode+filter+NMS) + map-back + Weighted Boxes Fusion",
                    "ms": t_full, "img_s": B / t_full * 1e3, "roofline": roof(nbytes, t_full, peak), "wbf_alone_ms": t_wbf,
+                   "form": "TTAFusion.graph: views alternating over 3 CUDA streams, one CUDA graph", "eager_view_after_view_ms": t_eager,
+                   "graph_equals_eager": same,
                    "fused_per_img": float(fusion.wbf.oc.float().mean()),
                    "cpu_baseline": {"value": 2 / cpu_t, "unit": "img/s", "cores": cpu_cores, "kind": "port", "sample": "2 images x 6 views, best of 1 after 1 warm-up"}}
     out["timing"] = "CUDA events around every iteration, a 256 MB buffer written between iterations (L2 flush, not timed)"

@@ -117,3 +117,40 @@ class TTAFusion:
 
     def fuse(self):
         return self.wbf(self.bx, self.sc, self.lb, self.cnt)
+
+    def run(self, postprocessors, view_outputs, n_streams=2):
+        """Whole TTA step: view v's decode + NMS + map-back run on side stream v % n_streams, so the (small, latency-bound) NMS and
+        map-back kernels of one view execute under the (HBM-bound) decode of the next; WBF follows the join on the current stream.
+        postprocessors: one yolo.YoloPostprocessor per view (each owns its buffers); view_outputs: per view the list of head
+        tensors.  Same results as calling the views one after the other; no host synchronisation, CUDA-graph capturable."""
+        first = view_outputs[0][0]
+        dev = first.device if first.is_cuda else postprocessors[0].device
+        with torch.cuda.device(dev):
+            self._alloc(int(first.shape[0]), dev)
+            cur = torch.cuda.current_stream(dev)
+            if getattr(self, "_streams_dev", None) != (dev, n_streams):
+                self._side = [torch.cuda.Stream(device=dev) for _ in range(max(1, int(n_streams)))]
+                self._streams_dev = (dev, n_streams)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            for s in self._side:
+                s.wait_event(fork)
+            for v in range(len(self.views)):
+                with torch.cuda.stream(self._side[v % len(self._side)]):
+                    det, count, _ = postprocessors[v](view_outputs[v])
+                    self.map_back(v, det, count)
+            for s in self._side:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                cur.wait_event(ev)
+            return self.fuse()
+
+    def graph(self, postprocessors, view_outputs, n_streams=2, warmup=3):
+        """Capture run() on fixed input buffers into one CUDA graph -> (replay, fused outputs)."""
+        for _ in range(warmup):
+            out = self.run(postprocessors, view_outputs, n_streams)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.run(postprocessors, view_outputs, n_streams)
+        return g.replay, out

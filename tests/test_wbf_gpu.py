@@ -115,3 +115,43 @@ def test_tta_pipeline_matches_oracle():
         assert np.array_equal(ol[b, :m].cpu().numpy().astype(np.float64), rl)
         assert np.allclose(ob[b, :m].cpu().numpy().astype(np.float64), rb, rtol=1e-5, atol=1e-7)
         assert np.allclose(os_[b, :m].cpu().numpy(), rs, rtol=1e-5, atol=0)
+
+
+def test_tta_run_on_streams_and_graph_equal_the_sequential_chain():
+    """TTAFusion.run (views alternating over two side streams, WBF after the join) and its CUDA-graph form return the bits of the
+    view-after-view chain, also when the graph is replayed on new head values."""
+    from heltondetection_b200 import synth, yolo, wbf
+    B, img, nc = 4, 640, 80
+    views, _ = synth.tta_heads(B, img, nc, G=8, seed=1240)
+    vspec = [(r, flip, size) for (_, r, flip, size) in views]
+    devh = [[h.cuda() for h in heads] for (heads, _, _, _) in views]
+
+    def sequential(hv):
+        fusion = wbf.TTAFusion(vspec, (img, img), nc, max_det=300, iou_thr=0.55, skip_box_thr=0.001)
+        pp = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45)
+        for v in range(len(views)):
+            det, cnt, _ = pp(hv[v])
+            fusion.map_back(v, det, cnt)
+        return [t.clone() for t in fusion.fuse()]
+
+    ref = sequential(devh)
+    fusion = wbf.TTAFusion(vspec, (img, img), nc, max_det=300, iou_thr=0.55, skip_box_thr=0.001)
+    pps = [yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45) for _ in views]
+    got = fusion.run(pps, devh)
+    torch.cuda.synchronize()
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    replay, out = fusion.graph(pps, devh)
+    views2, _ = synth.tta_heads(B, img, nc, G=8, seed=1241)
+    for hv, (heads, _, _, _) in zip(devh, views2):
+        for dst, src in zip(hv, heads):
+            dst.copy_(src)
+    replay()
+    torch.cuda.synchronize()
+    ref2 = sequential(devh)
+    assert int(ref2[3].sum()) > 0 and not torch.equal(ref2[0], ref[0])
+    assert torch.equal(out[3], ref2[3])                      # fused boxes per image
+    for b in range(B):                                       # rows past the count keep whatever an earlier call left there
+        m = int(ref2[3][b])
+        for a, r in zip(out[:3], ref2[:3]):
+            assert torch.equal(a[b, :m], r[b, :m])
