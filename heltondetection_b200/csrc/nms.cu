@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) box_iou_kernel(const float4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ host
-// ---- "did a recent call have a large image?"  One mapped host word per (device, workspace-hash slot): the large-path kernels
+// ---- "did a recent call have a large image?"  One mapped host word per device: the large-path kernels
 // store the call id there (a posted write over PCIe), the host reads it at the next call without synchronising.  The answer only
 // selects between kernels that return identical bits, so a stale value costs time, never correctness.
 #include <mutex>
@@ -356,10 +356,14 @@ static bool nms_hint_slot(const void* workspace, cudaStream_t st, unsigned** dev
         g_hint_dev[d] = (unsigned*)dv;
         g_hint_host[d] = (unsigned*)h;
     }
-    const unsigned slot = (unsigned)((((uintptr_t)workspace) >> 8) * 2654435761u) % NMS_HINT_SLOTS;
+    // one word per device: keying it by the workspace address looked finer-grained but missed exactly when it mattered -- the
+    // warm-up calls before a CUDA-graph capture and the captured call do not always see the same workspace address (a first call
+    // that allocates, a capture-time memory pool), so a dense workload could freeze the slow 256-thread kernel into its graph
+    (void)workspace;
+    const unsigned slot = 0u;
     const unsigned last_big = *reinterpret_cast<volatile unsigned*>(g_hint_host[d] + slot);
     const unsigned prev = g_hint_calls[d][slot];
-    *large_recent = (prev - last_big) < 64u;         // one of the last 64 calls through this workspace reported a large image
+    *large_recent = (prev - last_big) < 64u;         // one of the last 64 calls on this device reported a large image
     *call_id = ++g_hint_calls[d][slot];
     *dev_word = g_hint_dev[d] + slot;
     return true;

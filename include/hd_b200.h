@@ -126,8 +126,8 @@ HD_API size_t hd_sort_nms_workspace_size(int B, int cap);
 /* Images with more than 512 candidates are sorted and suppressed by one CTA each, or -- when the batch is small enough to
  * leave most SMs idle (B <= 33 on a B200) -- by a thread-block cluster of 4 or 8 CTAs per image; bit-identical outputs.
  * One-CTA images with more than 2048 candidates are ordered by a bucket sort on the score word (bitonic network as the fallback
- * for degenerate score distributions); the 1024-thread kernel is used while one of the last 64 calls through the same workspace
- * saw such an image, a 256-thread variant (co-resident with other kernels) otherwise -- same bits either way.
+ * for degenerate score distributions); the 1024-thread kernel is used while one of the last 64 calls on the same device
+ * saw such an image (one word per device), a 256-thread variant (co-resident with other kernels) otherwise -- same bits either way.
  * hd_nms_set_mode: 0 = automatic (default), 1 = one CTA per image only, 2 = clusters whenever the batch allows, 3 = always the
  * 256-thread variant, 4 = always the 1024-thread variant, 5 = as 1 with the bitonic network for every size.  Returns the
  * previous mode (developer / test aid). */

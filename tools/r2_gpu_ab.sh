@@ -1,14 +1,13 @@
 #!/bin/bash
-# headline check after a decode-kernel change: tests, bench (no configs) twice, cfg4 pipelined
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_yolo_gpu.py tests/test_fullsize_gpu.py tests/test_golden_gpu.py tests/test_properties_gpu.py -x -q 2>&1 | tail -3
-for round in 1 2; do
-  python bench.py --no-configs --e2e-steps 2 > gpurun_out/ab_new_$round.json 2>/dev/null
-done
+timeout 600 python -m pytest tests/test_nms_gpu.py tests/test_yolo_gpu.py tests/test_fullsize_gpu.py tests/test_peer_gpu.py -x -q 2>&1 | tail -3
+timeout 100 python tools/cfg1_probe.py 2>&1 | tail -9
+python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"
 python - <<'PY'
-import json, glob
-for f in sorted(glob.glob('gpurun_out/ab_new_*.json')):
-    j = json.loads(open(f).read().strip().splitlines()[-1])
-    print(f, 'value %.0f' % j['value'], 'ms %.4f' % j['ms_per_step'], 'serial %.4f' % j['step_ms_serial'])
+import json
+j = json.loads(open('gpurun_out/bench_n1.json').read().strip().splitlines()[-1])
+print('value %.0f' % j['value'], 'ms/step %.4f' % j['ms_per_step'], 'serial %.4f' % j['step_ms_serial'], 'frac %.3f' % j['roofline']['frac'], 'e2e %.0f' % j['e2e']['value'])
+for k, v in j.get('configs', {}).items():
+    if isinstance(v, dict):
+        print(k, 'ms %.4f' % v['ms'], 'frac %.3f' % v['roofline']['frac'], ('pipelined %.4f ms frac %.3f' % (v['pipelined']['ms'], v['pipelined']['roofline']['frac'])) if 'pipelined' in v else '', v.get('eager_view_after_view_ms', ''), v.get('graph_equals_eager', ''))
 PY
-timeout 100 python tools/cfg4_pipe.py 1 3
