@@ -226,3 +226,30 @@ def test_multi_label_matches_oracle(cfg):
             assert torch.equal(det[b, :n, 5].cpu(), ref[b][:, 5])
     if conf < 0.01:
         assert any(r.shape[0] != s.shape[0] or not torch.equal(r, s) for r, s in zip(ref, ref1)), "multi_label should change the low-threshold result"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("dense", [False, True])
+@pytest.mark.parametrize("nc,thr", [(1, 0.3), (3, 0.25), (10, 0.001), (11, 0.02), (17, 0.001), (35, 0.01), (82, 0.001)])
+def test_packed_survivor_variant_candidates_match_oracle(nc, thr, dense, dtype):
+    """conf < 0.05 or nc < 16 selects the packed-survivor decode kernel (objectness + box + first nc % U class planes in one load batch,
+    last nc % U planes in one batch, logit-domain pre-test, survivors dealt out one per lane); U = 8 planes for fp32 heads and 16 for
+    16-bit heads, so the class counts cover empty / merged / separate head and tail batches for both.  The candidate set, classes and
+    indices must equal the oracle's on the widened inputs, in both read modes."""
+    import oracle
+    from heltondetection_b200 import synth, yolo
+    heads, _ = synth.yolo_heads(2, 320, nc, 12, 300 + nc)
+    hd = [h.to(dtype).cuda() for h in heads]
+    wide = [h.float().cpu() for h in hd]
+    pred = oracle.yolo.decode_box(wide)
+    got = yolo.YoloPostprocessor(conf_thres=thr, dense_read=dense).candidates(hd)
+    n_total = 0
+    for b in range(2):
+        ref, ridx = oracle.yolo.filter_candidates(pred[b], thr, False)
+        c, idx = got[b]
+        assert torch.equal(idx.cpu(), ridx), f"candidate set differs: {idx.numel()} vs {ridx.numel()}"
+        assert torch.equal(c[:, 5].cpu(), ref[:, 5])
+        assert boxes_close(c[:, :4], ref[:, :4])
+        assert close(c[:, 4], ref[:, 4], scale=1e-3)
+        n_total += ridx.numel()
+    assert n_total > 0
