@@ -361,7 +361,7 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = hd_dist.bind_to_gpu_numa(local) if world > 1 else None   # before any pinned allocation
+    numa = hd_dist.bind_to_gpu_numa(local)   # before any pinned allocation (also at N=1: the e2e leg reads pinned host memory)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     strong = args.scaling == "strong"

@@ -10,7 +10,8 @@ import torch.distributed as dist
 def bind_to_gpu_numa(device_index):
     """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE pinned host buffers are allocated (first touch
     then places them on that node), so that zero-copy reads and H2D copies of 8 ranks do not all cross the socket interconnect.
-    Best effort: returns the node id, or None when the topology cannot be read."""
+    Best effort: returns the node id (sysfs), "nvml:<first>-<last cpu>" when only NVML knows the GPU's CPU set, or None when the
+    topology cannot be read (then nothing is changed)."""
     import os
     try:
         import torch
@@ -29,6 +30,22 @@ def bind_to_gpu_numa(device_index):
         if allowed:
             os.sched_setaffinity(0, allowed)
             return node
+    except Exception:  # noqa: BLE001
+        pass
+    # sysfs hides the node (containers / VMs report -1): ask NVML for the GPU's ideal CPU set instead
+    try:
+        import pynvml
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            return f"nvml:{min(allowed)}-{max(allowed)}"
     except Exception:  # noqa: BLE001
         pass
     return None
