@@ -12,6 +12,8 @@ j = json.loads(open('gpurun_out/bench_n1.json').read().strip().splitlines()[-1])
 print('value %.0f' % j['value'], 'ms/step %.4f' % j['ms_per_step'], 'serial %.4f' % j['step_ms_serial'], 'frac %.3f' % j['roofline']['frac'],
       'launches/step', j['gpu_launches'] / j['steps'], 'e2e %.0f' % j['e2e']['value'], 'clocks', j.get('clocks'))
 for k, v in j.get('configs', {}).items():
+    if not isinstance(v, dict):
+        continue
     print(k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items() if a in ('ms', 'img_s', 'keep_indices_match_oracle')},
           'frac %.3f' % v['roofline']['frac'] if 'roofline' in v else '', ('pipelined %.4f ms frac %.3f' % (v['pipelined']['ms'], v['pipelined']['roofline']['frac'])) if 'pipelined' in v else '')
 r = json.loads(open('gpurun_out/bench_ref.json').read().strip().splitlines()[-1])
