@@ -284,9 +284,9 @@ class PostprocessPipeline:
         pipe.fork(); [pipe.step(k) for k in range(K)]; pipe.join()      # outputs of step k: pipe.outputs(k)
     """
 
-    def __init__(self, pool, depth=2, peer=None, device=None, cycle_graph=False, min_cycle=48, **pp_kwargs):
+    def __init__(self, pool, depth=2, peer=None, device=None, cycle_graph=False, min_cycle=48, cycle_exact=False, **pp_kwargs):
         import math
-        self.pool, self.depth, self.peer, self.min_cycle = list(pool), int(depth), peer, min_cycle
+        self.pool, self.depth, self.peer, self.min_cycle, self.cycle_exact = list(pool), int(depth), peer, min_cycle, bool(cycle_exact)
         first = self.pool[0][0]
         self.device = torch.device(device) if device is not None else first.device
         if peer is not None and (peer.slots < self.depth or peer.slots % self.depth):
@@ -321,8 +321,13 @@ class PostprocessPipeline:
         step (at 32 images a step is ~40 us of GPU time: a Python loop issuing it step by step is host bound)."""
         dev, depth = self.device, self.depth
         # a cycle ends with the pipeline drained, so it should hold many steps: a multiple of the (input, workspace, gather slot)
-        # period that is at least ~48 steps long
-        self.cycle_len = self.n_graphs * max(1, -(-int(self.min_cycle) // self.n_graphs))
+        # period that is at least ~48 steps long -- or (cycle_exact) exactly min_cycle steps, for a caller that runs a fixed number
+        # of steps and wants them to be whole cycles (a cycle always starts from step 0's input / workspace / slot assignment and
+        # is fenced from its neighbours by full joins, so its length need not be a multiple of the period)
+        if self.cycle_exact:
+            self.cycle_len = max(1, int(self.min_cycle))
+        else:
+            self.cycle_len = self.n_graphs * max(1, -(-int(self.min_cycle) // self.n_graphs))
         main = torch.cuda.Stream(dev)
         streams = [torch.cuda.Stream(dev) for _ in range(depth)]
         side = torch.cuda.Stream(dev)
@@ -360,8 +365,8 @@ class PostprocessPipeline:
             torch.cuda.synchronize(dev)
 
     def run(self, k0, n_steps):
-        """steps k0 .. k0+n_steps-1 with as few host calls as possible (whole cycles as one graph launch); k0 must be a multiple
-        of the cycle length when the cycle graph is used"""
+        """steps k0 .. k0+n_steps-1 with as few host calls as possible (whole cycles as one graph launch, the remainder step by
+        step); the cycle graph is used when k0 is a multiple of the (input, workspace, slot) period"""
         k = k0
         if self.cycle is not None and k % self.n_graphs == 0:
             cur = torch.cuda.current_stream(self.device)

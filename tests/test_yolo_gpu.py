@@ -253,3 +253,42 @@ def test_packed_survivor_variant_candidates_match_oracle(nc, thr, dense, dtype):
         assert close(c[:, 4], ref[:, 4], scale=1e-3)
         n_total += ridx.numel()
     assert n_total > 0
+
+
+@pytest.mark.parametrize("cycle_exact,min_cycle", [(False, 4), (True, 5)])
+def test_postprocess_pipeline_cycles_equal_step_by_step(cycle_exact, min_cycle):
+    """PostprocessPipeline (steps over `depth` streams; whole cycles as one CUDA graph, the remainder step by step): after n steps the
+    postprocessor that ran step k last holds the detections of pool[k % len(pool)] -- for the rounded cycle length (a multiple of
+    the input/workspace period) and for an exact one that is not a multiple of anything."""
+    from heltondetection_b200 import synth, yolo
+    pool = [[h.cuda() for h in synth.yolo_heads(2, 320, 20, 8, 500 + j)[0]] for j in range(3)]
+    single = yolo.YoloPostprocessor(conf_thres=0.25, iou_thres=0.45)
+    want = []
+    for hs in pool:
+        want.append([t.clone() for t in single(hs)])
+    pipe = yolo.PostprocessPipeline(pool, depth=2, cycle_graph=True, min_cycle=min_cycle, cycle_exact=cycle_exact, conf_thres=0.25, iou_thres=0.45)
+    assert pipe.cycle is not None, getattr(pipe, "cycle_error", "")
+    assert pipe.cycle_len == (5 if cycle_exact else 6)
+    for n in (pipe.cycle_len, pipe.cycle_len + 2, 2 * pipe.cycle_len + 1):
+        for t in pipe.outputs(0) + pipe.outputs(1):
+            t.zero_()
+        pipe.fork(); pipe.run(0, n); pipe.join()
+        torch.cuda.synchronize()
+        # which step ran last on each of the two postprocessors: cycles always execute steps 0..cycle_len-1, the remainder continues at k
+        last = {}
+        k = 0
+        while n - k >= pipe.cycle_len:
+            for kk in range(pipe.cycle_len):
+                last[kk % 2] = kk % 3
+            k += pipe.cycle_len
+        while k < n:
+            g = k % pipe.n_graphs
+            last[g % 2] = g % 3
+            k += 1
+        for j in (0, 1):
+            det, cnt, idx = pipe.outputs(j)
+            wd, wc, wi = want[last[j]]
+            assert torch.equal(cnt, wc)
+            for b in range(2):
+                m = int(wc[b])
+                assert m > 0 and torch.equal(det[b, :m], wd[b, :m]) and torch.equal(idx[b, :m], wi[b, :m])
