@@ -14,7 +14,8 @@ _CONF = {"avg": _lib.WBF_AVG, "max": _lib.WBF_MAX, "box_and_model_avg": _lib.WBF
 
 class WbfBatched:
     """boxes [B,V,M,4], scores [B,V,M], labels [B,V,M] (float), counts [B,V] int32 ->
-    (boxes [B,V*M,4] f32, scores [B,V*M] f64, labels [B,V*M] f32, count [B] int32)."""
+    (boxes [B,V*M,4] f32, scores [B,V*M] f64, labels [B,V*M] f32, count [B] int32).  The output buffers are reused by every call;
+    rows of image b at and beyond count[b] are unspecified (whatever an earlier call left there)."""
 
     def __init__(self, num_labels, weights=None, iou_thr=0.55, skip_box_thr=0.0, conf_type="avg", allows_overflow=False,
                  rescale="len_weights"):

@@ -358,7 +358,7 @@ HD_API int hd_rpn_finish_levels(const float* det, const int64_t* slot, const int
  * labels [B,V,M] (float holding integers in [0,num_labels)), counts [B,V] valid rows per view.
  * weights: HOST array of V doubles (NULL = all 1).  Outputs, sorted by fused score desc, padded to V*M rows:
  *   out_boxes [B,V*M,4] f32, out_scores [B,V*M] f64 (the reference returns float64), out_labels [B,V*M] f32,
- *   out_count [B].
+ *   out_count [B]; rows of image b at and beyond out_count[b] are not written.
  * hd_tta_map_back writes view v of the WBF inputs from that view's detections det [B,max_det,6] (view px):
  *   un-flip x' = view_w - x (corners swapped), / scale, / (img_w, img_h).
  * ------------------------------------------------------------------------------------------- */
