@@ -311,6 +311,8 @@ class PostprocessPipeline:
                 self.replays.append(rp)
                 self.outs.append((det, cnt, idx))
         self._ev = torch.cuda.Event()
+        self._dirty, self._side_dirty = [True] * self.depth, True              # streams that may hold work a cycle replay has not waited for
+        self._fork_pending, self._cycle_pending, self._side_cycle_pending = [False] * self.depth, [False] * self.depth, False
         self.cycle = None
         if cycle_graph:
             self._capture_cycle()
@@ -366,22 +368,27 @@ class PostprocessPipeline:
 
     def run(self, k0, n_steps):
         """steps k0 .. k0+n_steps-1 with as few host calls as possible (whole cycles as one graph launch, the remainder step by
-        step); the cycle graph is used when k0 is a multiple of the (input, workspace, slot) period"""
+        step); the cycle graph is used when k0 is a multiple of the (input, workspace, slot) period.  Cross-stream dependencies
+        are issued lazily: a cycle replay waits only for pipeline streams that received work since the last replay, and the
+        streams wait for the replay when they are next used -- a run made of whole cycles costs one wait + one graph launch per
+        cycle on the host (at 32-image shards the ~20 stream waits of the eager form delayed the launch by more than a step)."""
         k = k0
         if self.cycle is not None and k % self.n_graphs == 0:
             cur = torch.cuda.current_stream(self.device)
             while k0 + n_steps - k >= self.cycle_len:
                 self._main.wait_stream(cur)
-                for s in self.streams:
-                    self._main.wait_stream(s)
-                if self.peer is not None:
+                for i, st in enumerate(self.streams):
+                    if self._dirty[i]:
+                        self._main.wait_stream(st)
+                        self._dirty[i] = False
+                if self.peer is not None and self._side_dirty:
                     self._main.wait_stream(self.side)
+                    self._side_dirty = False
                 with torch.cuda.stream(self._main):
                     self.cycle.replay()
-                for s in self.streams:                      # later single steps (and the next cycle) follow the cycle
-                    s.wait_stream(self._main)
+                self._cycle_pending = [True] * self.depth     # later single steps follow the cycle (wait issued at their first use)
                 if self.peer is not None:
-                    self.side.wait_stream(self._main)
+                    self._side_cycle_pending = True
                     self._used = [True] * self.n_slots
                 k += self.cycle_len
         while k < k0 + n_steps:
@@ -389,14 +396,25 @@ class PostprocessPipeline:
             k += 1
 
     def fork(self):
-        """the pipeline streams wait for the work queued so far on the current stream"""
+        """the pipeline streams wait for the work queued so far on the current stream (the wait itself is issued when a stream is
+        next used; a cycle replay orders itself after the current stream anyway)"""
         self._ev.record()
-        for s in self.streams:
-            s.wait_event(self._ev)
+        self._fork_pending = [True] * self.depth
+
+    def _use_stream(self, i):
+        st = self.streams[i]
+        if self._fork_pending[i]:
+            st.wait_event(self._ev)
+            self._fork_pending[i] = False
+        if self._cycle_pending[i]:
+            st.wait_stream(self._main)
+            self._cycle_pending[i] = False
+        self._dirty[i] = True
+        return st
 
     def step(self, k):
         g = k % self.n_graphs
-        s = self.streams[g % self.depth]
+        s = self._use_stream(g % self.depth)
         with torch.cuda.stream(s):
             if self.peer is not None:
                 slot = g % self.n_slots
@@ -404,6 +422,10 @@ class PostprocessPipeline:
                     s.wait_event(self._gathered[slot])      # the slot's previous contents have been gathered everywhere
                 self.replays[g]()
                 self._stepped[slot].record(s)
+                if self._side_cycle_pending:
+                    self.side.wait_stream(self._main)
+                    self._side_cycle_pending = False
+                self._side_dirty = True
                 with torch.cuda.stream(self.side):           # completion barrier off the compute streams
                     self.side.wait_event(self._stepped[slot])
                     self.peer.barrier(channel=slot)
@@ -417,7 +439,8 @@ class PostprocessPipeline:
         return self.outs[k % self.n_graphs]
 
     def stream_of(self, k):
-        return self.streams[(k % self.n_graphs) % self.depth]
+        """the stream step k runs on, ordered after the last fork() / cycle replay -- for the caller's own copies around the step"""
+        return self._use_stream((k % self.n_graphs) % self.depth)
 
     def join(self):
         """the current stream waits for every pipeline stream"""
