@@ -43,7 +43,7 @@ def bind_to_gpu_numa(device_index):
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
         allowed = os.sched_getaffinity(0) & cpus
-        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+        if len(allowed) >= 4 and len(allowed) < len(os.sched_getaffinity(0)):   # (never squeeze a rank onto a handful of CPUs)
             os.sched_setaffinity(0, allowed)
             return f"nvml:{min(allowed)}-{max(allowed)}"
     except Exception:  # noqa: BLE001
