@@ -600,9 +600,11 @@ __global__ void __launch_bounds__(256, 4) yolo_decode_filter_kernel(const __grid
     yolo_decode_item<VEC, T>(p, item, threadIdx.x & 31, cand_box, cand_score, cand_cls, cand_anchor, cand_count);
 }
 
-// packed-survivor variant (evaluation thresholds / small heads), see yolo_decode_item_packed
+// packed-survivor variant (evaluation thresholds / small heads), see yolo_decode_item_packed.  80 registers, 3 CTAs per SM: this
+// variant is bound by issue slots and load latency, not by warps in flight, and at 64 registers it spilled inside the plane loop
+// (cfg4: 211 -> 192 us one step at a time, 133 -> 122 us pipelined)
 template <bool VEC, typename T = float>
-__global__ void __launch_bounds__(256, 4) yolo_decode_filter_packed_kernel(const __grid_constant__ YoloParams p,
+__global__ void __launch_bounds__(256, 3) yolo_decode_filter_packed_kernel(const __grid_constant__ YoloParams p,
                                                                         float4* __restrict__ cand_box,
                                                                         float* __restrict__ cand_score,
                                                                         int* __restrict__ cand_cls,
